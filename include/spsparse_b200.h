@@ -1,0 +1,143 @@
+/*
+ * spsparse_b200.h -- C ABI of the B200-native spsparse hot path (libspsparse_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The reference
+ * (citibeth/spsparse) is a header-only C++ template library with no FFI of its own, so each entry
+ * point below names the reference routine it replaces (paths relative to the reference tree);
+ * the C++ template layer in include/spsparse/ (same names and argument order as the reference)
+ * is a thin host wrapper over these calls -- see INTEGRATION.md.
+ *
+ * Types: IndexT = int32 (non-negative), ValT = double, rank 1 or 2 -- the instantiation used by
+ * every reference test (tests/test_multiply_sparse.cpp:90-97, tests/test_array.cpp:68).
+ *
+ * Conventions
+ *  - every function returns 0 (SPB_OK) or an SPB_ERR_* code; spb_last_error() gives the text
+ *    (thread-local).  Nothing throws across the ABI.  There is NO CPU fallback: a missing or
+ *    failing GPU is an error.
+ *  - calls are synchronous for the caller unless noted; one CUDA stream per context.
+ *  - `spb_coo` handles own device memory unless created by spb_coo_wrap_device; free them with
+ *    spb_coo_free.  No function keeps a host pointer after it returns.
+ */
+#ifndef SPSPARSE_B200_H
+#define SPSPARSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spb_ctx spb_ctx; /* device + stream + workspace pool */
+typedef struct spb_coo spb_coo; /* device-resident COO array (struct-of-arrays, like
+                                   VectorCooArray::index_vecs/val_vec, VectorCooArray.hpp:22-23) */
+
+enum {
+    SPB_OK = 0,
+    SPB_ERR_CUDA = 1,       /* CUDA runtime failure (message has the CUDA error string) */
+    SPB_ERR_ARG = 2,        /* bad argument (null pointer, rank, index out of bounds, ...) */
+    SPB_ERR_INNER_DIM = 3,  /* multiply: inner dimensions differ (multiply_sparse.hpp:172-174) */
+    SPB_ERR_NOT_SORTED = 4, /* dim_beginnings on an unsorted array (algorithm.hpp:82-84) */
+    SPB_ERR_TOO_LARGE = 5   /* more than 2^30 entries in one sort (reference cap: 2^31, algorithm.hpp:419) */
+};
+
+/* DuplicatePolicy, same order as spsparse.hpp:25-26 */
+enum { SPB_LEAVE_ALONE = 0, SPB_ADD = 1, SPB_REPLACE = 2 };
+
+const char *spb_last_error(void);
+int spb_version(void);
+
+/* ---- context --------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out);
+int spb_ctx_destroy(spb_ctx *ctx);
+int spb_ctx_sync(spb_ctx *ctx);
+int spb_ctx_device(const spb_ctx *ctx, int *device, void **cuda_stream);
+
+/* ---- COO arrays  (VectorCooArray, VectorCooArray.hpp:8-158) ---------------------------- */
+/* sort_order: NULL or {-1,..} = unsorted/edit mode; else the order the data is ALREADY sorted
+ * and consolidated in (what VectorCooArray::sort_order records, VectorCooArray.hpp:33-34,131-135). */
+int spb_coo_upload(spb_ctx *ctx, int rank, const uint64_t *shape, const int32_t *const *idx,
+                   const double *val, uint64_t n, const int *sort_order, spb_coo **out);
+/* Wraps caller-owned device arrays without copying (used for NCCL-gathered operands). */
+int spb_coo_wrap_device(spb_ctx *ctx, int rank, const uint64_t *shape, int32_t *const *d_idx,
+                        double *d_val, uint64_t n, const int *sort_order, spb_coo **out);
+/* Uninitialised device storage for n entries (filled by the generators below or by the caller). */
+int spb_coo_alloc(spb_ctx *ctx, int rank, const uint64_t *shape, uint64_t n, spb_coo **out);
+int spb_coo_info(const spb_coo *a, int *rank, uint64_t *shape /*[rank]*/, uint64_t *n,
+                 int *sort_order /*[rank]*/);
+int spb_coo_device_ptrs(const spb_coo *a, int32_t **d_idx /*[rank]*/, double **d_val);
+int spb_coo_set_sorted(spb_coo *a, const int *sort_order); /* VectorCooArray::set_sorted :131-135 */
+int spb_coo_download(spb_ctx *ctx, const spb_coo *a, int32_t *const *idx, double *val);
+int spb_coo_free(spb_ctx *ctx, spb_coo *a);
+
+/* ---- consolidate  (spsparse::consolidate, algorithm.hpp:251-319; sorted_permutation :411-427;
+ *      the in-place form VectorCooArray::consolidate, VectorCooArray.hpp:299-311) -------------
+ * Stable sort by (idx[sort_order[0]], idx[sort_order[1]]), zero inputs dropped, NaN inputs dropped
+ * only in the leading run when zero_nan, duplicates merged by `policy`; index columns keep the
+ * array's own dimension order.  `out` is a new array flagged sorted by sort_order. */
+typedef struct {
+    uint64_t n_in, n_kept, n_out; /* entries in, after the input-zero drop, after merging */
+    int key_bits, passes;         /* significant key bits, 8-bit radix passes run */
+    float ms_total, ms_sort, ms_reduce;
+} spb_consolidate_stats;
+int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int policy, int zero_nan,
+                    spb_coo **out, spb_consolidate_stats *stats /* may be NULL */);
+
+/* ---- dim_beginnings  (spsparse::dim_beginnings, algorithm.hpp:74-118) -------------------
+ * Offsets of the first entry of every non-empty value of dimension sort_order[0], plus the
+ * sentinel n.  Writes min(count, cap) offsets to host memory, returns the full count. */
+int spb_dim_beginnings(spb_ctx *ctx, const spb_coo *sorted, uint64_t *out, uint64_t cap, uint64_t *count);
+
+/* ---- multiply, matrix*matrix  (spsparse::multiply, multiply_sparse.hpp:152-248) ---------
+ * out = C * diag(si) * op(A) * diag(sj) * op(B) * diag(sk); scale vectors may be NULL; they are
+ * used as stored (ascending, non-repeating).  A and B are consolidated internally unless already
+ * flagged sorted in the order the reference needs (Consolidate<>, algorithm.hpp:354-369).
+ * The result is row-major sorted, unique, exact-zero sums dropped, and -- like the reference's --
+ * left flagged unsorted / in edit mode. */
+typedef struct {
+    uint64_t products;       /* F: intermediate products a*b formed */
+    uint64_t nnz_a, nnz_b;   /* after consolidation */
+    uint64_t rows_a;         /* non-empty rows of op(A) */
+    uint64_t rows_merge;     /* rows done by the register k-way-merge kernels */
+    uint64_t rows_esc;       /* rows done by expand-sort-compress */
+    uint64_t products_esc;
+    uint64_t nnz_c;
+    float ms_prepare;        /* consolidations of A and B, CSR build, scale densify */
+    float ms_symbolic, ms_numeric, ms_total;
+} spb_mm_stats;
+int spb_multiply_mm(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,
+                    const spb_coo *scalej, const spb_coo *B, char transpose_B, const spb_coo *scalek,
+                    int policy, int zero_nan, spb_coo **out, spb_mm_stats *stats /* may be NULL */);
+
+/* Operands prepared once, multiply many times (what bench.py times as "SpGEMM only").
+ * A must be consolidated with sort_order {a_row_dim, 1-a_row_dim}; B with {b_inner_dim, 1-b_inner_dim}
+ * (i.e. sorted by the inner index first).  Same arithmetic and output as spb_multiply_mm. */
+int spb_multiply_mm_prepared(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A,
+                             int a_row_dim, const spb_coo *scalej, const spb_coo *B, int b_inner_dim,
+                             const spb_coo *scalek, spb_coo **out, spb_mm_stats *stats);
+
+/* ---- multiply, matrix*vector  (spsparse::multiply, multiply_sparse.hpp:281-365) -------- */
+int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,
+                    const spb_coo *scalej, const spb_coo *V, int policy, int zero_nan, spb_coo **out);
+
+/* ---- synthetic inputs, generated on the device (the same arithmetic as
+ *      oracle/spsparse_oracle.c:orc_gen_* and spsparse_b200/gen.py) --------------------------- */
+/* config 2 family: n entries [i0, i0+n) over `ubase` distinct draws in a 2^bits x 2^bits shape. */
+int spb_gen_dup_coo(spb_ctx *ctx, uint64_t seed, uint64_t i0, uint64_t n, uint64_t ubase, int bits,
+                    uint64_t zero_every, spb_coo **out);
+/* config 5 family: rows [r0, r1) of an m x m pentadiagonal matrix, 5 entries per row inserted in a
+ * scrambled order; out-of-range diagonals are emitted as explicit 0.0 entries on the clamped column. */
+int spb_gen_banded(spb_ctx *ctx, uint64_t seed, uint64_t m, uint64_t r0, uint64_t r1, spb_coo **out);
+/* config 3 family: (ny*nx) x (gy*gx) bilinear-overlap matrix, 4 entries per row, scrambled. */
+int spb_gen_regrid(spb_ctx *ctx, uint64_t seed, uint32_t ny, uint32_t nx, uint32_t gy, uint32_t gx,
+                   spb_coo **out);
+/* config 4 family: R-MAT, 2^scale rows/cols, nedges raw edges (duplicates kept). */
+int spb_gen_rmat(spb_ctx *ctx, uint64_t seed, int scale, uint64_t nedges, spb_coo **out);
+/* dense-support sparse vector: indices 0..dim-1 ascending, value 0.5+u01(seed+j), flagged sorted. */
+int spb_gen_vector(spb_ctx *ctx, uint64_t seed, uint64_t dim, spb_coo **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPSPARSE_B200_H */

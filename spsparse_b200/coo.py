@@ -1,0 +1,208 @@
+"""Host-side Python mirror of the reference's interface for the hot path, over the C ABI.
+
+Names follow the reference (slib/spsparse): ``CooArray`` plays ``VectorCooArray``
+(VectorCooArray.hpp:8-158) with device-resident storage; ``consolidate`` / ``multiply`` take the
+same arguments in the same order as algorithm.hpp:251-256 and multiply_sparse.hpp:152-164 /
+281-291.  The C++ template layer in include/spsparse/ is the drop-in for C++ callers; this module
+is what tests/ and bench.py drive.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ConsolidateStats, MMStats, check, vp
+
+LEAVE_ALONE, ADD, REPLACE = 0, 1, 2  # DuplicatePolicy, spsparse.hpp:25-26
+ROW_MAJOR, COL_MAJOR = (0, 1), (1, 0)  # spsparse.cpp:30-31
+
+ERR_INNER_DIM, ERR_NOT_SORTED = 3, 4
+
+
+class Context:
+    """One GPU + one CUDA stream (pass torch's ``stream.cuda_stream`` to share it)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load()
+        h = vp()
+        check(self.lib.spb_ctx_create(device, vp(stream) if stream else None, C.byref(h)))
+        self.h, self.device = h, device
+
+    def sync(self):
+        check(self.lib.spb_ctx_sync(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.spb_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def _order(so):
+    if so is None:
+        return None
+    so = list(so) + [0]
+    return (C.c_int * 2)(so[0], so[1])
+
+
+class CooArray:
+    """Device-resident COO array (int32 indices, fp64 values, rank 1 or 2)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_host(cls, ctx, shape, idx, val, sort_order=None):
+        shape = [int(s) for s in shape]
+        rank = len(shape)
+        idx = [np.ascontiguousarray(a, dtype=np.int32) for a in idx]
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        n = int(val.shape[0])
+        ptrs = (_lib.i32p * rank)(*[a.ctypes.data_as(_lib.i32p) for a in idx])
+        h = vp()
+        check(ctx.lib.spb_coo_upload(ctx.h, rank, (C.c_uint64 * rank)(*shape), ptrs, val.ctypes.data_as(_lib.f64p),
+                                     n, _order(sort_order), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap_device(cls, ctx, shape, idx_ptrs, val_ptr, n, sort_order=None):
+        shape = [int(s) for s in shape]
+        rank = len(shape)
+        ptrs = (vp * rank)(*[vp(int(p)) for p in idx_ptrs])
+        h = vp()
+        check(ctx.lib.spb_coo_wrap_device(ctx.h, rank, (C.c_uint64 * rank)(*shape), ptrs, vp(int(val_ptr)), int(n),
+                                          _order(sort_order), C.byref(h)))
+        return cls(ctx, h)
+
+    # -- accessors ----------------------------------------------------------------------------
+    def _info(self):
+        rank = C.c_int()
+        shape = (C.c_uint64 * 2)()
+        n = C.c_uint64()
+        so = (C.c_int * 2)()
+        check(self.ctx.lib.spb_coo_info(self.h, C.byref(rank), shape, C.byref(n), so))
+        r = rank.value
+        return r, tuple(int(shape[k]) for k in range(r)), int(n.value), tuple(int(so[k]) for k in range(r))
+
+    @property
+    def rank(self):
+        return self._info()[0]
+
+    @property
+    def shape(self):
+        return self._info()[1]
+
+    def size(self):
+        return self._info()[2]
+
+    @property
+    def sort_order(self):
+        so = self._info()[3]
+        return None if so[0] < 0 else so
+
+    def device_ptrs(self):
+        idx = (vp * 2)()
+        val = vp()
+        check(self.ctx.lib.spb_coo_device_ptrs(self.h, idx, C.byref(val)))
+        return [idx[k] for k in range(self.rank)], val.value
+
+    def to_host(self):
+        rank, shape, n, _ = self._info()
+        idx = [np.empty(n, dtype=np.int32) for _ in range(rank)]
+        val = np.empty(n, dtype=np.float64)
+        ptrs = (_lib.i32p * rank)(*[a.ctypes.data_as(_lib.i32p) for a in idx])
+        check(self.ctx.lib.spb_coo_download(self.ctx.h, self.h, ptrs, val.ctypes.data_as(_lib.f64p)))
+        return idx, val
+
+    def dim_beginnings(self):
+        """spsparse::dim_beginnings (algorithm.hpp:74-118)."""
+        cnt = C.c_uint64()
+        cap = self.size() + 1
+        out = np.empty(cap, dtype=np.uint64)
+        check(self.ctx.lib.spb_dim_beginnings(self.ctx.h, self.h, out.ctypes.data_as(_lib.u64p), cap, C.byref(cnt)))
+        return out[:cnt.value].astype(np.int64)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.spb_coo_free(self.ctx.h, self.h)
+            self.h = None
+
+
+def consolidate(ctx: Context, A: CooArray, sort_order, duplicate_policy=ADD, zero_nan=False, stats=False):
+    """spsparse::consolidate (algorithm.hpp:251-319): returns the new, sorted array."""
+    h = vp()
+    st = ConsolidateStats()
+    check(ctx.lib.spb_consolidate(ctx.h, A.h, _order(sort_order), int(duplicate_policy), int(bool(zero_nan)),
+                                  C.byref(h), C.byref(st)))
+    out = CooArray(ctx, h)
+    return (out, st) if stats else out
+
+
+def _h(x):
+    return x.h if x is not None else None
+
+
+def multiply(ctx: Context, Cst, scalei, A, transpose_A, scalej, B, transpose_B=None, scalek=None,
+             duplicate_policy=ADD, zero_nan=False, stats=False):
+    """spsparse::multiply.  With a rank-2 ``B`` this is the matrix*matrix form
+    (multiply_sparse.hpp:152-248); with a rank-1 ``B`` (then ``transpose_B``/``scalek`` must be
+    omitted) it is the matrix*vector form (multiply_sparse.hpp:281-365)."""
+    h = vp()
+    if B.rank == 1:
+        check(ctx.lib.spb_multiply_mv(ctx.h, float(Cst), _h(scalei), A.h, transpose_A.encode(), _h(scalej), B.h,
+                                      int(duplicate_policy), int(bool(zero_nan)), C.byref(h)))
+        return CooArray(ctx, h)
+    st = MMStats()
+    check(ctx.lib.spb_multiply_mm(ctx.h, float(Cst), _h(scalei), A.h, transpose_A.encode(), _h(scalej), B.h,
+                                  transpose_B.encode(), _h(scalek), int(duplicate_policy), int(bool(zero_nan)),
+                                  C.byref(h), C.byref(st)))
+    out = CooArray(ctx, h)
+    return (out, st) if stats else out
+
+
+def multiply_prepared(ctx: Context, Cst, scalei, A, a_row_dim, scalej, B, b_inner_dim, scalek):
+    """SpGEMM on operands consolidated beforehand (A by (row, inner), B by (inner, col))."""
+    h = vp()
+    st = MMStats()
+    check(ctx.lib.spb_multiply_mm_prepared(ctx.h, float(Cst), _h(scalei), A.h, int(a_row_dim), _h(scalej), B.h,
+                                           int(b_inner_dim), _h(scalek), C.byref(h), C.byref(st)))
+    return CooArray(ctx, h), st
+
+
+# ---- synthetic inputs on the device ------------------------------------
+def gen_dup_coo(ctx, seed, i0, n, ubase, bits, zero_every=0):
+    h = vp()
+    check(ctx.lib.spb_gen_dup_coo(ctx.h, seed, i0, n, ubase, bits, zero_every, C.byref(h)))
+    return CooArray(ctx, h)
+
+
+def gen_banded(ctx, seed, m, r0, r1):
+    h = vp()
+    check(ctx.lib.spb_gen_banded(ctx.h, seed, m, r0, r1, C.byref(h)))
+    return CooArray(ctx, h)
+
+
+def gen_regrid(ctx, seed, ny, nx, gy, gx):
+    h = vp()
+    check(ctx.lib.spb_gen_regrid(ctx.h, seed, ny, nx, gy, gx, C.byref(h)))
+    return CooArray(ctx, h)
+
+
+def gen_rmat(ctx, seed, scale, nedges):
+    h = vp()
+    check(ctx.lib.spb_gen_rmat(ctx.h, seed, scale, nedges, C.byref(h)))
+    return CooArray(ctx, h)
+
+
+def gen_vector(ctx, seed, dim):
+    h = vp()
+    check(ctx.lib.spb_gen_vector(ctx.h, seed, dim, C.byref(h)))
+    return CooArray(ctx, h)

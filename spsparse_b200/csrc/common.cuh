@@ -1,0 +1,106 @@
+// common.cuh -- shared device/host helpers for libspsparse_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+typedef int64_t i64;
+typedef unsigned long long ull;
+
+#define SPB_FULL_MASK 0xffffffffu
+
+// ---- error plumbing ------------------------------------------------------------------------
+extern thread_local std::string g_last_error;
+int spb_fail(int code, const char *fmt, ...);
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return spb_fail(1, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                            cudaGetErrorString(e__));                                         \
+    } while (0)
+
+#define CKR(expr)                  \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// ---- small device utilities ------------------------------------------------------------------
+__host__ __device__ __forceinline__ int bits_for(u64 extent) {
+    // bits needed to represent 0..extent-1
+    if (extent <= 1) return 0;
+    u64 x = extent - 1;
+    int b = 0;
+    while (x) { ++b; x >>= 1; }
+    return b;
+}
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ u32 lanemask_lt() {
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// streaming (read-once) loads: keep them out of L1 so that reusable data stays there
+__device__ __forceinline__ u64 ld_stream_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ i32 ld_stream_i32(const i32 *p) {
+    i32 v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// decoupled look-back status words (flag in the top two bits)
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(u32 *p, u32 v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// warp-level inclusive scan
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(SPB_FULL_MASK, v, o);
+        if (lane_id() >= (u32)o) v += t;
+    }
+    return v;
+}
+
+// splitmix64 finaliser; SURVEY.md Appendix C.  Must match oracle/spsparse_oracle.c:mix64.
+__host__ __device__ __forceinline__ u64 mix64(u64 x) {
+    u64 z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ double u01(u64 x) { return (double)(mix64(x) >> 11) * 0x1.0p-53; }
+
+static inline u64 div_up(u64 a, u64 b) { return (a + b - 1) / b; }

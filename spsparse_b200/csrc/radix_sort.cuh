@@ -1,0 +1,307 @@
+// radix_sort.cuh -- stable LSD radix sort of packed (hi,lo) index keys with an fp64 payload.
+//
+// Replaces sorted_permutation + CmpIndex + std::stable_sort (reference slib/spsparse/
+// algorithm.hpp:375-427).  One-sweep organisation: a single histogram kernel counts every 8-bit
+// digit of every pass up front; each pass then reads its input once and writes it once, ranking
+// items inside a 4096-entry tile with warp-level match/ballot multi-split and chaining the tiles'
+// per-digit counts with a decoupled look-back.  Pass 0 reads the caller's struct-of-arrays COO
+// directly, packs (hi << bits_lo) | lo on the fly and applies consolidate()'s input drop rule
+// (algorithm.hpp:272-275, 284-292), so filtered entries never enter the sort.
+#pragma once
+#include "common.cuh"
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_IPT = 16;
+constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 entries per tile
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_RADIX_BITS = 8;
+constexpr int RS_RADIX = 1 << RS_RADIX_BITS;
+constexpr int RS_NB = RS_RADIX + 1;  // +1: bucket of filtered / out-of-range items (never written)
+constexpr int RS_MAX_PASSES = 8;
+constexpr size_t RS_SMEM_BYTES =
+    (size_t)RS_TILE * 16 + (size_t)RS_WARPS * RS_NB * sizeof(u32) + 64;
+
+// Look-back word of the sort: [31:30] flag, [29:0] count  => at most 2^30 entries per sort.
+#define RS_FLAG_AGG (1u << 30)
+#define RS_FLAG_INCL (2u << 30)
+#define RS_VALUE(w) ((w) & ((1u << 30) - 1))
+
+// Where pass 0 reads from, and which inputs it drops.
+struct SortInput {
+    const i32 *hi;      // index vector of the leading sort dimension
+    const i32 *lo;      // second sort dimension, or nullptr (rank 1)
+    const double *val;
+    u32 n;
+    int bits_lo;        // key = (hi << bits_lo) | lo
+    u32 extent_hi, extent_lo;  // bounds check (VectorCooArray::add, VectorCooArray.hpp:245-262)
+    int drop_zero;      // drop val == 0 inputs (always, for consolidate)
+    int drop_nan;       // zero_nan: drop NaN inputs that precede the first kept entry of the
+                        // REFERENCE's sorted sequence (the "leading run", algorithm.hpp:272-275)
+    const i32 *ref_hi;  // key in the reference's sort order (may differ from ours when multiply
+    const i32 *ref_lo;  // needs B bucketed by its inner index)
+    int ref_bits_lo;
+    const u64 *first_kept;  // [0] smallest reference key among non-none inputs, [1] its smallest position
+};
+
+__device__ __forceinline__ u64 pack_key(i32 hi, i32 lo, int bits_lo) {
+    return ((u64)(u32)hi << bits_lo) | (u64)(u32)lo;
+}
+
+__device__ __forceinline__ bool input_kept(const SortInput &in, u32 i, double v) {
+    if (in.drop_zero && v == 0.0) return false;
+    if (in.drop_nan && isnan(v)) {
+        u64 rk = pack_key(in.ref_hi[i], in.ref_lo ? in.ref_lo[i] : 0, in.ref_bits_lo);
+        u64 kmin = in.first_kept[0];
+        if (rk < kmin || (rk == kmin && (u64)i < in.first_kept[1])) return false;
+    }
+    return true;
+}
+
+// ---- zero_nan support: locate the first kept entry of the reference's sorted sequence ---------
+__global__ void k_first_kept_key(SortInput in, u64 *first_kept) {
+    u64 best = ~0ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += (u64)gridDim.x * blockDim.x) {
+        double v = in.val[i];
+        if (v == 0.0 || isnan(v)) continue;
+        u64 rk = pack_key(in.ref_hi[i], in.ref_lo ? in.ref_lo[i] : 0, in.ref_bits_lo);
+        best = rk < best ? rk : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 t = __shfl_xor_sync(SPB_FULL_MASK, best, o);
+        best = t < best ? t : best;
+    }
+    if (lane_id() == 0 && best != ~0ull) atomicMin((ull *)&first_kept[0], (ull)best);
+}
+__global__ void k_first_kept_pos(SortInput in, u64 *first_kept) {
+    const u64 kmin = first_kept[0];
+    u64 best = ~0ull;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += (u64)gridDim.x * blockDim.x) {
+        double v = in.val[i];
+        if (v == 0.0 || isnan(v)) continue;
+        u64 rk = pack_key(in.ref_hi[i], in.ref_lo ? in.ref_lo[i] : 0, in.ref_bits_lo);
+        if (rk == kmin) best = i < best ? i : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 t = __shfl_xor_sync(SPB_FULL_MASK, best, o);
+        best = t < best ? t : best;
+    }
+    if (lane_id() == 0 && best != ~0ull) atomicMin((ull *)&first_kept[1], (ull)best);
+}
+
+// ---- histogram of every digit of every pass (one read of the index vectors + values) -----------
+// counters[0] = kept entries, counters[1] = 1 if an index was out of bounds.
+__global__ void __launch_bounds__(512) k_sort_hist(SortInput in, int passes, u32 *hist, u32 *counters) {
+    __shared__ u32 s_h[RS_MAX_PASSES * RS_RADIX];
+    for (int t = threadIdx.x; t < passes * RS_RADIX; t += blockDim.x) s_h[t] = 0;
+    __syncthreads();
+    u32 kept = 0, oob = 0;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += stride) {
+        i32 hi = ld_stream_i32(in.hi + i);
+        i32 lo = in.lo ? ld_stream_i32(in.lo + i) : 0;
+        double v = ld_stream_f64(in.val + i);
+        if ((u32)hi >= in.extent_hi || (u32)lo >= in.extent_lo) { oob = 1; continue; }
+        if (!input_kept(in, (u32)i, v)) continue;
+        ++kept;
+        u64 key = pack_key(hi, lo, in.bits_lo);
+        for (int p = 0; p < passes; ++p) {
+            atomicAdd(&s_h[p * RS_RADIX + (u32)(key & (RS_RADIX - 1))], 1u);
+            key >>= RS_RADIX_BITS;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < passes * RS_RADIX; t += blockDim.x)
+        if (s_h[t]) atomicAdd(&hist[t], s_h[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(SPB_FULL_MASK, kept, o);
+    if (lane_id() == 0 && kept) atomicAdd(&counters[0], kept);
+    if (oob) counters[1] = 1;
+}
+
+// histogram of already packed keys (expand-sort-compress path)
+__global__ void __launch_bounds__(512) k_keys_hist(const u64 *__restrict__ keys, u64 n, int passes, u32 *hist) {
+    __shared__ u32 s_h[RS_MAX_PASSES * RS_RADIX];
+    for (int t = threadIdx.x; t < passes * RS_RADIX; t += blockDim.x) s_h[t] = 0;
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 key = ld_stream_u64(keys + i);
+        for (int p = 0; p < passes; ++p) {
+            atomicAdd(&s_h[p * RS_RADIX + (u32)(key & (RS_RADIX - 1))], 1u);
+            key >>= RS_RADIX_BITS;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < passes * RS_RADIX; t += blockDim.x)
+        if (s_h[t]) atomicAdd(&hist[t], s_h[t]);
+}
+
+// exclusive scan of each pass's 256 counts -> first output slot of each digit (in place)
+__global__ void __launch_bounds__(RS_RADIX) k_bucket_starts(u32 *hist) {
+    __shared__ u32 s_w[RS_RADIX / 32];
+    u32 *h = hist + blockIdx.x * RS_RADIX;
+    u32 c = h[threadIdx.x];
+    u32 incl = warp_incl_scan(c);
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 add = 0;
+    for (u32 w = 0; w < (threadIdx.x >> 5); ++w) add += s_w[w];
+    h[threadIdx.x] = add + incl - c;
+}
+
+struct PassArgs {
+    const u64 *keys_in;      // passes >= 1
+    const double *vals_in;
+    u64 *keys_out;
+    double *vals_out;
+    const u32 *n_ptr;        // device-resident entry count for passes >= 1 (n_kept)
+    const u32 *bucket_start; // [256], this pass
+    u32 *lookback;           // [tiles][256], zeroed
+    u32 *ticket;             // zeroed
+    int shift;               // digit = (key >> shift) & 255
+};
+
+template <bool PASS0>
+__global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortInput in) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);
+    double *s_vals = reinterpret_cast<double *>(s_keys + RS_TILE);
+    u32 *s_wcnt = reinterpret_cast<u32 *>(s_vals + RS_TILE);  // [RS_WARPS][RS_NB]; later: global bases
+    u32 *s_misc = s_wcnt + RS_WARPS * RS_NB;                 // [0] tile, [1..8] warp sums
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_misc[0] = atomicAdd(a.ticket, 1u);
+    for (int t = tid; t < RS_WARPS * RS_NB; t += RS_THREADS) s_wcnt[t] = 0;
+    __syncthreads();
+    const u32 tile = s_misc[0];
+    const u32 n = PASS0 ? in.n : *a.n_ptr;
+    const u64 tile_base = (u64)tile * RS_TILE;
+    if (tile_base >= n) return;
+
+    // ---- load (warp-striped: item order inside the tile is (warp, k, lane)) ------------------
+    const u64 wbase = tile_base + (u64)warp * (32 * RS_IPT) + lane;
+    u64 key[RS_IPT];
+    double val[PASS0 ? RS_IPT : 1];
+    u32 valid_bits = 0;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        u64 i = wbase + (u64)k * 32;
+        bool ok = i < n;
+        if (PASS0) {
+            i32 hi = 0, lo = 0;
+            double v = 0.0;
+            if (ok) {
+                hi = ld_stream_i32(in.hi + i);
+                lo = in.lo ? ld_stream_i32(in.lo + i) : 0;
+                v = ld_stream_f64(in.val + i);
+                ok = ((u32)hi < in.extent_hi) && ((u32)lo < in.extent_lo) && input_kept(in, (u32)i, v);
+            }
+            key[k] = pack_key(hi, lo, in.bits_lo);
+            val[k] = v;
+        } else {
+            key[k] = ok ? ld_stream_u64(a.keys_in + i) : 0;
+        }
+        valid_bits |= (ok ? 1u : 0u) << k;
+    }
+
+    // ---- rank inside the warp: match-any multi-split, warp-private digit counters ------------
+    u32 *mycnt = s_wcnt + warp * RS_NB;
+    const u32 lt = lanemask_lt();
+    unsigned short pos[RS_IPT];
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        u32 d = ((valid_bits >> k) & 1u) ? (u32)((key[k] >> a.shift) & (RS_RADIX - 1)) : (u32)RS_RADIX;
+        u32 peers = __match_any_sync(SPB_FULL_MASK, d);
+        u32 leader = __ffs(peers) - 1;
+        u32 before = 0;
+        if (lane == leader) {
+            before = mycnt[d];
+            mycnt[d] = before + __popc(peers);
+        }
+        before = __shfl_sync(SPB_FULL_MASK, before, leader);
+        pos[k] = (unsigned short)(before + __popc(peers & lt));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit (thread d): offsets of each warp, tile total, start inside the tile --------
+    u32 total = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) total += s_wcnt[w * RS_NB + tid];
+    // publish this tile's count of digit `tid` as early as possible
+    u32 *lb = a.lookback + (u64)tile * RS_RADIX + tid;
+    st_relaxed_u32(lb, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | total);
+    u32 incl = warp_incl_scan(total);
+    if (lane == 31) s_misc[1 + warp] = incl;
+    __syncthreads();
+    u32 lstart = incl - total;
+    for (u32 w = 0; w < warp; ++w) lstart += s_misc[1 + w];
+    const u32 nvalid_if_last = lstart + total;  // meaningful for tid == 255
+    {
+        u32 run = lstart;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            u32 c = s_wcnt[w * RS_NB + tid];
+            s_wcnt[w * RS_NB + tid] = run;
+            run += c;
+        }
+    }
+    if (tid == RS_RADIX - 1) s_misc[12] = nvalid_if_last;
+    __syncthreads();
+    const u32 nvalid = s_misc[12];
+
+    // ---- stage keys (and values) in digit order in shared memory ------------------------------
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        if ((valid_bits >> k) & 1u) {
+            u32 d = (u32)((key[k] >> a.shift) & (RS_RADIX - 1));
+            u32 p = mycnt[d] + pos[k];
+            pos[k] = (unsigned short)p;
+            s_keys[p] = key[k];
+            if (PASS0) s_vals[p] = val[k];
+        }
+    }
+    if (!PASS0) {
+        double v[RS_IPT];
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            u64 i = wbase + (u64)k * 32;
+            v[k] = ((valid_bits >> k) & 1u) ? ld_stream_f64(a.vals_in + i) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k)
+            if ((valid_bits >> k) & 1u) s_vals[pos[k]] = v[k];
+    }
+
+    // ---- decoupled look-back, one digit per thread ----------------------------------------------
+    u32 excl = 0;
+    if (tile > 0) {
+        const u32 *p = lb - RS_RADIX;
+        for (;;) {
+            u32 w;
+            do { w = ld_relaxed_u32(p); } while ((w >> 30) == 0);
+            excl += RS_VALUE(w);
+            if ((w >> 30) == 2) break;
+            p -= RS_RADIX;
+        }
+        st_relaxed_u32(lb, RS_FLAG_INCL | (excl + total));
+    }
+    const u32 gbase = a.bucket_start[tid] + excl - lstart;  // global slot = gbase + position in tile
+    __syncthreads();  // all staging done, s_wcnt free
+    s_wcnt[tid] = gbase;
+    __syncthreads();
+
+    // ---- write out: consecutive threads -> consecutive staged items -> runs of consecutive slots -
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        u32 p = (u32)k * RS_THREADS + tid;
+        if (p < nvalid) {
+            u64 kk = s_keys[p];
+            u32 dst = s_wcnt[(u32)((kk >> a.shift) & (RS_RADIX - 1))] + p;
+            a.keys_out[dst] = kk;
+            a.vals_out[dst] = s_vals[p];
+        }
+    }
+}

@@ -1,0 +1,955 @@
+// spb_api.cu -- implementation of the C ABI declared in include/spsparse_b200.h.
+// Host orchestration only; every data-path step is one of the hand-written kernels in
+// radix_sort.cuh / reduce_by_key.cuh / scan.cuh / csr.cuh / spgemm.cuh / gen.cuh.  No CUB, Thrust,
+// cuSPARSE or CPU fallback.
+#include "../../include/spsparse_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "csr.cuh"
+#include "gen.cuh"
+#include "radix_sort.cuh"
+#include "reduce_by_key.cuh"
+#include "scan.cuh"
+#include "spgemm.cuh"
+
+thread_local std::string g_last_error;
+
+int spb_fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+struct spb_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count;
+    u32 merge_max_products;  // bin threshold, env SPB_MERGE_MAX_PRODUCTS
+    u64 esc_chunk;           // products per expand-sort-compress chunk, env SPB_ESC_CHUNK
+};
+
+struct spb_coo {
+    int rank;
+    u64 shape[2];
+    u64 n;
+    i32 *idx[2];
+    double *val;
+    int sort_order[2];
+    bool owned;
+};
+
+// ---- stream-ordered scratch memory, released when the scope ends ---------------------------------
+struct Scratch {
+    spb_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit Scratch(spb_ctx *c) : ctx(c) {}
+    ~Scratch() { for (void *p : ptrs) cudaFreeAsync(p, ctx->stream); }
+    template <typename T>
+    int get(T **out, u64 count) {
+        void *p = nullptr;
+        size_t bytes = (size_t)(count ? count : 1) * sizeof(T);
+        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+        if (e != cudaSuccess) return spb_fail(SPB_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        ptrs.push_back(p);
+        *out = (T *)p;
+        return 0;
+    }
+    template <typename T>
+    int zeroed(T **out, u64 count) {
+        CKR(get(out, count));
+        CK(cudaMemsetAsync(*out, 0, (size_t)(count ? count : 1) * sizeof(T), ctx->stream));
+        return 0;
+    }
+    void release(void *p) {  // free early
+        for (size_t i = 0; i < ptrs.size(); ++i)
+            if (ptrs[i] == p) { cudaFreeAsync(p, ctx->stream); ptrs.erase(ptrs.begin() + i); return; }
+    }
+    void keep(void *p) {  // hand ownership to the caller
+        for (size_t i = 0; i < ptrs.size(); ++i)
+            if (ptrs[i] == p) { ptrs.erase(ptrs.begin() + i); return; }
+    }
+};
+
+struct Timer {  // CUDA events on the context stream
+    cudaStream_t s;
+    std::vector<cudaEvent_t> ev;
+    explicit Timer(cudaStream_t st) : s(st) {}
+    ~Timer() { for (auto e : ev) cudaEventDestroy(e); }
+    int mark() {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.push_back(e);
+        return (int)ev.size() - 1;
+    }
+    float ms(int a, int b) {
+        float t = 0;
+        cudaEventSynchronize(ev[b]);
+        cudaEventElapsedTime(&t, ev[a], ev[b]);
+        return t;
+    }
+};
+
+static inline u32 grid_for(u64 n, u32 threads, u32 cap) {
+    u64 g = div_up(n ? n : 1, threads);
+    return (u32)(g < cap ? g : cap);
+}
+
+// ==================================================================================================
+extern "C" {
+
+const char *spb_last_error(void) { return g_last_error.c_str(); }
+int spb_version(void) { return 100; }
+
+int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
+    if (!out) return spb_fail(SPB_ERR_ARG, "spb_ctx_create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return spb_fail(SPB_ERR_CUDA, "no CUDA device available (%s); spsparse_b200 has no CPU fallback",
+                        cudaGetErrorString(e));
+    if (device < 0 || device >= count) return spb_fail(SPB_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    CK(cudaSetDevice(device));
+    spb_ctx *c = new spb_ctx();
+    c->device = device;
+    c->own_stream = (cuda_stream == nullptr);
+    if (c->own_stream) CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    else c->stream = (cudaStream_t)cuda_stream;
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    // keep freed scratch in the pool: steady-state calls never reach cudaMalloc
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    u64 thresh = ~0ull;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    CK(cudaFuncSetAttribute(k_radix_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+    const char *s = getenv("SPB_MERGE_MAX_PRODUCTS");
+    c->merge_max_products = s ? (u32)strtoul(s, nullptr, 10) : 1024u;
+    s = getenv("SPB_ESC_CHUNK");
+    c->esc_chunk = s ? strtoull(s, nullptr, 10) : (1ull << 27);
+    if (c->esc_chunk < 1) c->esc_chunk = 1;
+    *out = c;
+    return SPB_OK;
+}
+
+int spb_ctx_destroy(spb_ctx *ctx) {
+    if (!ctx) return SPB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SPB_OK;
+}
+
+int spb_ctx_sync(spb_ctx *ctx) {
+    if (!ctx) return spb_fail(SPB_ERR_ARG, "null context");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+
+int spb_ctx_device(const spb_ctx *ctx, int *device, void **cuda_stream) {
+    if (!ctx) return spb_fail(SPB_ERR_ARG, "null context");
+    if (device) *device = ctx->device;
+    if (cuda_stream) *cuda_stream = (void *)ctx->stream;
+    return SPB_OK;
+}
+
+// ---- COO handles ---------------------------------------------------------------------------------
+static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocate, spb_coo **out) {
+    if (!ctx || !out || !shape) return spb_fail(SPB_ERR_ARG, "null argument");
+    if (rank != 1 && rank != 2) return spb_fail(SPB_ERR_ARG, "rank must be 1 or 2 (got %d)", rank);
+    for (int k = 0; k < rank; ++k)
+        if (shape[k] > (1ull << 31)) return spb_fail(SPB_ERR_ARG, "extent %llu exceeds the int32 index range", (ull)shape[k]);
+    if (n >= (1ull << 31)) return spb_fail(SPB_ERR_TOO_LARGE, "%llu entries: the reference's own cap is 2^31 (algorithm.hpp:419)", (ull)n);
+    spb_coo *a = new spb_coo();
+    a->rank = rank;
+    a->shape[0] = shape[0];
+    a->shape[1] = rank > 1 ? shape[1] : 1;
+    a->n = n;
+    a->idx[0] = a->idx[1] = nullptr;
+    a->val = nullptr;
+    a->sort_order[0] = -1;
+    a->sort_order[1] = 0;
+    a->owned = allocate;
+    if (allocate) {
+        CK(cudaSetDevice(ctx->device));
+        size_t cnt = n ? n : 1;
+        for (int k = 0; k < rank; ++k) CK(cudaMallocAsync((void **)&a->idx[k], cnt * sizeof(i32), ctx->stream));
+        CK(cudaMallocAsync((void **)&a->val, cnt * sizeof(double), ctx->stream));
+    }
+    *out = a;
+    return SPB_OK;
+}
+
+static void set_order(spb_coo *a, const int *so) {
+    a->sort_order[0] = -1;
+    a->sort_order[1] = 0;
+    if (so && so[0] >= 0) {
+        a->sort_order[0] = so[0];
+        a->sort_order[1] = a->rank > 1 ? so[1] : 0;
+    }
+}
+
+int spb_coo_alloc(spb_ctx *ctx, int rank, const uint64_t *shape, uint64_t n, spb_coo **out) {
+    return coo_new(ctx, rank, shape, n, true, out);
+}
+
+int spb_coo_upload(spb_ctx *ctx, int rank, const uint64_t *shape, const int32_t *const *idx, const double *val,
+                   uint64_t n, const int *sort_order, spb_coo **out) {
+    if (n && (!idx || !val)) return spb_fail(SPB_ERR_ARG, "null data pointer");
+    CKR(coo_new(ctx, rank, shape, n, true, out));
+    spb_coo *a = *out;
+    set_order(a, sort_order);
+    if (n) {
+        for (int k = 0; k < rank; ++k)
+            CK(cudaMemcpyAsync(a->idx[k], idx[k], n * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(a->val, val, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // host buffers are free to go when we return
+    return SPB_OK;
+}
+
+int spb_coo_wrap_device(spb_ctx *ctx, int rank, const uint64_t *shape, int32_t *const *d_idx, double *d_val,
+                        uint64_t n, const int *sort_order, spb_coo **out) {
+    if (n && (!d_idx || !d_val)) return spb_fail(SPB_ERR_ARG, "null device pointer");
+    CKR(coo_new(ctx, rank, shape, n, false, out));
+    spb_coo *a = *out;
+    for (int k = 0; k < rank; ++k) a->idx[k] = d_idx ? d_idx[k] : nullptr;
+    a->val = d_val;
+    set_order(a, sort_order);
+    return SPB_OK;
+}
+
+int spb_coo_info(const spb_coo *a, int *rank, uint64_t *shape, uint64_t *n, int *sort_order) {
+    if (!a) return spb_fail(SPB_ERR_ARG, "null array");
+    if (rank) *rank = a->rank;
+    for (int k = 0; k < a->rank; ++k) {
+        if (shape) shape[k] = a->shape[k];
+        if (sort_order) sort_order[k] = a->sort_order[k];
+    }
+    if (n) *n = a->n;
+    return SPB_OK;
+}
+
+int spb_coo_device_ptrs(const spb_coo *a, int32_t **d_idx, double **d_val) {
+    if (!a) return spb_fail(SPB_ERR_ARG, "null array");
+    for (int k = 0; k < a->rank; ++k) if (d_idx) d_idx[k] = a->idx[k];
+    if (d_val) *d_val = a->val;
+    return SPB_OK;
+}
+
+int spb_coo_set_sorted(spb_coo *a, const int *sort_order) {
+    if (!a) return spb_fail(SPB_ERR_ARG, "null array");
+    set_order(a, sort_order);
+    return SPB_OK;
+}
+
+int spb_coo_download(spb_ctx *ctx, const spb_coo *a, int32_t *const *idx, double *val) {
+    if (!ctx || !a) return spb_fail(SPB_ERR_ARG, "null argument");
+    if (a->n) {
+        for (int k = 0; k < a->rank; ++k)
+            if (idx && idx[k]) CK(cudaMemcpyAsync(idx[k], a->idx[k], a->n * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+        if (val) CK(cudaMemcpyAsync(val, a->val, a->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+
+int spb_coo_free(spb_ctx *ctx, spb_coo *a) {
+    if (!a) return SPB_OK;
+    if (a->owned && ctx) {
+        for (int k = 0; k < 2; ++k) if (a->idx[k]) cudaFreeAsync(a->idx[k], ctx->stream);
+        if (a->val) cudaFreeAsync(a->val, ctx->stream);
+    }
+    delete a;
+    return SPB_OK;
+}
+
+}  // extern "C"
+
+// ==================================================================================================
+// sort + duplicate-reduce core, shared by consolidate and by multiply's operand preparation
+// ==================================================================================================
+struct SortJob {
+    SortInput in;      // pass-0 source and drop rule
+    int bits_hi;       // significant bits of the leading key part
+    int policy;        // POLICY_*
+};
+
+// Runs the radix passes over packed keys already in (keysA, valsA) [n_ptr entries, upper bound n_cap];
+// the sorted data ends up in *keys_sorted / *vals_sorted (one of the two buffer pairs).
+static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passes, u32 n_cap, const u32 *n_ptr,
+                            u32 *hist, u64 *kA, double *vA, u64 *kB, double *vB, const SortInput *in0,
+                            u64 **keys_sorted, double **vals_sorted) {
+    const u32 tiles = (u32)div_up(n_cap ? n_cap : 1, RS_TILE);
+    u32 *lookback, *tickets;
+    CKR(ws.zeroed(&lookback, (u64)passes * tiles * RS_RADIX));
+    CKR(ws.zeroed(&tickets, (u64)passes));
+    u64 *kin = kA, *kout = kB;
+    double *vin = vA, *vout = vB;
+    for (int p = 0; p < passes; ++p) {
+        PassArgs a;
+        a.n_ptr = n_ptr;
+        a.bucket_start = hist + (u64)p * RS_RADIX;
+        a.lookback = lookback + (u64)p * tiles * RS_RADIX;
+        a.ticket = tickets + p;
+        a.shift = p * RS_RADIX_BITS;
+        if (p == 0 && first_pass == 0) {
+            // pass 0 reads the caller's arrays and writes buffer A
+            a.keys_in = nullptr; a.vals_in = nullptr; a.keys_out = kA; a.vals_out = vA;
+            k_radix_pass<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            kin = kA; vin = vA; kout = kB; vout = vB;
+        } else {
+            a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
+            SortInput dummy;
+            memset(&dummy, 0, sizeof dummy);
+            k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            u64 *tk = kin; kin = kout; kout = tk;
+            double *tv = vin; vin = vout; vout = tv;
+        }
+    }
+    CK(cudaGetLastError());
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    return 0;
+}
+
+// Sorts job.in by (hi,lo), applies the drop rule and the duplicate policy, writes the result into
+// out_hi/out_lo/out_val (capacity in.n each) and returns the counts.
+static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_lo, double *out_val,
+                       u32 *h_kept, u32 *h_out, spb_consolidate_stats *st) {
+    const SortInput &in = job.in;
+    const u32 n = in.n;
+    const int key_bits = job.bits_hi + in.bits_lo;
+    int passes = (key_bits + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
+    if (passes < 1) passes = 1;
+    if (passes > RS_MAX_PASSES) return spb_fail(SPB_ERR_ARG, "key of %d bits is too wide", key_bits);
+    if (n > (1u << 30)) return spb_fail(SPB_ERR_TOO_LARGE, "%u entries exceed the 2^30 per-sort limit", n);
+    Scratch ws(ctx);
+    Timer tm(ctx->stream);
+    const int t0 = tm.mark();
+
+    u32 *hist, *counters;  // counters: [0] kept, [1] out-of-bounds flag, [2] out count, [3] long runs
+    u64 *first_kept;
+    CKR(ws.zeroed(&hist, (u64)passes * RS_RADIX));
+    CKR(ws.zeroed(&counters, 8));
+    CKR(ws.get(&first_kept, 2));
+    CK(cudaMemsetAsync(first_kept, 0xFF, 2 * sizeof(u64), ctx->stream));
+    SortInput in0 = in;
+    in0.first_kept = first_kept;
+    const u32 sgrid = (u32)ctx->sm_count * 4;
+    if (in.drop_nan) {
+        k_first_kept_key<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
+        k_first_kept_pos<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
+    }
+    k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, hist, counters);
+    k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
+    CK(cudaGetLastError());
+
+    u64 *kA, *kB = nullptr, *ks;
+    double *vA, *vB = nullptr, *vs;
+    CKR(ws.get(&kA, n));
+    CKR(ws.get(&vA, n));
+    if (passes > 1) { CKR(ws.get(&kB, n)); CKR(ws.get(&vB, n)); }
+    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs));
+    const int t1 = tm.mark();
+
+    const u32 rtiles = (u32)div_up(n, RK_TILE);
+    ReduceArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.keys = ks; ra.vals = vs; ra.n_ptr = counters; ra.bits_lo = in.bits_lo; ra.policy = job.policy;
+    ra.out_hi = out_hi; ra.out_lo = out_lo; ra.out_val = out_val; ra.out_count = counters + 2;
+    CKR(ws.zeroed(&ra.state, rtiles));
+    CKR(ws.zeroed(&ra.ticket, 1));
+    ra.long_cap = n / RK_LONG_RUN + 1;
+    CKR(ws.get(&ra.long_list, 2ull * ra.long_cap));
+    ra.long_count = counters + 3;
+    k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
+    if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
+        k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
+    CK(cudaGetLastError());
+    const int t2 = tm.mark();
+
+    u32 h[4];
+    CK(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h[1]) return spb_fail(SPB_ERR_ARG, "Sparse index out of bounds (an index is negative or >= its extent)");
+    *h_kept = h[0];
+    *h_out = h[2];
+    if (st) {
+        st->n_in = n; st->n_kept = h[0]; st->n_out = h[2];
+        st->key_bits = key_bits; st->passes = passes;
+        st->ms_sort = tm.ms(t0, t1); st->ms_reduce = tm.ms(t1, t2); st->ms_total = tm.ms(t0, t2);
+    }
+    return 0;
+}
+
+// consolidate `in` into a fresh array sorted by `so`; `ref_so` is the order the reference would have
+// used at this call site (decides which NaNs form the "leading run" when zero_nan).
+static int consolidate_core(spb_ctx *ctx, const spb_coo *in, const int *so, const int *ref_so, int policy,
+                            bool drop_zero, int zero_nan, spb_coo **out, spb_consolidate_stats *st) {
+    if (in->n > (1ull << 30)) return spb_fail(SPB_ERR_TOO_LARGE, "%llu entries exceed the 2^30 per-sort limit", (ull)in->n);
+    spb_coo *r = nullptr;
+    CKR(coo_new(ctx, in->rank, in->shape, in->n, true, &r));
+    set_order(r, so);
+    if (st) memset(st, 0, sizeof *st);
+    if (in->n == 0) { *out = r; return SPB_OK; }  // algorithm.hpp:263,318
+    const int d0 = so[0], d1 = in->rank > 1 ? so[1] : -1;
+    SortJob job;
+    memset(&job, 0, sizeof job);
+    job.in.hi = in->idx[d0];
+    job.in.lo = d1 >= 0 ? in->idx[d1] : nullptr;
+    job.in.val = in->val;
+    job.in.n = (u32)in->n;
+    job.in.bits_lo = d1 >= 0 ? bits_for(in->shape[d1]) : 0;
+    job.in.extent_hi = (u32)(in->shape[d0] > 0xffffffffull ? 0xffffffffu : in->shape[d0]);
+    job.in.extent_lo = d1 >= 0 ? (u32)in->shape[d1] : 1u;
+    job.in.drop_zero = drop_zero ? 1 : 0;
+    job.in.drop_nan = (drop_zero && zero_nan) ? 1 : 0;
+    const int r0 = ref_so[0], r1 = in->rank > 1 ? ref_so[1] : -1;
+    job.in.ref_hi = in->idx[r0];
+    job.in.ref_lo = r1 >= 0 ? in->idx[r1] : nullptr;
+    job.in.ref_bits_lo = r1 >= 0 ? bits_for(in->shape[r1]) : 0;
+    job.bits_hi = bits_for(in->shape[d0]);
+    job.policy = policy;
+    u32 kept = 0, nout = 0;
+    int rc = sort_reduce(ctx, job, r->idx[d0], d1 >= 0 ? r->idx[d1] : nullptr, r->val, &kept, &nout, st);
+    if (rc) { spb_coo_free(ctx, r); return rc; }
+    r->n = nout;
+    *out = r;
+    return SPB_OK;
+}
+
+static int check_order(const spb_coo *a, const int *so, const char *what) {
+    if (!so) return spb_fail(SPB_ERR_ARG, "%s: sort_order is null", what);
+    bool seen[2] = {false, false};
+    for (int k = 0; k < a->rank; ++k) {
+        if (so[k] < 0 || so[k] >= a->rank || seen[so[k]])
+            return spb_fail(SPB_ERR_ARG, "%s: sort_order is not a permutation of the dimensions", what);
+        seen[so[k]] = true;
+    }
+    return 0;
+}
+
+// ---- row structure -------------------------------------------------------------------------------
+struct RowIndex {   // compressed rows of a sorted array (scratch-owned)
+    u32 *start;     // [nrows+1]
+    i32 *id;        // [nrows]
+    u32 nrows;
+};
+
+static int build_row_index(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, RowIndex *ri) {
+    CKR(ws.get(&ri->start, (u64)n + 1));
+    CKR(ws.get(&ri->id, (u64)n));
+    u32 *count, *ticket;
+    u64 *state;
+    const u32 tiles = (u32)div_up(n ? n : 1, RH_TILE);
+    CKR(ws.zeroed(&count, 1));
+    CKR(ws.zeroed(&ticket, 1));
+    CKR(ws.zeroed(&state, tiles));
+    if (n) k_row_heads<<<tiles, RH_THREADS, 0, ctx->stream>>>(hi, n, ri->start, ri->id, count, state, ticket);
+    k_row_sentinel<<<1, 1, 0, ctx->stream>>>(ri->start, count, n);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&ri->nrows, count, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ws.release(state);
+    return 0;
+}
+
+template <typename InT, typename OutT>
+static int exclusive_scan(spb_ctx *ctx, Scratch &ws, const InT *in, OutT *out, u64 n) {
+    if (n == 0) { CK(cudaMemsetAsync(out, 0, sizeof(OutT), ctx->stream)); return 0; }
+    const u32 tiles = (u32)div_up(n, SC_TILE);
+    u64 *state;
+    u32 *ticket;
+    CKR(ws.zeroed(&state, tiles));
+    CKR(ws.zeroed(&ticket, 1));
+    k_exclusive_scan<InT, OutT><<<tiles, SC_THREADS, 0, ctx->stream>>>(in, out, n, state, ticket);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// dense pointer over `extent` values of the leading index of a sorted array
+static int build_dense_ptr(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, u64 extent, u32 **ptr_out) {
+    RowIndex ri;
+    CKR(build_row_index(ctx, ws, hi, n, &ri));
+    u32 *len, *ptr, *cnt;
+    CKR(ws.zeroed(&len, extent + 1));
+    CKR(ws.get(&ptr, extent + 2));
+    CKR(ws.get(&cnt, 1));
+    CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    if (ri.nrows) k_scatter_row_len<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, len);
+    CKR((exclusive_scan<u32, u32>(ctx, ws, len, ptr, extent)));
+    CK(cudaStreamSynchronize(ctx->stream));  // &ri.nrows (host) was read by the async copy above
+    ws.release(ri.start); ws.release(ri.id); ws.release(len);
+    *ptr_out = ptr;
+    return 0;
+}
+
+static int densify(spb_ctx *ctx, Scratch &ws, const spb_coo *v, u64 dim, double **dense, unsigned char **mask) {
+    CKR(ws.zeroed(dense, dim));
+    if (mask) CKR(ws.zeroed(mask, dim));
+    if (v->n) k_densify<<<grid_for(v->n, 256, 1u << 16), 256, 0, ctx->stream>>>(v->idx[0], v->val, v->n, dim, *dense, mask ? *mask : nullptr);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ==================================================================================================
+// multiply core on prepared operands
+// ==================================================================================================
+static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key_bits, int kbits,
+                           const MMOperands &m, u32 row_lo, i32 *t_row, i32 *t_k, double *t_v, u32 *h_out) {
+    Scratch ws(ctx);  // everything allocated here dies with this call
+    int passes = (key_bits + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
+    if (passes < 1) passes = 1;
+    u32 *hist, *counters;
+    CKR(ws.zeroed(&hist, (u64)passes * RS_RADIX));
+    CKR(ws.zeroed(&counters, 8));
+    CK(cudaMemcpyAsync(counters, &count, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    k_keys_hist<<<grid_for(count, 512, (u32)ctx->sm_count * 4), 512, 0, ctx->stream>>>(kA, count, passes, hist);
+    k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
+    u64 *kB, *ks;
+    double *vB, *vs;
+    CKR(ws.get(&kB, count));
+    CKR(ws.get(&vB, count));
+    // input is in A; passes ping-pong A->B->A...
+    {
+        const u32 tiles = (u32)div_up(count, RS_TILE);
+        u32 *lookback, *tickets;
+        CKR(ws.zeroed(&lookback, (u64)passes * tiles * RS_RADIX));
+        CKR(ws.zeroed(&tickets, (u64)passes));
+        u64 *kin = kA, *kout = kB;
+        double *vin = vA, *vout = vB;
+        SortInput dummy;
+        memset(&dummy, 0, sizeof dummy);
+        for (int p = 0; p < passes; ++p) {
+            PassArgs a;
+            a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
+            a.n_ptr = counters;
+            a.bucket_start = hist + (u64)p * RS_RADIX;
+            a.lookback = lookback + (u64)p * tiles * RS_RADIX;
+            a.ticket = tickets + p;
+            a.shift = p * RS_RADIX_BITS;
+            k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            u64 *tk = kin; kin = kout; kout = tk;
+            double *tv = vin; vin = vout; vout = tv;
+        }
+        ks = kin; vs = vin;
+        CK(cudaGetLastError());
+    }
+    const u32 rtiles = (u32)div_up(count, RK_TILE);
+    ReduceArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.keys = ks; ra.vals = vs; ra.n_ptr = counters; ra.bits_lo = kbits; ra.policy = POLICY_ADD;
+    ra.out_hi = t_row; ra.out_lo = t_k; ra.out_val = t_v; ra.out_count = counters + 2;
+    CKR(ws.zeroed(&ra.state, rtiles));
+    CKR(ws.zeroed(&ra.ticket, 1));
+    ra.row_ids = m.arow_id; ra.row_base = (i32)row_lo; ra.si = m.si; ra.sk = m.sk; ra.C = m.C;
+    k_reduce_by_key<MODE_ESC><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_out, counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+struct EscChunk { i32 *row; i32 *k; double *v; u32 n; };
+
+// A: consolidated, sorted by (a_row_dim, other).  B: consolidated, sorted by (b_inner_dim, other).
+static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, int a_row_dim,
+                         const spb_coo *sj, const spb_coo *B, int b_inner_dim, const spb_coo *sk,
+                         spb_coo *out, spb_mm_stats *st, Timer &tm, int t_begin) {
+    Scratch ws(ctx);
+    const int a_in = 1 - a_row_dim, b_col = 1 - b_inner_dim;
+    const u64 m_rows = A->shape[a_row_dim], n_inner = A->shape[a_in], n_cols = B->shape[b_col];
+    MMOperands m;
+    memset(&m, 0, sizeof m);
+    m.C = C;
+    m.a_j = A->idx[a_in]; m.a_val = A->val; m.nnz_a = (u32)A->n;
+    RowIndex ri;
+    CKR(build_row_index(ctx, ws, A->idx[a_row_dim], (u32)A->n, &ri));
+    m.arow_id = ri.id; m.arow_start = ri.start; m.nrows = ri.nrows;
+    u32 *bptr;
+    CKR(build_dense_ptr(ctx, ws, B->idx[b_inner_dim], (u32)B->n, n_inner, &bptr));
+    m.bptr = bptr; m.b_k = B->idx[b_col]; m.b_val = B->val;
+    double *d;
+    unsigned char *mask;
+    if (si) { CKR(densify(ctx, ws, si, m_rows, &d, nullptr)); m.si = d; }
+    if (sj) { CKR(densify(ctx, ws, sj, n_inner, &d, &mask)); m.sj = d; m.sj_mask = mask; }
+    if (sk) { CKR(densify(ctx, ws, sk, n_cols, &d, nullptr)); m.sk = d; }
+    const int t_prep = tm.mark();
+
+    // ---- symbolic: products per entry / row, bins, output counts -------------------------------
+    const u32 nrows = m.nrows;
+    u32 *ent_f, *row_cnt;
+    u64 *ent_off, *esc_f, *esc_off, *c_ptr;
+    unsigned char *row_cls;
+    ull *stats;
+    CKR(ws.get(&ent_f, m.nnz_a));
+    CKR(ws.get(&ent_off, (u64)m.nnz_a + 1));
+    CKR(ws.get(&row_cls, nrows));
+    CKR(ws.get(&esc_f, nrows));
+    CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
+    CKR(ws.zeroed(&stats, 4));
+    const u32 cap = (u32)ctx->sm_count * 32;
+    k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
+    CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
+    k_row_bins<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, ctx->merge_max_products, row_cls, esc_f, stats);
+    CK(cudaGetLastError());
+    ull h_stats[4];
+    CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ws.release(ent_f);
+
+    if (h_stats[1]) k_merge_rows<false><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, nullptr, nullptr, nullptr, nullptr);
+    CK(cudaGetLastError());
+
+    // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
+    std::vector<EscChunk> chunks;
+    u32 *esc_first = nullptr;
+    if (h_stats[3]) {
+        CKR(ws.get(&esc_off, (u64)nrows + 1));
+        CKR((exclusive_scan<u64, u64>(ctx, ws, esc_f, esc_off, nrows)));
+        CKR(ws.get(&esc_first, nrows));
+        const u64 f_esc = h_stats[3];
+        const u32 nchunks = (u32)div_up(f_esc, ctx->esc_chunk);
+        u32 *rb;
+        u64 *pb;
+        CKR(ws.get(&rb, (u64)nchunks + 1));
+        CKR(ws.get(&pb, (u64)nchunks + 1));
+        k_esc_chunks<<<(u32)div_up((u64)nchunks + 1, 128), 128, 0, ctx->stream>>>(esc_off, nrows, ctx->esc_chunk, nchunks, rb, pb);
+        CK(cudaGetLastError());
+        std::vector<u32> h_rb(nchunks + 1);
+        std::vector<u64> h_pb(nchunks + 1);
+        CK(cudaMemcpyAsync(h_rb.data(), rb, (nchunks + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_pb.data(), pb, (nchunks + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int kbits = bits_for(n_cols);
+        for (u32 c = 0; c < nchunks; ++c) {
+            const u32 r_lo = h_rb[c], r_hi = h_rb[c + 1];
+            const u64 cnt64 = h_pb[c + 1] - h_pb[c];
+            if (cnt64 == 0) continue;
+            if (cnt64 > (1ull << 30))
+                return spb_fail(SPB_ERR_TOO_LARGE, "a single row of the product needs %llu intermediate products (> 2^30)", (ull)cnt64);
+            const u32 cnt = (u32)cnt64;
+            const int key_bits = bits_for((u64)(r_hi - r_lo)) + kbits;
+            u64 *kA;
+            double *vA;
+            i32 *t_row, *t_k;
+            double *t_v;
+            CKR(ws.get(&kA, cnt)); CKR(ws.get(&vA, cnt));
+            CKR(ws.get(&t_row, cnt)); CKR(ws.get(&t_k, cnt)); CKR(ws.get(&t_v, cnt));
+            k_esc_expand<<<grid_for(cnt, 256, cap), 256, 0, ctx->stream>>>(m, esc_off, ent_off, r_lo, r_hi, h_pb[c], cnt, kbits, kA, vA);
+            CK(cudaGetLastError());
+            u32 nout = 0;
+            CKR(esc_sort_reduce(ctx, kA, vA, cnt, key_bits, kbits, m, r_lo, t_row, t_k, t_v, &nout));
+            ws.release(kA); ws.release(vA);
+            EscChunk ch;
+            ch.n = nout;
+            // shrink the temporaries to what was produced
+            CKR(ws.get(&ch.row, nout)); CKR(ws.get(&ch.k, nout)); CKR(ws.get(&ch.v, nout));
+            if (nout) {
+                CK(cudaMemcpyAsync(ch.row, t_row, nout * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ch.k, t_k, nout * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(ch.v, t_v, nout * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                k_esc_row_spans<<<grid_for(nout, 256, cap), 256, 0, ctx->stream>>>(ch.row, nout, esc_first, row_cnt);
+                k_esc_row_counts<<<grid_for(nout, 256, cap), 256, 0, ctx->stream>>>(ch.row, nout, esc_first, row_cnt);
+            }
+            ws.release(t_row); ws.release(t_k); ws.release(t_v);
+            chunks.push_back(ch);
+        }
+        CK(cudaGetLastError());
+    }
+
+    // ---- place the rows ---------------------------------------------------------------------------
+    CKR(ws.get(&c_ptr, (u64)nrows + 1));
+    CKR((exclusive_scan<u32, u64>(ctx, ws, row_cnt, c_ptr, nrows)));
+    u64 nnz_c = 0;
+    CK(cudaMemcpyAsync(&nnz_c, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int t_sym = tm.mark();
+    if (nnz_c >= (1ull << 31))
+        return spb_fail(SPB_ERR_TOO_LARGE, "product has %llu entries; a VectorCooArray holds < 2^31 (algorithm.hpp:419)", (ull)nnz_c);
+
+    // ---- numeric ------------------------------------------------------------------------------------
+    size_t cnt = nnz_c ? nnz_c : 1;
+    CK(cudaMallocAsync((void **)&out->idx[0], cnt * sizeof(i32), ctx->stream));
+    CK(cudaMallocAsync((void **)&out->idx[1], cnt * sizeof(i32), ctx->stream));
+    CK(cudaMallocAsync((void **)&out->val, cnt * sizeof(double), ctx->stream));
+    out->owned = true;
+    out->n = nnz_c;
+    if (h_stats[1] && nnz_c)
+        k_merge_rows<true><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, c_ptr, out->idx[0], out->idx[1], out->val);
+    for (auto &ch : chunks)
+        if (ch.n) k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
+    CK(cudaGetLastError());
+    const int t_num = tm.mark();
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st) {
+        st->products = h_stats[0]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2]; st->products_esc = h_stats[3];
+        st->nnz_a = A->n; st->nnz_b = B->n; st->rows_a = nrows; st->nnz_c = nnz_c;
+        st->ms_prepare = tm.ms(t_begin, t_prep);
+        st->ms_symbolic = tm.ms(t_prep, t_sym);
+        st->ms_numeric = tm.ms(t_sym, t_num);
+        st->ms_total = tm.ms(t_begin, t_num);
+    }
+    return SPB_OK;
+}
+
+// ==================================================================================================
+extern "C" {
+
+int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int policy, int zero_nan,
+                    spb_coo **out, spb_consolidate_stats *stats) {
+    if (!ctx || !in || !out) return spb_fail(SPB_ERR_ARG, "spb_consolidate: null argument");
+    CKR(check_order(in, sort_order, "spb_consolidate"));
+    if (policy < 0 || policy > 2) return spb_fail(SPB_ERR_ARG, "unknown duplicate policy %d", policy);
+    CK(cudaSetDevice(ctx->device));
+    return consolidate_core(ctx, in, sort_order, sort_order, policy, true, zero_nan, out, stats);
+}
+
+int spb_dim_beginnings(spb_ctx *ctx, const spb_coo *a, uint64_t *out, uint64_t cap, uint64_t *count) {
+    if (!ctx || !a || !count) return spb_fail(SPB_ERR_ARG, "spb_dim_beginnings: null argument");
+    if (a->sort_order[0] < 0)
+        return spb_fail(SPB_ERR_NOT_SORTED, "dim_beginnings() required the VectorCooArray is sorted first.");
+    *count = 0;
+    if (a->n == 0) return SPB_OK;  // algorithm.hpp:89: empty array, empty list
+    CK(cudaSetDevice(ctx->device));
+    Scratch ws(ctx);
+    RowIndex ri;
+    CKR(build_row_index(ctx, ws, a->idx[a->sort_order[0]], (u32)a->n, &ri));
+    *count = (u64)ri.nrows + 1;
+    u64 take = *count < cap ? *count : cap;
+    if (out && take) {
+        std::vector<u32> h(take);
+        CK(cudaMemcpyAsync(h.data(), ri.start, take * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (u64 i = 0; i < take; ++i) out[i] = h[i];
+    }
+    return SPB_OK;
+}
+
+static int scale_ok(const spb_coo *s, const char *name) {
+    if (s && s->rank != 1) return spb_fail(SPB_ERR_ARG, "%s must be a rank-1 array", name);
+    return 0;
+}
+
+int spb_multiply_mm_prepared(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, int a_row_dim,
+                             const spb_coo *sj, const spb_coo *B, int b_inner_dim, const spb_coo *sk,
+                             spb_coo **out, spb_mm_stats *stats) {
+    if (!ctx || !A || !B || !out) return spb_fail(SPB_ERR_ARG, "spb_multiply_mm_prepared: null argument");
+    if (A->rank != 2 || B->rank != 2) return spb_fail(SPB_ERR_ARG, "A and B must be rank-2 arrays");
+    if ((a_row_dim | 1) != 1 || (b_inner_dim | 1) != 1) return spb_fail(SPB_ERR_ARG, "dimension must be 0 or 1");
+    CKR(scale_ok(si, "scalei")); CKR(scale_ok(sj, "scalej")); CKR(scale_ok(sk, "scalek"));
+    if (A->sort_order[0] != a_row_dim || B->sort_order[0] != b_inner_dim)
+        return spb_fail(SPB_ERR_NOT_SORTED, "prepared operands must be consolidated by (row, inner) and (inner, col)");
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    const u64 shape[2] = {A->shape[a_row_dim], B->shape[1 - b_inner_dim]};
+    if (A->shape[1 - a_row_dim] != B->shape[b_inner_dim])
+        return spb_fail(SPB_ERR_INNER_DIM, "Inner dimensions for A (%ld) and B (%ld) must match!",
+                        (long)A->shape[1 - a_row_dim], (long)B->shape[b_inner_dim]);
+    spb_coo *r = nullptr;
+    CKR(coo_new(ctx, 2, shape, 0, false, &r));
+    r->owned = true;
+    *out = r;
+    if (C == 0.0 || (si && si->n == 0) || A->n == 0 || (sj && sj->n == 0) || B->n == 0 || (sk && sk->n == 0))
+        return SPB_OK;
+    Timer tm(ctx->stream);
+    const int t0 = tm.mark();
+    int rc = multiply_core(ctx, C, si, A, a_row_dim, sj, B, b_inner_dim, sk, r, stats, tm, t0);
+    if (rc) { spb_coo_free(ctx, r); *out = nullptr; }
+    return rc;
+}
+
+int spb_multiply_mm(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, char tA, const spb_coo *sj,
+                    const spb_coo *B, char tB, const spb_coo *sk, int policy, int zero_nan, spb_coo **out,
+                    spb_mm_stats *stats) {
+    if (!ctx || !A || !B || !out) return spb_fail(SPB_ERR_ARG, "spb_multiply_mm: null argument");
+    if (A->rank != 2 || B->rank != 2) return spb_fail(SPB_ERR_ARG, "A and B must be rank-2 arrays");
+    if (policy < 0 || policy > 2) return spb_fail(SPB_ERR_ARG, "unknown duplicate policy %d", policy);
+    CKR(scale_ok(si, "scalei")); CKR(scale_ok(sj, "scalej")); CKR(scale_ok(sk, "scalek"));
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    // multiply_sparse.hpp:167-169
+    const int a_so[2] = {tA == 'T' ? 1 : 0, tA == 'T' ? 0 : 1};
+    const int b_so[2] = {tB == 'T' ? 0 : 1, tB == 'T' ? 1 : 0};  // the reference's order: (col, inner)
+    const int b_mine[2] = {b_so[1], b_so[0]};                      // ours: (inner, col)
+    const u64 shape[2] = {A->shape[a_so[0]], B->shape[b_so[0]]};
+    if (A->shape[a_so[1]] != B->shape[b_so[1]])  // :172-174
+        return spb_fail(SPB_ERR_INNER_DIM, "Inner dimensions for A (%ld) and B (%ld) must match!",
+                        (long)A->shape[a_so[1]], (long)B->shape[b_so[1]]);
+    spb_coo *r = nullptr;
+    CKR(coo_new(ctx, 2, shape, 0, false, &r));
+    r->owned = true;
+    *out = r;
+    // :178-184
+    if (C == 0.0 || (si && si->n == 0) || A->n == 0 || (sj && sj->n == 0) || B->n == 0 || (sk && sk->n == 0))
+        return SPB_OK;
+    Timer tm(ctx->stream);
+    const int t0 = tm.mark();
+    // Consolidate<> (algorithm.hpp:354-369): reuse an operand already flagged sorted in the needed order
+    spb_coo *Ac = nullptr, *Bc = nullptr;
+    int rc = 0;
+    const spb_coo *Ause = A, *Buse = B;
+    if (!(A->sort_order[0] == a_so[0] && A->sort_order[1] == a_so[1])) {
+        rc = consolidate_core(ctx, A, a_so, a_so, policy, true, zero_nan, &Ac, nullptr);
+        Ause = Ac;
+    }
+    if (!rc) {
+        if (B->sort_order[0] == b_so[0] && B->sort_order[1] == b_so[1]) {
+            // the reference would use B as stored: re-bucket by inner index, keep every entry
+            rc = consolidate_core(ctx, B, b_mine, b_so, POLICY_KEEP_ALL, false, 0, &Bc, nullptr);
+        } else {
+            rc = consolidate_core(ctx, B, b_mine, b_so, policy, true, zero_nan, &Bc, nullptr);
+        }
+        Buse = Bc;
+    }
+    if (!rc && Ause->n && Buse->n)
+        rc = multiply_core(ctx, C, si, Ause, a_so[0], sj, Buse, b_mine[0], sk, r, stats, tm, t0);
+    spb_coo_free(ctx, Ac);
+    spb_coo_free(ctx, Bc);
+    if (rc) { spb_coo_free(ctx, r); *out = nullptr; }
+    return rc;
+}
+
+int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, char tA, const spb_coo *sj,
+                    const spb_coo *V, int policy, int zero_nan, spb_coo **out) {
+    if (!ctx || !A || !V || !out) return spb_fail(SPB_ERR_ARG, "spb_multiply_mv: null argument");
+    if (A->rank != 2 || V->rank != 1) return spb_fail(SPB_ERR_ARG, "A must be rank 2 and V rank 1");
+    if (policy < 0 || policy > 2) return spb_fail(SPB_ERR_ARG, "unknown duplicate policy %d", policy);
+    CKR(scale_ok(si, "scalei")); CKR(scale_ok(sj, "scalej"));
+    CK(cudaSetDevice(ctx->device));
+    const int a_so[2] = {tA == 'T' ? 1 : 0, tA == 'T' ? 0 : 1};  // multiply_sparse.hpp:294
+    const u64 shape[1] = {A->shape[a_so[0]]};
+    if (A->shape[a_so[1]] != V->shape[0])  // :298-300
+        return spb_fail(SPB_ERR_INNER_DIM, "Inner dimensions for A (%ld) and V (%ld) must match!",
+                        (long)A->shape[a_so[1]], (long)V->shape[0]);
+    spb_coo *r = nullptr;
+    CKR(coo_new(ctx, 1, shape, 0, false, &r));
+    r->owned = true;
+    *out = r;
+    if (C == 0.0 || (si && si->n == 0) || A->n == 0 || (sj && sj->n == 0) || V->n == 0) return SPB_OK;  // :304-309
+    spb_coo *Ac = nullptr, *Vc = nullptr;
+    const spb_coo *Ause = A, *Vuse = V;
+    const int v_so[2] = {0, 0};
+    int rc = 0;
+    if (!(A->sort_order[0] == a_so[0] && A->sort_order[1] == a_so[1])) {
+        rc = consolidate_core(ctx, A, a_so, a_so, policy, true, zero_nan, &Ac, nullptr);  // :312
+        Ause = Ac;
+    }
+    if (!rc && V->sort_order[0] != 0) {
+        rc = consolidate_core(ctx, V, v_so, v_so, policy, true, zero_nan, &Vc, nullptr);  // :313
+        Vuse = Vc;
+    }
+    if (!rc && Ause->n) {
+        Scratch ws(ctx);
+        const u64 m_rows = A->shape[a_so[0]], n_inner = A->shape[a_so[1]];
+        MMOperands m;
+        memset(&m, 0, sizeof m);
+        m.C = C;
+        m.a_j = Ause->idx[a_so[1]]; m.a_val = Ause->val; m.nnz_a = (u32)Ause->n;
+        RowIndex ri;
+        rc = build_row_index(ctx, ws, Ause->idx[a_so[0]], (u32)Ause->n, &ri);
+        double *d, *vd, *row_val;
+        unsigned char *mask, *vmask, *row_keep;
+        u32 *slot;
+        if (!rc) {
+            m.arow_id = ri.id; m.arow_start = ri.start; m.nrows = ri.nrows;
+            if (si) { rc = densify(ctx, ws, si, m_rows, &d, nullptr); m.si = d; }
+        }
+        if (!rc && sj) { rc = densify(ctx, ws, sj, n_inner, &d, &mask); m.sj = d; m.sj_mask = mask; }
+        if (!rc) rc = densify(ctx, ws, Vuse, n_inner, &vd, &vmask);
+        if (!rc) rc = ws.get(&row_val, ri.nrows);
+        if (!rc) rc = ws.get(&row_keep, ri.nrows);
+        if (!rc) rc = ws.get(&slot, (u64)ri.nrows + 1);
+        if (!rc) {
+            const u32 cap = (u32)ctx->sm_count * 32;
+            k_mv_rows<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(m, vd, vmask, row_val, row_keep);
+            rc = exclusive_scan<unsigned char, u32>(ctx, ws, row_keep, slot, ri.nrows);
+            u32 nout = 0;
+            if (!rc) {
+                cudaMemcpyAsync(&nout, slot + ri.nrows, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream);
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = spb_fail(SPB_ERR_CUDA, "multiply_mv: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            if (!rc) {
+                size_t cnt = nout ? nout : 1;
+                if (cudaMallocAsync((void **)&r->idx[0], cnt * sizeof(i32), ctx->stream) != cudaSuccess ||
+                    cudaMallocAsync((void **)&r->val, cnt * sizeof(double), ctx->stream) != cudaSuccess)
+                    rc = spb_fail(SPB_ERR_CUDA, "multiply_mv: out of device memory");
+            }
+            if (!rc) {
+                r->n = nout;
+                if (nout) k_mv_emit<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(ri.nrows, ri.id, row_val, row_keep, slot, r->idx[0], r->val);
+                if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = spb_fail(SPB_ERR_CUDA, "multiply_mv: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        }
+    }
+    spb_coo_free(ctx, Ac);
+    spb_coo_free(ctx, Vc);
+    if (rc) { spb_coo_free(ctx, r); *out = nullptr; }
+    return rc;
+}
+
+// ---- generators ------------------------------------------------------------------------------------
+int spb_gen_dup_coo(spb_ctx *ctx, uint64_t seed, uint64_t i0, uint64_t n, uint64_t ubase, int bits,
+                    uint64_t zero_every, spb_coo **out) {
+    if (!ctx || !out || bits < 1 || bits > 31 || ubase == 0) return spb_fail(SPB_ERR_ARG, "spb_gen_dup_coo: bad argument");
+    const u64 shape[2] = {1ull << bits, 1ull << bits};
+    CKR(coo_new(ctx, 2, shape, n, true, out));
+    if (n) k_gen_dup_coo<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, i0, n, ubase, bits, zero_every, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    CK(cudaGetLastError());
+    return SPB_OK;
+}
+
+int spb_gen_banded(spb_ctx *ctx, uint64_t seed, uint64_t mdim, uint64_t r0, uint64_t r1, spb_coo **out) {
+    if (!ctx || !out || r1 < r0 || r1 > mdim) return spb_fail(SPB_ERR_ARG, "spb_gen_banded: bad argument");
+    const u64 shape[2] = {mdim, mdim};
+    const u64 n = (r1 - r0) * 5;
+    CKR(coo_new(ctx, 2, shape, n, true, out));
+    if (n) k_gen_banded<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, mdim, r0, n, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    CK(cudaGetLastError());
+    return SPB_OK;
+}
+
+int spb_gen_regrid(spb_ctx *ctx, uint64_t seed, uint32_t ny, uint32_t nx, uint32_t gy, uint32_t gx, spb_coo **out) {
+    if (!ctx || !out || !ny || !nx || !gy || !gx) return spb_fail(SPB_ERR_ARG, "spb_gen_regrid: bad argument");
+    const u64 shape[2] = {(u64)ny * nx, (u64)gy * gx};
+    const u64 n = shape[0] * 4;
+    CKR(coo_new(ctx, 2, shape, n, true, out));
+    k_gen_regrid<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, ny, nx, gy, gx, n, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    CK(cudaGetLastError());
+    return SPB_OK;
+}
+
+int spb_gen_rmat(spb_ctx *ctx, uint64_t seed, int scale, uint64_t nedges, spb_coo **out) {
+    if (!ctx || !out || scale < 1 || scale > 30) return spb_fail(SPB_ERR_ARG, "spb_gen_rmat: bad argument");
+    const u64 shape[2] = {1ull << scale, 1ull << scale};
+    CKR(coo_new(ctx, 2, shape, nedges, true, out));
+    if (nedges) k_gen_rmat<<<grid_for(nedges, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, scale, nedges, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    CK(cudaGetLastError());
+    return SPB_OK;
+}
+
+int spb_gen_vector(spb_ctx *ctx, uint64_t seed, uint64_t dim, spb_coo **out) {
+    if (!ctx || !out) return spb_fail(SPB_ERR_ARG, "spb_gen_vector: bad argument");
+    const u64 shape[1] = {dim};
+    CKR(coo_new(ctx, 1, shape, dim, true, out));
+    if (dim) k_gen_vector<<<grid_for(dim, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, dim, (*out)->idx[0], (*out)->val);
+    CK(cudaGetLastError());
+    const int so[1] = {0};
+    set_order(*out, so);
+    return SPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+"""Helpers for the -m gpu parity tests: move oracle-side Coo objects through the C ABI."""
+import numpy as np
+
+import spsparse_b200 as sp
+from oracle.oracle import Coo
+
+
+def up(ctx, c: Coo):
+    if c is None:
+        return None
+    return sp.CooArray.from_host(ctx, c.shape, c.idx, c.val, c.sort_order)
+
+
+def down(a: sp.CooArray) -> Coo:
+    idx, val = a.to_host()
+    return Coo(a.shape, idx, val, a.sort_order)

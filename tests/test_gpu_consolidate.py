@@ -1,0 +1,167 @@
+"""-m gpu parity tests for consolidate / dim_beginnings: the CUDA path (through the C ABI) against
+the reference-generated fixtures, the CPU oracle on fresh seeded inputs, and size-independent
+properties at larger sizes.  Index structure must be bit-exact; values are bit-exact too because
+the duplicate fold keeps the reference's left-to-right order (tolerance stated where it is not)."""
+import numpy as np
+import pytest
+
+import _cases
+import _golden
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import spsparse_b200 as sp
+    with sp.Context(0) as c:
+        yield c
+
+
+def gpu_consolidate(ctx, a, so, pol=O.ADD, zn=False):
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    A = up(ctx, a)
+    R = sp.consolidate(ctx, A, so, pol, zn)
+    out = down(R)
+    db = R.dim_beginnings() if a.rank == 2 else None
+    A.free(); R.free()
+    return out, db
+
+
+# tests/test_array.cpp:135-168
+def test_known_answer(ctx):
+    a = O.Coo((2, 4), [[1, 1, 0, 0, 1], [3, 2, 3, 1, 2]], [5., 3., 17., 14., 15.])
+    r, db = gpu_consolidate(ctx, a, (0, 1))
+    assert r.idx[0].tolist() == [0, 0, 1, 1] and r.idx[1].tolist() == [1, 3, 2, 3]
+    assert r.val.tolist() == [14., 17., 18., 5.] and db.tolist() == [0, 2, 4]
+    assert r.sort_order == (0, 1)
+    r, db = gpu_consolidate(ctx, a, (1, 0))
+    assert r.idx[0].tolist() == [0, 1, 0, 1] and r.idx[1].tolist() == [1, 2, 3, 3]
+    assert r.val.tolist() == [14., 18., 17., 5.] and db.tolist() == [0, 1, 2, 4]
+
+
+def test_fixtures_from_the_reference(ctx):
+    p = _golden.pack("consolidate_cases")
+    for s in range(int(p["count"])):
+        a, want = _golden.get_coo(p, f"c{s}_in"), _golden.get_coo(p, f"c{s}_out")
+        pol, zn, *so = (int(x) for x in p[f"c{s}_args"])
+        got, db = gpu_consolidate(ctx, a, tuple(so), pol, zn)
+        assert _cases.same_coo(got, want), f"consolidate case {s}"
+        if a.rank == 2:
+            assert np.array_equal(db, p[f"c{s}_db"]), f"dim_beginnings case {s}"
+
+
+def test_against_oracle_fresh_seeds(ctx, orc):
+    for s in range(1000, 1060):
+        c = _cases.consolidate_case(s)
+        a = O.Coo(tuple(c["shape"]), c["idx"], c["val"])
+        args = (tuple(c["sort_order"]), c["policy"], c["zero_nan"])
+        got, db = gpu_consolidate(ctx, a, *args)
+        want = orc.consolidate(a, *args)
+        assert _cases.same_coo(got, want), s
+        if a.rank == 2:
+            assert np.array_equal(db, orc.dim_beginnings(want)), s
+
+
+def test_edge_cases(ctx, orc):
+    import spsparse_b200 as sp
+    # empty input: empty output, still flagged sorted (algorithm.hpp:263,318)
+    r, db = gpu_consolidate(ctx, O.Coo((4, 4), [[], []], []), (0, 1))
+    assert r.n == 0 and r.sort_order == (0, 1) and len(db) == 0
+    # everything dropped
+    r, _ = gpu_consolidate(ctx, O.Coo((4, 4), [[1, 2], [1, 2]], [0.0, -0.0]), (0, 1))
+    assert r.n == 0
+    r, _ = gpu_consolidate(ctx, O.Coo((4, 4), [[1, 2], [1, 2]], [np.nan, 0.0]), (0, 1), O.ADD, True)
+    assert r.n == 0
+    # one long run of duplicates (exercises the deferred long-run path); integer values => exact
+    n = 20000
+    a = O.Coo((8, 8), [np.full(n, 3), np.full(n, 5)], np.arange(1, n + 1, dtype=np.float64))
+    for pol, want in ((O.ADD, n * (n + 1) / 2), (O.LEAVE_ALONE, 1.0), (O.REPLACE, float(n))):
+        r, _ = gpu_consolidate(ctx, a, (0, 1), pol)
+        assert r.n == 1 and r.val[0] == want
+    # long run of reals: tree order differs from the left fold => 1e-12 relative (north_star tolerance)
+    rng = np.random.default_rng(3)
+    a = O.Coo((8, 8), [np.full(n, 3), np.full(n, 5)], 0.5 + rng.random(n))
+    r, _ = gpu_consolidate(ctx, a, (0, 1))
+    want = orc.consolidate(a, (0, 1))
+    assert abs(r.val[0] - want.val[0]) <= 1e-12 * abs(want.val[0])
+    # maximum extents: 2^31 x 2^31 shape, indices at both ends
+    big = (1 << 31) - 1
+    a = O.Coo((1 << 31, 1 << 31), [[big, 0, big, 0], [big, big, big, 0]], [1., 2., 3., 4.])
+    r, db = gpu_consolidate(ctx, a, (0, 1))
+    assert r.idx[0].tolist() == [0, 0, big] and r.idx[1].tolist() == [0, big, big] and r.val.tolist() == [4., 2., 4.]
+    # out-of-bounds index is an error, like VectorCooArray::add (VectorCooArray.hpp:245-262)
+    A = sp.CooArray.from_host(ctx, (4, 4), [[1, 4], [1, 1]], [1., 1.])
+    with pytest.raises(sp.SpbError):
+        sp.consolidate(ctx, A, (0, 1))
+    # dim_beginnings on an unsorted array is an error (algorithm.hpp:82-84)
+    with pytest.raises(sp.SpbError) as e:
+        A.dim_beginnings()
+    assert e.value.code == 4
+    A.free()
+
+
+def test_config2_family_known_answer(ctx):
+    """Reduced-size member of BASELINE config 2; known answer from the genuine reference."""
+    import spsparse_b200 as sp
+    z = np.load(_golden.os.path.join(_golden.HERE, "golden", "config2_small.npz"))
+    A = sp.gen_dup_coo(ctx, 0x5EED0002, 0, 300000, 210000, 12, 1024)
+    R = sp.consolidate(ctx, A, (0, 1))
+    idx, val = R.to_host()
+    assert len(val) == int(z["nnz"])
+    w = np.arange(1, len(val) + 1, dtype=np.uint64)
+    assert [int((w * x.astype(np.uint64)).sum()) for x in idx] == [int(c) for c in z["chk"]]
+    assert np.array_equal(idx[0][::64], z["idx0"]) and np.array_equal(val[::64], z["val"])
+    A.free(); R.free()
+
+
+def test_device_generator_matches_cpu(ctx, orc):
+    import spsparse_b200 as sp
+    from spsparse_b200 import gen
+    A = sp.gen_dup_coo(ctx, 77, 1000, 50000, 30000, 10, 64)
+    idx, val = A.to_host()
+    want = orc.gen_dup_coo(77, 1000, 50000, 30000, 10, 64)
+    npv = gen.dup_coo(77, 1000, 50000, 30000, 10, 64)
+    for k in range(2):
+        assert np.array_equal(idx[k], want.idx[k]) and np.array_equal(idx[k], npv[1][k])
+    assert np.array_equal(val, want.val) and np.array_equal(val, npv[2])
+    A.free()
+    for name, dev, host in (("banded", sp.gen_banded(ctx, 5, 1000, 100, 700), gen.banded(5, 1000, 100, 700)),
+                            ("regrid", sp.gen_regrid(ctx, 6, 32, 25, 10, 10), gen.regrid(6, 32, 25, 10, 10)),
+                            ("rmat", sp.gen_rmat(ctx, 7, 10, 5000), gen.rmat(7, 10, 5000)),
+                            ("vector", sp.gen_vector(ctx, 8, 333), gen.vector(8, 333))):
+        idx, val = dev.to_host()
+        assert dev.shape == tuple(host[0]), name
+        for k in range(len(idx)):
+            assert np.array_equal(idx[k], host[1][k]), name
+        assert np.array_equal(val, host[2]), name
+        dev.free()
+
+
+def test_properties_at_scale(ctx):
+    """2^24-entry member of config 2 (too big for the oracle in a unit test): sortedness, uniqueness,
+    idempotence, count and value-sum conservation."""
+    import spsparse_b200 as sp
+    n, ub = 1 << 24, int(0.7 * (1 << 24))
+    A = sp.gen_dup_coo(ctx, 0x5EED0002, 0, n, ub, 24, 0)
+    R, st = sp.consolidate(ctx, A, (0, 1), stats=True)
+    idx, val = R.to_host()
+    _, aval = A.to_host()
+    key = (idx[0].astype(np.int64) << 24) | idx[1]
+    assert np.all(np.diff(key) > 0)                      # strictly ascending => sorted and unique
+    assert st.n_in == n and st.n_kept == n and st.n_out == len(val)
+    assert abs(val.sum() - aval.sum()) <= 1e-9 * aval.sum()
+    assert ub - 64 <= len(val) <= ub                     # ~ub distinct tuples (a few random collisions)
+    R2 = sp.consolidate(ctx, R, (0, 1))                   # idempotent
+    idx2, val2 = R2.to_host()
+    assert np.array_equal(idx2[0], idx[0]) and np.array_equal(idx2[1], idx[1]) and np.array_equal(val2, val)
+    Rc = sp.consolidate(ctx, A, (1, 0))                   # the other order holds the same multiset
+    idxc, valc = Rc.to_host()
+    keyc = (idxc[1].astype(np.int64) << 24) | idxc[0]
+    assert np.all(np.diff(keyc) > 0)
+    o = np.argsort((idxc[0].astype(np.int64) << 24) | idxc[1], kind="stable")
+    assert np.array_equal(idxc[0][o], idx[0]) and np.array_equal(idxc[1][o], idx[1]) and np.array_equal(valc[o], val)
+    for x in (A, R, R2, Rc):
+        x.free()

@@ -1,0 +1,200 @@
+"""-m gpu parity tests for multiply (matrix*matrix and matrix*vector) through the C ABI."""
+import numpy as np
+import pytest
+
+import _cases
+import _golden
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import spsparse_b200 as sp
+    with sp.Context(0) as c:
+        yield c
+
+
+def gpu_mm(ctx, Cst, si, A, tA, sj, B, tB, sk, pol=O.ADD, zn=False):
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    hs = [up(ctx, x) for x in (si, A, sj, B, sk)]
+    R = sp.multiply(ctx, Cst, hs[0], hs[1], tA, hs[2], hs[3], tB, hs[4], pol, zn)
+    out = down(R)
+    for h in hs + [R]:
+        if h is not None:
+            h.free()
+    return out
+
+
+def gpu_mv(ctx, Cst, si, A, tA, sj, V, pol=O.ADD, zn=False):
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    hs = [up(ctx, x) for x in (si, A, sj, V)]
+    R = sp.multiply(ctx, Cst, hs[0], hs[1], tA, hs[2], hs[3], duplicate_policy=pol, zero_nan=zn)
+    out = down(R)
+    for h in hs + [R]:
+        if h is not None:
+            h.free()
+    return out
+
+
+# tests/test_multiply_sparse.cpp:41-79 (disabled in the reference, verified against it)
+def test_scaled_known_answer(ctx):
+    row = O.Coo((2, 10), [[0, 0, 0, 0, 1], [8, 4, 0, 3, 8]], [6., 4., 2., 3., 3.])
+    scale = O.Coo((10,), [[0, 4, 8]], [2., 4., 4.], (0,))
+    col = O.Coo((10, 1), [[0, 3, 8], [0, 0, 0]], [2., 3., 5.])
+    eye = O.Coo((10,), [np.arange(10)], np.ones(10), (0,))
+    r = gpu_mm(ctx, 1.0, eye, row, ".", scale, col, ".", eye)
+    assert r.shape == (2, 1) and r.sort_order is None  # left in edit mode like the reference
+    assert r.idx[0].tolist() == [0, 1] and r.idx[1].tolist() == [0, 0] and r.val.tolist() == [128., 60.]
+
+
+# tests/test_multiply_sparse.cpp:84-136, :138-203 -- BASELINE config 1, seeds 1..999
+def test_reference_random_tests(ctx):
+    p = _golden.pack("reference_random_tests")
+    eye = O.Coo((5,), [np.arange(5)], np.ones(5), (0,))
+    for seed in range(1, 1000, 1 if _golden.os.environ.get("SPB_FULL_TESTS") else 3):
+        A, B, Cg = (_golden.get_coo(p, f"mm{seed}_{x}") for x in "ABC")
+        got = gpu_mm(ctx, 1.0, None, A, ".", eye, B, ".", None)
+        assert _cases.same_coo(got, Cg), f"MM seed {seed}"
+        A, V, Cg = (_golden.get_coo(p, f"mv{seed}_{x}") for x in "AVC")
+        assert _cases.same_coo(gpu_mv(ctx, 1.0, None, A, ".", None, V), Cg), f"MV seed {seed}"
+
+
+def test_mm_fixtures_from_the_reference(ctx):
+    p = _golden.pack("multiply_mm_cases")
+    for s in range(int(p["count"])):
+        si, A, sj, B, sk, want = (_golden.get_coo(p, f"m{s}_{x}") for x in ("si", "A", "sj", "B", "sk", "out"))
+        Cst, tA, tB, pol, zn = p[f"m{s}_args"]
+        got = gpu_mm(ctx, float(Cst), si, A, chr(int(tA)), sj, B, chr(int(tB)), sk, int(pol), int(zn))
+        assert _cases.same_coo(got, want), f"mm case {s}"
+
+
+def test_mv_fixtures_from_the_reference(ctx):
+    p = _golden.pack("multiply_mv_cases")
+    for s in range(int(p["count"])):
+        si, A, sj, V, want = (_golden.get_coo(p, f"v{s}_{x}") for x in ("si", "A", "sj", "V", "out"))
+        Cst, tA, pol, zn = p[f"v{s}_args"]
+        got = gpu_mv(ctx, float(Cst), si, A, chr(int(tA)), sj, V, int(pol), int(zn))
+        assert _cases.same_coo(got, want), f"mv case {s}"
+
+
+def test_mm_against_oracle_fresh_seeds(ctx, orc):
+    for s in range(2000, 2080):
+        c = _cases.mm_case(s, big=(s % 4 == 0))
+        args = (c["C"], c["si"], c["A"], c["tA"], c["sj"], c["B"], c["tB"], c["sk"], c["policy"], c["zero_nan"])
+        assert _cases.same_coo(gpu_mm(ctx, *args), orc.multiply_mm(*args)), s
+
+
+def test_errors_and_empties(ctx):
+    import spsparse_b200 as sp
+    A = O.Coo((2, 3), [[0], [0]], [1.])
+    B = O.Coo((2, 2), [[0], [0]], [1.])
+    with pytest.raises(sp.SpbError) as e:  # multiply_sparse.hpp:172-174
+        gpu_mm(ctx, 1.0, None, A, ".", None, B, ".", None)
+    assert e.value.code == 3
+    B = O.Coo((3, 2), [[0], [0]], [1.])
+    empty = O.Coo((2, 3), [[], []], [])
+    assert gpu_mm(ctx, 0.0, None, A, ".", None, B, ".", None).n == 0        # C == 0  (:178)
+    r = gpu_mm(ctx, 1.0, None, empty, ".", None, B, ".", None)                # empty A
+    assert r.n == 0 and r.shape == (2, 2)
+    assert gpu_mm(ctx, 1.0, O.Coo((2,), [[]], [], (0,)), A, ".", None, B, ".", None).n == 0  # empty scale
+    allzero = O.Coo((2, 3), [[0, 1], [0, 2]], [0., 0.])                        # consolidates to nothing
+    assert gpu_mm(ctx, 1.0, None, allzero, ".", None, B, ".", None).n == 0
+
+
+def _esc_env(monkeypatch, merge_max, chunk):
+    monkeypatch.setenv("SPB_MERGE_MAX_PRODUCTS", str(merge_max))
+    monkeypatch.setenv("SPB_ESC_CHUNK", str(chunk))
+
+
+def test_expand_sort_compress_path(orc, monkeypatch):
+    """Force every row through expand-sort-compress (and through several chunks): same answers."""
+    import spsparse_b200 as sp
+    _esc_env(monkeypatch, 0, 37)
+    with sp.Context(0) as c2:
+        for s in list(range(2100, 2130)) + [2400, 2404]:
+            c = _cases.mm_case(s, big=(s % 4 == 0))
+            args = (c["C"], c["si"], c["A"], c["tA"], c["sj"], c["B"], c["tB"], c["sk"], c["policy"], c["zero_nan"])
+            assert _cases.same_coo(gpu_mm(c2, *args), orc.multiply_mm(*args)), s
+
+
+def test_mixed_bins_medium(orc, monkeypatch):
+    """A few thousand rows with a handful of heavy rows: merge rows and ESC rows interleave."""
+    import spsparse_b200 as sp
+    rng = np.random.default_rng(11)
+    m, nj, nk = 3000, 2500, 2000
+    n = 12000
+    ai, aj = rng.integers(0, m, n), rng.integers(0, nj, n)
+    heavy = rng.choice(m, 5, replace=False)
+    ai = np.concatenate([ai, np.repeat(heavy, 300)]); aj = np.concatenate([aj, rng.integers(0, nj, 1500)])
+    A = O.Coo((m, nj), [ai, aj], 0.5 + rng.random(len(ai)))
+    nb = 15000
+    B = O.Coo((nj, nk), [rng.integers(0, nj, nb), rng.integers(0, nk, nb)], 0.5 + rng.random(nb))
+    sj = O.Coo((nj,), [np.arange(nj)], 0.5 + rng.random(nj), (0,))
+    want, st = orc.multiply_mm(1.0, None, A, ".", sj, B, ".", None, want_stats=True)
+    _esc_env(monkeypatch, 64, 5000)
+    with sp.Context(0) as c2:
+        from _gpu import up, down
+        hs = [up(c2, x) for x in (A, sj, B)]
+        R, gst = sp.multiply(c2, 1.0, None, hs[0], ".", hs[1], hs[2], ".", None, stats=True)
+        got = down(R)
+        assert gst.products == st["F"] and gst.nnz_a == st["nnzA"] and gst.nnz_b == st["nnzB"]
+        assert gst.rows_esc > 0 and gst.rows_merge > 0
+        assert _cases.same_coo(got, want)
+        # transposed route: (A*diag(sj)*B)^T == B^T * diag(sj) * A^T ; same multiset of entries
+        Rt = sp.multiply(c2, 1.0, None, hs[2], "T", hs[1], hs[0], "T", None)
+        gt = down(Rt)
+        o = np.lexsort((gt.idx[0], gt.idx[1]))
+        assert np.array_equal(gt.idx[1][o], got.idx[0]) and np.array_equal(gt.idx[0][o], got.idx[1])
+        assert np.allclose(gt.val[o], got.val, rtol=1e-12, atol=0)  # different summation order: 1e-12 relative
+        for h in hs + [R, Rt]:
+            h.free()
+
+
+def test_regrid_and_banded_families_small(ctx, orc):
+    """Reduced-size members of BASELINE configs 3 and 5 against the CPU oracle."""
+    import spsparse_b200 as sp
+    from spsparse_b200 import gen
+    from _gpu import down
+    # config 3: A (ny*nx x gy*gx), C = A diag(s) A^T
+    shp, idx, val = gen.regrid(0x5EED0003, 64, 50, 20, 16)
+    s = gen.vector(0x5EED0013, shp[1])
+    A = O.Coo(shp, idx, val)
+    S = O.Coo(s[0], s[1], s[2], (0,))
+    want, st = orc.multiply_mm(1.0, None, A, ".", S, A, "T", None, want_stats=True)
+    dA = sp.gen_regrid(ctx, 0x5EED0003, 64, 50, 20, 16)
+    dS = sp.gen_vector(ctx, 0x5EED0013, shp[1])
+    R, gst = sp.multiply(ctx, 1.0, None, dA, ".", dS, dA, "T", None, stats=True)
+    assert _cases.same_coo(down(R), want)
+    assert gst.products == st["F"] and gst.nnz_c == want.n
+    for h in (dA, dS, R):
+        h.free()
+    # config 5: pentadiagonal A diag(w) B
+    m = 5000
+    a = gen.banded(0x5EED0005, m, 0, m); b = gen.banded(0x5EED0015, m, 0, m); w = gen.vector(0x5EED0025, m)
+    want, st = orc.multiply_mm(1.0, None, O.Coo(*a), ".", O.Coo(w[0], w[1], w[2], (0,)), O.Coo(*b), ".", None, want_stats=True)
+    dA, dB, dW = sp.gen_banded(ctx, 0x5EED0005, m, 0, m), sp.gen_banded(ctx, 0x5EED0015, m, 0, m), sp.gen_vector(ctx, 0x5EED0025, m)
+    R, gst = sp.multiply(ctx, 1.0, None, dA, ".", dW, dB, ".", None, stats=True)
+    assert _cases.same_coo(down(R), want)
+    assert gst.products == st["F"]
+    assert want.n == 9 * m - 20
+    for h in (dA, dB, dW, R):
+        h.free()
+
+
+def test_rmat_family_small(ctx, orc):
+    """Reduced-size member of BASELINE config 4 (skewed rows: both bins in use)."""
+    import spsparse_b200 as sp
+    from spsparse_b200 import gen
+    from _gpu import down
+    shp, idx, val = gen.rmat(0x5EED0004, 12, 4 << 12)
+    A = O.Coo(shp, idx, val)
+    want, st = orc.multiply_mm(1.0, None, A, ".", None, A, ".", None, want_stats=True)
+    dA = sp.gen_rmat(ctx, 0x5EED0004, 12, 4 << 12)
+    R, gst = sp.multiply(ctx, 1.0, None, dA, ".", None, dA, ".", None, stats=True)
+    assert gst.products == st["F"] and gst.rows_esc > 0 and gst.rows_merge > 0
+    assert _cases.same_coo(down(R), want)
+    dA.free(); R.free()
