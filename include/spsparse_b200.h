@@ -53,6 +53,8 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out);
 int spb_ctx_destroy(spb_ctx *ctx);
 int spb_ctx_sync(spb_ctx *ctx);
 int spb_ctx_device(const spb_ctx *ctx, int *device, void **cuda_stream);
+/* kernels launched through this context so far (measurement aid) */
+int spb_ctx_launch_count(const spb_ctx *ctx, uint64_t *launches);
 
 /* ---- COO arrays  (VectorCooArray, VectorCooArray.hpp:8-158) ---------------------------- */
 /* sort_order: NULL or {-1,..} = unsorted/edit mode; else the order the data is ALREADY sorted
@@ -80,6 +82,7 @@ typedef struct {
     uint64_t n_in, n_kept, n_out; /* entries in, after the input-zero drop, after merging */
     int key_bits, passes;         /* significant key bits, 8-bit radix passes run */
     float ms_total, ms_sort, ms_reduce;
+    float ms_pass; /* mean duration of one radix scatter pass (passes after the first), 0 if only one */
 } spb_consolidate_stats;
 int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int policy, int zero_nan,
                     spb_coo **out, spb_consolidate_stats *stats /* may be NULL */);

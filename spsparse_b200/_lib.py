@@ -18,7 +18,8 @@ vp = C.c_void_p
 class ConsolidateStats(C.Structure):
     _fields_ = [("n_in", C.c_uint64), ("n_kept", C.c_uint64), ("n_out", C.c_uint64),
                 ("key_bits", C.c_int), ("passes", C.c_int),
-                ("ms_total", C.c_float), ("ms_sort", C.c_float), ("ms_reduce", C.c_float)]
+                ("ms_total", C.c_float), ("ms_sort", C.c_float), ("ms_reduce", C.c_float),
+                ("ms_pass", C.c_float)]
 
 
 class MMStats(C.Structure):
@@ -40,6 +41,7 @@ SIGNATURES = {
     "spb_ctx_destroy": (C.c_int, [vp]),
     "spb_ctx_sync": (C.c_int, [vp]),
     "spb_ctx_device": (C.c_int, [vp, intp, C.POINTER(vp)]),
+    "spb_ctx_launch_count": (C.c_int, [vp, u64p]),
     "spb_coo_upload": (C.c_int, [vp, C.c_int, u64p, C.POINTER(i32p), f64p, C.c_uint64, intp, C.POINTER(vp)]),
     "spb_coo_wrap_device": (C.c_int, [vp, C.c_int, u64p, C.POINTER(vp), vp, C.c_uint64, intp, C.POINTER(vp)]),
     "spb_coo_alloc": (C.c_int, [vp, C.c_int, u64p, C.c_uint64, C.POINTER(vp)]),

@@ -114,10 +114,17 @@ class CooArray:
         check(self.ctx.lib.spb_coo_device_ptrs(self.h, idx, C.byref(val)))
         return [idx[k] for k in range(self.rank)], val.value
 
-    def to_host(self):
+    def to_host(self, out=None):
+        """Copies the entries to the host.  ``out=(idx_arrays, val_array)`` reuses caller buffers
+        (e.g. pinned memory); they must be contiguous, int32 / float64, of exactly size() entries."""
         rank, shape, n, _ = self._info()
-        idx = [np.empty(n, dtype=np.int32) for _ in range(rank)]
-        val = np.empty(n, dtype=np.float64)
+        if out is not None:
+            idx, val = out
+            assert all(a.dtype == np.int32 and a.flags.c_contiguous and a.shape[0] == n for a in idx)
+            assert val.dtype == np.float64 and val.flags.c_contiguous and val.shape[0] == n
+        else:
+            idx = [np.empty(n, dtype=np.int32) for _ in range(rank)]
+            val = np.empty(n, dtype=np.float64)
         ptrs = (_lib.i32p * rank)(*[a.ctypes.data_as(_lib.i32p) for a in idx])
         check(self.ctx.lib.spb_coo_download(self.ctx.h, self.h, ptrs, val.ctypes.data_as(_lib.f64p)))
         return idx, val

@@ -37,6 +37,7 @@ struct spb_ctx {
     int sm_count;
     u32 merge_max_products;  // bin threshold, env SPB_MERGE_MAX_PRODUCTS
     u64 esc_chunk;           // products per expand-sort-compress chunk, env SPB_ESC_CHUNK
+    u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
 };
 
 struct spb_coo {
@@ -138,6 +139,7 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     c->merge_max_products = s ? (u32)strtoul(s, nullptr, 10) : 1024u;
     s = getenv("SPB_ESC_CHUNK");
     c->esc_chunk = s ? strtoull(s, nullptr, 10) : (1ull << 27);
+    c->launches = 0;
     if (c->esc_chunk < 1) c->esc_chunk = 1;
     *out = c;
     return SPB_OK;
@@ -155,6 +157,12 @@ int spb_ctx_destroy(spb_ctx *ctx) {
 int spb_ctx_sync(spb_ctx *ctx) {
     if (!ctx) return spb_fail(SPB_ERR_ARG, "null context");
     CK(cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+
+int spb_ctx_launch_count(const spb_ctx *ctx, uint64_t *launches) {
+    if (!ctx || !launches) return spb_fail(SPB_ERR_ARG, "null argument");
+    *launches = ctx->launches;
     return SPB_OK;
 }
 
@@ -291,7 +299,7 @@ struct SortJob {
 // the sorted data ends up in *keys_sorted / *vals_sorted (one of the two buffer pairs).
 static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passes, u32 n_cap, const u32 *n_ptr,
                             u32 *hist, u64 *kA, double *vA, u64 *kB, double *vB, const SortInput *in0,
-                            u64 **keys_sorted, double **vals_sorted) {
+                            u64 **keys_sorted, double **vals_sorted, Timer *tm, int *mark_after_first) {
     const u32 tiles = (u32)div_up(n_cap ? n_cap : 1, RS_TILE);
     u32 *lookback, *tickets;
     CKR(ws.zeroed(&lookback, (u64)passes * tiles * RS_RADIX));
@@ -308,13 +316,14 @@ static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passe
         if (p == 0 && first_pass == 0) {
             // pass 0 reads the caller's arrays and writes buffer A
             a.keys_in = nullptr; a.vals_in = nullptr; a.keys_out = kA; a.vals_out = vA;
-            k_radix_pass<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            ++ctx->launches, k_radix_pass<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
             kin = kA; vin = vA; kout = kB; vout = vB;
+            if (tm) *mark_after_first = tm->mark();
         } else {
             a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
             SortInput dummy;
             memset(&dummy, 0, sizeof dummy);
-            k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            ++ctx->launches, k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
             u64 *tk = kin; kin = kout; kout = tk;
             double *tv = vin; vin = vout; vout = tv;
         }
@@ -350,11 +359,11 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     in0.first_kept = first_kept;
     const u32 sgrid = (u32)ctx->sm_count * 4;
     if (in.drop_nan) {
-        k_first_kept_key<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
-        k_first_kept_pos<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
+        ++ctx->launches, k_first_kept_key<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
+        ++ctx->launches, k_first_kept_pos<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
     }
-    k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, hist, counters);
-    k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
+    ++ctx->launches, k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, hist, counters);
+    ++ctx->launches, k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
     CK(cudaGetLastError());
 
     u64 *kA, *kB = nullptr, *ks;
@@ -362,7 +371,8 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     CKR(ws.get(&kA, n));
     CKR(ws.get(&vA, n));
     if (passes > 1) { CKR(ws.get(&kB, n)); CKR(ws.get(&vB, n)); }
-    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs));
+    int t_p0 = t0;
+    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs, &tm, &t_p0));
     const int t1 = tm.mark();
 
     const u32 rtiles = (u32)div_up(n, RK_TILE);
@@ -375,9 +385,9 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     ra.long_cap = n / RK_LONG_RUN + 1;
     CKR(ws.get(&ra.long_list, 2ull * ra.long_cap));
     ra.long_count = counters + 3;
-    k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
+    ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
     if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
-        k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
+        ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
     CK(cudaGetLastError());
     const int t2 = tm.mark();
 
@@ -391,6 +401,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         st->n_in = n; st->n_kept = h[0]; st->n_out = h[2];
         st->key_bits = key_bits; st->passes = passes;
         st->ms_sort = tm.ms(t0, t1); st->ms_reduce = tm.ms(t1, t2); st->ms_total = tm.ms(t0, t2);
+        st->ms_pass = passes > 1 ? tm.ms(t_p0, t1) / (float)(passes - 1) : 0.f;
     }
     return 0;
 }
@@ -458,8 +469,8 @@ static int build_row_index(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, RowI
     CKR(ws.zeroed(&count, 1));
     CKR(ws.zeroed(&ticket, 1));
     CKR(ws.zeroed(&state, tiles));
-    if (n) k_row_heads<<<tiles, RH_THREADS, 0, ctx->stream>>>(hi, n, ri->start, ri->id, count, state, ticket);
-    k_row_sentinel<<<1, 1, 0, ctx->stream>>>(ri->start, count, n);
+    if (n) ++ctx->launches, k_row_heads<<<tiles, RH_THREADS, 0, ctx->stream>>>(hi, n, ri->start, ri->id, count, state, ticket);
+    ++ctx->launches, k_row_sentinel<<<1, 1, 0, ctx->stream>>>(ri->start, count, n);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&ri->nrows, count, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -475,7 +486,7 @@ static int exclusive_scan(spb_ctx *ctx, Scratch &ws, const InT *in, OutT *out, u
     u32 *ticket;
     CKR(ws.zeroed(&state, tiles));
     CKR(ws.zeroed(&ticket, 1));
-    k_exclusive_scan<InT, OutT><<<tiles, SC_THREADS, 0, ctx->stream>>>(in, out, n, state, ticket);
+    ++ctx->launches, k_exclusive_scan<InT, OutT><<<tiles, SC_THREADS, 0, ctx->stream>>>(in, out, n, state, ticket);
     CK(cudaGetLastError());
     return 0;
 }
@@ -489,7 +500,7 @@ static int build_dense_ptr(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, u64 
     CKR(ws.get(&ptr, extent + 2));
     CKR(ws.get(&cnt, 1));
     CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    if (ri.nrows) k_scatter_row_len<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, len);
+    if (ri.nrows) ++ctx->launches, k_scatter_row_len<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, len);
     CKR((exclusive_scan<u32, u32>(ctx, ws, len, ptr, extent)));
     CK(cudaStreamSynchronize(ctx->stream));  // &ri.nrows (host) was read by the async copy above
     ws.release(ri.start); ws.release(ri.id); ws.release(len);
@@ -500,7 +511,7 @@ static int build_dense_ptr(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, u64 
 static int densify(spb_ctx *ctx, Scratch &ws, const spb_coo *v, u64 dim, double **dense, unsigned char **mask) {
     CKR(ws.zeroed(dense, dim));
     if (mask) CKR(ws.zeroed(mask, dim));
-    if (v->n) k_densify<<<grid_for(v->n, 256, 1u << 16), 256, 0, ctx->stream>>>(v->idx[0], v->val, v->n, dim, *dense, mask ? *mask : nullptr);
+    if (v->n) ++ctx->launches, k_densify<<<grid_for(v->n, 256, 1u << 16), 256, 0, ctx->stream>>>(v->idx[0], v->val, v->n, dim, *dense, mask ? *mask : nullptr);
     CK(cudaGetLastError());
     return 0;
 }
@@ -517,8 +528,8 @@ static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key
     CKR(ws.zeroed(&hist, (u64)passes * RS_RADIX));
     CKR(ws.zeroed(&counters, 8));
     CK(cudaMemcpyAsync(counters, &count, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    k_keys_hist<<<grid_for(count, 512, (u32)ctx->sm_count * 4), 512, 0, ctx->stream>>>(kA, count, passes, hist);
-    k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
+    ++ctx->launches, k_keys_hist<<<grid_for(count, 512, (u32)ctx->sm_count * 4), 512, 0, ctx->stream>>>(kA, count, passes, hist);
+    ++ctx->launches, k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
     u64 *kB, *ks;
     double *vB, *vs;
     CKR(ws.get(&kB, count));
@@ -541,7 +552,7 @@ static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key
             a.lookback = lookback + (u64)p * tiles * RS_RADIX;
             a.ticket = tickets + p;
             a.shift = p * RS_RADIX_BITS;
-            k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            ++ctx->launches, k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
             u64 *tk = kin; kin = kout; kout = tk;
             double *tv = vin; vin = vout; vout = tv;
         }
@@ -556,7 +567,7 @@ static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key
     CKR(ws.zeroed(&ra.state, rtiles));
     CKR(ws.zeroed(&ra.ticket, 1));
     ra.row_ids = m.arow_id; ra.row_base = (i32)row_lo; ra.si = m.si; ra.sk = m.sk; ra.C = m.C;
-    k_reduce_by_key<MODE_ESC><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
+    ++ctx->launches, k_reduce_by_key<MODE_ESC><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_out, counters + 2, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -602,16 +613,16 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
     CKR(ws.zeroed(&stats, 4));
     const u32 cap = (u32)ctx->sm_count * 32;
-    k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
+    ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
     CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
-    k_row_bins<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, ctx->merge_max_products, row_cls, esc_f, stats);
+    ++ctx->launches, k_row_bins<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, ctx->merge_max_products, row_cls, esc_f, stats);
     CK(cudaGetLastError());
     ull h_stats[4];
     CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ws.release(ent_f);
 
-    if (h_stats[1]) k_merge_rows<false><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, nullptr, nullptr, nullptr, nullptr);
+    if (h_stats[1]) ++ctx->launches, k_merge_rows<false><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, nullptr, nullptr, nullptr, nullptr);
     CK(cudaGetLastError());
 
     // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
@@ -627,7 +638,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         u64 *pb;
         CKR(ws.get(&rb, (u64)nchunks + 1));
         CKR(ws.get(&pb, (u64)nchunks + 1));
-        k_esc_chunks<<<(u32)div_up((u64)nchunks + 1, 128), 128, 0, ctx->stream>>>(esc_off, nrows, ctx->esc_chunk, nchunks, rb, pb);
+        ++ctx->launches, k_esc_chunks<<<(u32)div_up((u64)nchunks + 1, 128), 128, 0, ctx->stream>>>(esc_off, nrows, ctx->esc_chunk, nchunks, rb, pb);
         CK(cudaGetLastError());
         std::vector<u32> h_rb(nchunks + 1);
         std::vector<u64> h_pb(nchunks + 1);
@@ -649,7 +660,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
             double *t_v;
             CKR(ws.get(&kA, cnt)); CKR(ws.get(&vA, cnt));
             CKR(ws.get(&t_row, cnt)); CKR(ws.get(&t_k, cnt)); CKR(ws.get(&t_v, cnt));
-            k_esc_expand<<<grid_for(cnt, 256, cap), 256, 0, ctx->stream>>>(m, esc_off, ent_off, r_lo, r_hi, h_pb[c], cnt, kbits, kA, vA);
+            ++ctx->launches, k_esc_expand<<<grid_for(cnt, 256, cap), 256, 0, ctx->stream>>>(m, esc_off, ent_off, r_lo, r_hi, h_pb[c], cnt, kbits, kA, vA);
             CK(cudaGetLastError());
             u32 nout = 0;
             CKR(esc_sort_reduce(ctx, kA, vA, cnt, key_bits, kbits, m, r_lo, t_row, t_k, t_v, &nout));
@@ -662,8 +673,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
                 CK(cudaMemcpyAsync(ch.row, t_row, nout * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
                 CK(cudaMemcpyAsync(ch.k, t_k, nout * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
                 CK(cudaMemcpyAsync(ch.v, t_v, nout * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-                k_esc_row_spans<<<grid_for(nout, 256, cap), 256, 0, ctx->stream>>>(ch.row, nout, esc_first, row_cnt);
-                k_esc_row_counts<<<grid_for(nout, 256, cap), 256, 0, ctx->stream>>>(ch.row, nout, esc_first, row_cnt);
+                ++ctx->launches, k_esc_row_spans<<<grid_for(nout, 256, cap), 256, 0, ctx->stream>>>(ch.row, nout, esc_first, row_cnt);
+                ++ctx->launches, k_esc_row_counts<<<grid_for(nout, 256, cap), 256, 0, ctx->stream>>>(ch.row, nout, esc_first, row_cnt);
             }
             ws.release(t_row); ws.release(t_k); ws.release(t_v);
             chunks.push_back(ch);
@@ -689,9 +700,9 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     out->owned = true;
     out->n = nnz_c;
     if (h_stats[1] && nnz_c)
-        k_merge_rows<true><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, c_ptr, out->idx[0], out->idx[1], out->val);
+        ++ctx->launches, k_merge_rows<true><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, c_ptr, out->idx[0], out->idx[1], out->val);
     for (auto &ch : chunks)
-        if (ch.n) k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
+        if (ch.n) ++ctx->launches, k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
     CK(cudaGetLastError());
     const int t_num = tm.mark();
     CK(cudaStreamSynchronize(ctx->stream));
@@ -875,7 +886,7 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
         if (!rc) rc = ws.get(&slot, (u64)ri.nrows + 1);
         if (!rc) {
             const u32 cap = (u32)ctx->sm_count * 32;
-            k_mv_rows<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(m, vd, vmask, row_val, row_keep);
+            ++ctx->launches, k_mv_rows<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(m, vd, vmask, row_val, row_keep);
             rc = exclusive_scan<unsigned char, u32>(ctx, ws, row_keep, slot, ri.nrows);
             u32 nout = 0;
             if (!rc) {
@@ -890,7 +901,7 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
             }
             if (!rc) {
                 r->n = nout;
-                if (nout) k_mv_emit<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(ri.nrows, ri.id, row_val, row_keep, slot, r->idx[0], r->val);
+                if (nout) ++ctx->launches, k_mv_emit<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(ri.nrows, ri.id, row_val, row_keep, slot, r->idx[0], r->val);
                 if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = spb_fail(SPB_ERR_CUDA, "multiply_mv: %s", cudaGetErrorString(cudaGetLastError()));
             }
         }
@@ -907,7 +918,7 @@ int spb_gen_dup_coo(spb_ctx *ctx, uint64_t seed, uint64_t i0, uint64_t n, uint64
     if (!ctx || !out || bits < 1 || bits > 31 || ubase == 0) return spb_fail(SPB_ERR_ARG, "spb_gen_dup_coo: bad argument");
     const u64 shape[2] = {1ull << bits, 1ull << bits};
     CKR(coo_new(ctx, 2, shape, n, true, out));
-    if (n) k_gen_dup_coo<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, i0, n, ubase, bits, zero_every, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    if (n) ++ctx->launches, k_gen_dup_coo<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, i0, n, ubase, bits, zero_every, (*out)->idx[0], (*out)->idx[1], (*out)->val);
     CK(cudaGetLastError());
     return SPB_OK;
 }
@@ -917,7 +928,7 @@ int spb_gen_banded(spb_ctx *ctx, uint64_t seed, uint64_t mdim, uint64_t r0, uint
     const u64 shape[2] = {mdim, mdim};
     const u64 n = (r1 - r0) * 5;
     CKR(coo_new(ctx, 2, shape, n, true, out));
-    if (n) k_gen_banded<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, mdim, r0, n, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    if (n) ++ctx->launches, k_gen_banded<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, mdim, r0, n, (*out)->idx[0], (*out)->idx[1], (*out)->val);
     CK(cudaGetLastError());
     return SPB_OK;
 }
@@ -927,7 +938,7 @@ int spb_gen_regrid(spb_ctx *ctx, uint64_t seed, uint32_t ny, uint32_t nx, uint32
     const u64 shape[2] = {(u64)ny * nx, (u64)gy * gx};
     const u64 n = shape[0] * 4;
     CKR(coo_new(ctx, 2, shape, n, true, out));
-    k_gen_regrid<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, ny, nx, gy, gx, n, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    ++ctx->launches, k_gen_regrid<<<grid_for(n, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, ny, nx, gy, gx, n, (*out)->idx[0], (*out)->idx[1], (*out)->val);
     CK(cudaGetLastError());
     return SPB_OK;
 }
@@ -936,7 +947,7 @@ int spb_gen_rmat(spb_ctx *ctx, uint64_t seed, int scale, uint64_t nedges, spb_co
     if (!ctx || !out || scale < 1 || scale > 30) return spb_fail(SPB_ERR_ARG, "spb_gen_rmat: bad argument");
     const u64 shape[2] = {1ull << scale, 1ull << scale};
     CKR(coo_new(ctx, 2, shape, nedges, true, out));
-    if (nedges) k_gen_rmat<<<grid_for(nedges, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, scale, nedges, (*out)->idx[0], (*out)->idx[1], (*out)->val);
+    if (nedges) ++ctx->launches, k_gen_rmat<<<grid_for(nedges, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, scale, nedges, (*out)->idx[0], (*out)->idx[1], (*out)->val);
     CK(cudaGetLastError());
     return SPB_OK;
 }
@@ -945,7 +956,7 @@ int spb_gen_vector(spb_ctx *ctx, uint64_t seed, uint64_t dim, spb_coo **out) {
     if (!ctx || !out) return spb_fail(SPB_ERR_ARG, "spb_gen_vector: bad argument");
     const u64 shape[1] = {dim};
     CKR(coo_new(ctx, 1, shape, dim, true, out));
-    if (dim) k_gen_vector<<<grid_for(dim, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, dim, (*out)->idx[0], (*out)->val);
+    if (dim) ++ctx->launches, k_gen_vector<<<grid_for(dim, 256, 1u << 20), 256, 0, ctx->stream>>>(seed, dim, (*out)->idx[0], (*out)->val);
     CK(cudaGetLastError());
     const int so[1] = {0};
     set_order(*out, so);
