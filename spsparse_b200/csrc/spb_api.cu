@@ -8,6 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -30,6 +34,78 @@ int spb_fail(int code, const char *fmt, ...) {
     return code;
 }
 
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static double g_alloc_ms = 0;   // host time spent inside cudaMallocAsync (SPB_TRACE diagnostics)
+static int g_trace = -1;
+static inline bool tracing() {
+    if (g_trace < 0) g_trace = getenv("SPB_TRACE") ? 1 : 0;
+    return g_trace == 1;
+}
+
+// ---- device memory pool ----------------------------------------------------------------------------
+// A size-keyed cache of cudaMalloc'ed blocks.  The hot path asks for the same multi-GB sizes every
+// call; the driver's stream-ordered pool re-maps physical memory for them again and again (20-350 ms
+// per request measured on B200), so blocks are kept here and handed back on an (almost) exact size
+// match.  All use is ordered on the context's single stream, so a freed block can be reused at once.
+struct DevPool {
+    std::multimap<size_t, void *> free_;
+    std::unordered_map<void *, size_t> live_;
+    std::mutex mu_;
+    size_t cached_bytes = 0;
+
+    static size_t round_up(size_t b) {
+        if (b < 512) return 512;
+        if (b < (1u << 20)) return (b + 511) & ~(size_t)511;
+        return (b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+    }
+    cudaError_t alloc(void **out, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu_);
+        const size_t want = round_up(bytes);
+        auto it = free_.lower_bound(want);
+        if (it != free_.end() && it->first <= want + want / 8) {  // at most 12.5% slack
+            *out = it->second;
+            live_[*out] = it->first;
+            cached_bytes -= it->first;
+            free_.erase(it);
+            return cudaSuccess;
+        }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+            cudaGetLastError();
+            trim_locked();
+            e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) return e;
+        }
+        live_[p] = want;
+        *out = p;
+        return cudaSuccess;
+    }
+    void release(void *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu_);
+        auto it = live_.find(p);
+        if (it == live_.end()) return;  // not ours (wrapped caller memory)
+        free_.insert({it->second, p});
+        cached_bytes += it->second;
+        live_.erase(it);
+    }
+    void trim_locked() {
+        cudaDeviceSynchronize();
+        for (auto &kv : free_) cudaFree(kv.second);
+        free_.clear();
+        cached_bytes = 0;
+    }
+    void destroy() {
+        std::lock_guard<std::mutex> g(mu_);
+        trim_locked();
+        for (auto &kv : live_) cudaFree(kv.first);
+        live_.clear();
+    }
+};
+
 struct spb_ctx {
     int device;
     cudaStream_t stream;
@@ -38,6 +114,7 @@ struct spb_ctx {
     u32 merge_max_products;  // bin threshold, env SPB_MERGE_MAX_PRODUCTS
     u64 esc_chunk;           // products per expand-sort-compress chunk, env SPB_ESC_CHUNK
     u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
+    DevPool pool;
 };
 
 struct spb_coo {
@@ -55,13 +132,15 @@ struct Scratch {
     spb_ctx *ctx;
     std::vector<void *> ptrs;
     explicit Scratch(spb_ctx *c) : ctx(c) {}
-    ~Scratch() { for (void *p : ptrs) cudaFreeAsync(p, ctx->stream); }
+    ~Scratch() { for (void *p : ptrs) ctx->pool.release(p); }
     template <typename T>
     int get(T **out, u64 count) {
         void *p = nullptr;
         size_t bytes = (size_t)(count ? count : 1) * sizeof(T);
-        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
-        if (e != cudaSuccess) return spb_fail(SPB_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        double t0 = tracing() ? now_ms() : 0;
+        cudaError_t e = ctx->pool.alloc(&p, bytes);
+        if (tracing()) { double dt = now_ms() - t0; g_alloc_ms += dt; if (dt > 1.0) fprintf(stderr, "[spb] pool.alloc(%zu MB) took %.2f ms\n", bytes >> 20, dt); }
+        if (e != cudaSuccess) return spb_fail(SPB_ERR_CUDA, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         ptrs.push_back(p);
         *out = (T *)p;
         return 0;
@@ -74,7 +153,7 @@ struct Scratch {
     }
     void release(void *p) {  // free early
         for (size_t i = 0; i < ptrs.size(); ++i)
-            if (ptrs[i] == p) { cudaFreeAsync(p, ctx->stream); ptrs.erase(ptrs.begin() + i); return; }
+            if (ptrs[i] == p) { ctx->pool.release(p); ptrs.erase(ptrs.begin() + i); return; }
     }
     void keep(void *p) {  // hand ownership to the caller
         for (size_t i = 0; i < ptrs.size(); ++i)
@@ -128,11 +207,6 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     if (c->own_stream) CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     else c->stream = (cudaStream_t)cuda_stream;
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    // keep freed scratch in the pool: steady-state calls never reach cudaMalloc
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
-    u64 thresh = ~0ull;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     CK(cudaFuncSetAttribute(k_radix_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
     const char *s = getenv("SPB_MERGE_MAX_PRODUCTS");
@@ -149,6 +223,7 @@ int spb_ctx_destroy(spb_ctx *ctx) {
     if (!ctx) return SPB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ctx->pool.destroy();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SPB_OK;
@@ -193,8 +268,8 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     if (allocate) {
         CK(cudaSetDevice(ctx->device));
         size_t cnt = n ? n : 1;
-        for (int k = 0; k < rank; ++k) CK(cudaMallocAsync((void **)&a->idx[k], cnt * sizeof(i32), ctx->stream));
-        CK(cudaMallocAsync((void **)&a->val, cnt * sizeof(double), ctx->stream));
+        for (int k = 0; k < rank; ++k) CK(ctx->pool.alloc((void **)&a->idx[k], cnt * sizeof(i32)));
+        CK(ctx->pool.alloc((void **)&a->val, cnt * sizeof(double)));
     }
     *out = a;
     return SPB_OK;
@@ -277,8 +352,8 @@ int spb_coo_download(spb_ctx *ctx, const spb_coo *a, int32_t *const *idx, double
 int spb_coo_free(spb_ctx *ctx, spb_coo *a) {
     if (!a) return SPB_OK;
     if (a->owned && ctx) {
-        for (int k = 0; k < 2; ++k) if (a->idx[k]) cudaFreeAsync(a->idx[k], ctx->stream);
-        if (a->val) cudaFreeAsync(a->val, ctx->stream);
+        for (int k = 0; k < 2; ++k) if (a->idx[k]) ctx->pool.release(a->idx[k]);
+        if (a->val) ctx->pool.release(a->val);
     }
     delete a;
     return SPB_OK;
@@ -599,6 +674,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     if (sj) { CKR(densify(ctx, ws, sj, n_inner, &d, &mask)); m.sj = d; m.sj_mask = mask; }
     if (sk) { CKR(densify(ctx, ws, sk, n_cols, &d, nullptr)); m.sk = d; }
     const int t_prep = tm.mark();
+    double h0 = now_ms();
+    if (tracing()) fprintf(stderr, "[spb] mm: prepare done (host), alloc so far %.2f ms\n", g_alloc_ms);
 
     // ---- symbolic: products per entry / row, bins, output counts -------------------------------
     const u32 nrows = m.nrows;
@@ -689,14 +766,15 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaMemcpyAsync(&nnz_c, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int t_sym = tm.mark();
+    if (tracing()) fprintf(stderr, "[spb] mm: symbolic host %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (nnz_c >= (1ull << 31))
         return spb_fail(SPB_ERR_TOO_LARGE, "product has %llu entries; a VectorCooArray holds < 2^31 (algorithm.hpp:419)", (ull)nnz_c);
 
     // ---- numeric ------------------------------------------------------------------------------------
     size_t cnt = nnz_c ? nnz_c : 1;
-    CK(cudaMallocAsync((void **)&out->idx[0], cnt * sizeof(i32), ctx->stream));
-    CK(cudaMallocAsync((void **)&out->idx[1], cnt * sizeof(i32), ctx->stream));
-    CK(cudaMallocAsync((void **)&out->val, cnt * sizeof(double), ctx->stream));
+    CK(ctx->pool.alloc((void **)&out->idx[0], cnt * sizeof(i32)));
+    CK(ctx->pool.alloc((void **)&out->idx[1], cnt * sizeof(i32)));
+    CK(ctx->pool.alloc((void **)&out->val, cnt * sizeof(double)));
     out->owned = true;
     out->n = nnz_c;
     if (h_stats[1] && nnz_c)
@@ -706,6 +784,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaGetLastError());
     const int t_num = tm.mark();
     CK(cudaStreamSynchronize(ctx->stream));
+    if (tracing()) fprintf(stderr, "[spb] mm: total host since prepare %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (st) {
         st->products = h_stats[0]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2]; st->products_esc = h_stats[3];
         st->nnz_a = A->n; st->nnz_b = B->n; st->rows_a = nrows; st->nnz_c = nnz_c;
@@ -895,8 +974,8 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
             }
             if (!rc) {
                 size_t cnt = nout ? nout : 1;
-                if (cudaMallocAsync((void **)&r->idx[0], cnt * sizeof(i32), ctx->stream) != cudaSuccess ||
-                    cudaMallocAsync((void **)&r->val, cnt * sizeof(double), ctx->stream) != cudaSuccess)
+                if (ctx->pool.alloc((void **)&r->idx[0], cnt * sizeof(i32)) != cudaSuccess ||
+                    ctx->pool.alloc((void **)&r->val, cnt * sizeof(double)) != cudaSuccess)
                     rc = spb_fail(SPB_ERR_CUDA, "multiply_mv: out of device memory");
             }
             if (!rc) {
