@@ -3,7 +3,7 @@
 // Replaces sorted_permutation + CmpIndex + std::stable_sort (reference slib/spsparse/
 // algorithm.hpp:375-427).  One-sweep organisation: a single histogram kernel counts every 8-bit
 // digit of every pass up front; each pass then reads its input once and writes it once, ranking
-// items inside a 4096-entry tile with warp-level match/ballot multi-split and chaining the tiles'
+// items inside a 4096-entry tile with a warp-level ballot multi-split and chaining the tiles'
 // per-digit counts with a decoupled look-back.  Pass 0 reads the caller's struct-of-arrays COO
 // directly, packs (hi << bits_lo) | lo on the fly and applies consolidate()'s input drop rule
 // (algorithm.hpp:272-275, 284-292), so filtered entries never enter the sort.
@@ -161,6 +161,7 @@ struct PassArgs {
     u32 *lookback;           // [tiles][256], zeroed
     u32 *ticket;             // zeroed
     int shift;               // digit = (key >> shift) & 255
+    int rank_mode;           // 0 ballots, 1 match.any, 2 timing-only fake (experiments; SPB_RANK_MODE)
 };
 
 template <bool PASS0>
@@ -183,40 +184,74 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
     // ---- load (warp-striped: item order inside the tile is (warp, k, lane)) ------------------
     const u64 wbase = tile_base + (u64)warp * (32 * RS_IPT) + lane;
     u64 key[RS_IPT];
-    double val[PASS0 ? RS_IPT : 1];
     u32 valid_bits = 0;
+    if (PASS0) {
+        // two batches of 8 so that at most 8 x (hi, lo, val) loads are in flight per thread; the value
+        // is only tested here (drop rule) and re-read from L2 when it is staged below
 #pragma unroll
-    for (int k = 0; k < RS_IPT; ++k) {
-        u64 i = wbase + (u64)k * 32;
-        bool ok = i < n;
-        if (PASS0) {
-            i32 hi = 0, lo = 0;
-            double v = 0.0;
-            if (ok) {
-                hi = ld_stream_i32(in.hi + i);
-                lo = in.lo ? ld_stream_i32(in.lo + i) : 0;
-                v = ld_stream_f64(in.val + i);
-                ok = ((u32)hi < in.extent_hi) && ((u32)lo < in.extent_lo) && input_kept(in, (u32)i, v);
+        for (int h = 0; h < RS_IPT; h += 8) {
+            i32 hi[8], lo[8];
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                u64 i = wbase + (u64)(h + k) * 32;
+                u64 ic = i < n ? i : (u64)n - 1;  // clamp: loads stay unconditional
+                hi[k] = ld_stream_i32(in.hi + ic);
+                lo[k] = in.lo ? ld_stream_i32(in.lo + ic) : 0;
+                v[k] = in.val[ic];
             }
-            key[k] = pack_key(hi, lo, in.bits_lo);
-            val[k] = v;
-        } else {
-            key[k] = ok ? ld_stream_u64(a.keys_in + i) : 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                u64 i = wbase + (u64)(h + k) * 32;
+                bool ok = (i < n) && ((u32)hi[k] < in.extent_hi) && ((u32)lo[k] < in.extent_lo) &&
+                          input_kept(in, (u32)i, v[k]);
+                key[h + k] = pack_key(hi[k], lo[k], in.bits_lo);
+                valid_bits |= (ok ? 1u : 0u) << (h + k);
+            }
         }
-        valid_bits |= (ok ? 1u : 0u) << k;
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            u64 i = wbase + (u64)k * 32;
+            bool ok = i < n;
+            key[k] = ok ? ld_stream_u64(a.keys_in + i) : 0;
+            valid_bits |= (ok ? 1u : 0u) << k;
+        }
+        // the values are staged after the ranking: pull their lines into L2 now (no registers held)
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            u64 i = wbase + (u64)k * 32;
+            if (i < n && (lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vals_in + i));
+        }
     }
 
-    // ---- rank inside the warp: match-any multi-split, warp-private digit counters ------------
+    // ---- rank inside the warp: ballot multi-split, warp-private digit counters ----------------
+    // (eight VOTEs + logic per item; MATCH.ANY costs ~64 ADU cycles per warp on sm_100 and capped the
+    // pass at ~45% of HBM bandwidth -- see profiles/r01_radix_pass_notes.md)
     u32 *mycnt = s_wcnt + warp * RS_NB;
     const u32 lt = lanemask_lt();
     unsigned short pos[RS_IPT];
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        u32 d = ((valid_bits >> k) & 1u) ? (u32)((key[k] >> a.shift) & (RS_RADIX - 1)) : (u32)RS_RADIX;
-        u32 peers = __match_any_sync(SPB_FULL_MASK, d);
-        u32 leader = __ffs(peers) - 1;
+        const bool ok = (valid_bits >> k) & 1u;
+        const u32 d = (u32)((key[k] >> a.shift) & (RS_RADIX - 1));
+        u32 peers;
+        if (a.rank_mode == 0) {
+            peers = __ballot_sync(SPB_FULL_MASK, ok);
+#pragma unroll
+            for (int b = 0; b < RS_RADIX_BITS; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const u32 m = __ballot_sync(SPB_FULL_MASK, bit);
+                peers &= bit ? m : ~m;
+            }
+        } else if (a.rank_mode == 1) {
+            peers = __match_any_sync(SPB_FULL_MASK, ok ? d : (u32)RS_RADIX);
+        } else {
+            peers = 1u << lane;  // WRONG ranks: timing experiment only
+        }
+        u32 leader = ok ? (u32)(__ffs(peers) - 1) : lane;
         u32 before = 0;
-        if (lane == leader) {
+        if (ok && lane == leader) {
             before = mycnt[d];
             mycnt[d] = before + __popc(peers);
         }
@@ -252,7 +287,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
     __syncthreads();
     const u32 nvalid = s_misc[12];
 
-    // ---- stage keys (and values) in digit order in shared memory ------------------------------
+    // ---- stage keys and values in digit order in shared memory --------------------------------
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
         if ((valid_bits >> k) & 1u) {
@@ -260,15 +295,15 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
             u32 p = mycnt[d] + pos[k];
             pos[k] = (unsigned short)p;
             s_keys[p] = key[k];
-            if (PASS0) s_vals[p] = val[k];
         }
     }
-    if (!PASS0) {
+    {
+        const double *vsrc = PASS0 ? in.val : a.vals_in;
         double v[RS_IPT];
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k) {
             u64 i = wbase + (u64)k * 32;
-            v[k] = ((valid_bits >> k) & 1u) ? ld_stream_f64(a.vals_in + i) : 0.0;
+            v[k] = ((valid_bits >> k) & 1u) ? ld_stream_f64(vsrc + i) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k)
@@ -276,15 +311,25 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
     }
 
     // ---- decoupled look-back, one digit per thread ----------------------------------------------
+    // Four predecessors are read at once: the walk back to the nearest tile with an inclusive prefix
+    // costs one L2 round trip per four hops instead of one per hop.
     u32 excl = 0;
     if (tile > 0) {
-        const u32 *p = lb - RS_RADIX;
-        for (;;) {
-            u32 w;
-            do { w = ld_relaxed_u32(p); } while ((w >> 30) == 0);
-            excl += RS_VALUE(w);
-            if ((w >> 30) == 2) break;
-            p -= RS_RADIX;
+        i64 p = (i64)tile - 1;
+        bool done = false;
+        while (!done) {
+            u32 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                w[u] = (p - u >= 0) ? ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid) : RS_FLAG_INCL;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (done) break;
+                while ((w[u] >> 30) == 0) w[u] = ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid);
+                excl += RS_VALUE(w[u]);
+                if ((w[u] >> 30) == 2) done = true;
+            }
+            p -= 4;
         }
         st_relaxed_u32(lb, RS_FLAG_INCL | (excl + total));
     }

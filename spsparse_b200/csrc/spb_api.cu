@@ -388,6 +388,7 @@ static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passe
         a.lookback = lookback + (u64)p * tiles * RS_RADIX;
         a.ticket = tickets + p;
         a.shift = p * RS_RADIX_BITS;
+        a.rank_mode = getenv("SPB_RANK_MODE") ? atoi(getenv("SPB_RANK_MODE")) : 0;
         if (p == 0 && first_pass == 0) {
             // pass 0 reads the caller's arrays and writes buffer A
             a.keys_in = nullptr; a.vals_in = nullptr; a.keys_out = kA; a.vals_out = vA;
@@ -627,6 +628,8 @@ static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key
             a.lookback = lookback + (u64)p * tiles * RS_RADIX;
             a.ticket = tickets + p;
             a.shift = p * RS_RADIX_BITS;
+            a.rank_mode = 0;
+        a.rank_mode = getenv("SPB_RANK_MODE") ? atoi(getenv("SPB_RANK_MODE")) : 0;
             ++ctx->launches, k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
             u64 *tk = kin; kin = kout; kout = tk;
             double *tv = vin; vin = vout; vout = tv;
@@ -699,7 +702,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaStreamSynchronize(ctx->stream));
     ws.release(ent_f);
 
-    if (h_stats[1]) ++ctx->launches, k_merge_rows<false><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, nullptr, nullptr, nullptr, nullptr);
+    if (h_stats[1]) ++ctx->launches, k_merge_count<<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt);
     CK(cudaGetLastError());
 
     // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
@@ -778,7 +781,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     out->owned = true;
     out->n = nnz_c;
     if (h_stats[1] && nnz_c)
-        ++ctx->launches, k_merge_rows<true><<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt, c_ptr, out->idx[0], out->idx[1], out->val);
+        ++ctx->launches, k_merge_numeric<<<(u32)div_up(nrows, MR_THREADS), MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
     for (auto &ch : chunks)
         if (ch.n) ++ctx->launches, k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
     CK(cudaGetLastError());

@@ -86,48 +86,49 @@ __global__ void k_row_bins(MMOperands m, const u64 *__restrict__ ent_off, u32 me
 }
 
 // ---- short rows: k-way merge in registers, one thread per row -----------------------------------
-// NUMERIC=false counts the outputs (exactly: zero sums and masked columns are not counted);
-// NUMERIC=true writes them at c_off.
-template <int NL, bool NUMERIC>
-__device__ __forceinline__ u32 merge_row(const MMOperands &m, u32 s, u32 len, i32 irow, u64 c_off,
-                                         i32 *c_i, i32 *c_k, double *c_v) {
+// The heads of up to NL column-sorted B rows live in registers; each step takes the smallest head
+// column, sums every list that holds it in list (= ascending j) order and advances those lists.
+template <int NL>
+struct RowMerge {
     u32 cur[NL], end[NL];
     i32 hk[NL];
     double hv[NL], as[NL];
+
+    __device__ __forceinline__ void init(const MMOperands &m, u32 s, u32 len) {
 #pragma unroll
-    for (int l = 0; l < NL; ++l) {
-        cur[l] = end[l] = 0;
-        hk[l] = INT32_MAX;
-        hv[l] = 0.0;
-        as[l] = 0.0;
-        if ((u32)l < len) {
-            i32 j = __ldg(m.a_j + s + l);
-            double a = __ldg(m.a_val + s + l);
-            bool ok = !m.sj_mask || m.sj_mask[j];
-            if (ok) {
-                cur[l] = __ldg(m.bptr + j);
-                end[l] = __ldg(m.bptr + j + 1);
-                as[l] = m.sj ? __dmul_rn(a, __ldg(m.sj + j)) : a;  // (a*s) first, multiply_sparse.hpp:228
-                if (cur[l] < end[l]) {
-                    hk[l] = __ldg(m.b_k + cur[l]);
-                    hv[l] = __ldg(m.b_val + cur[l]);
+        for (int l = 0; l < NL; ++l) {
+            cur[l] = end[l] = 0;
+            hk[l] = INT32_MAX;
+            hv[l] = 0.0;
+            as[l] = 0.0;
+            if ((u32)l < len) {
+                i32 j = __ldg(m.a_j + s + l);
+                double a = __ldg(m.a_val + s + l);
+                bool ok = !m.sj_mask || m.sj_mask[j];
+                if (ok) {
+                    cur[l] = __ldg(m.bptr + j);
+                    end[l] = __ldg(m.bptr + j + 1);
+                    as[l] = m.sj ? __dmul_rn(a, __ldg(m.sj + j)) : a;  // (a*s) first, multiply_sparse.hpp:228
+                    if (cur[l] < end[l]) {
+                        hk[l] = __ldg(m.b_k + cur[l]);
+                        hv[l] = __ldg(m.b_val + cur[l]);
+                    }
                 }
             }
         }
     }
-    double a_scale = 1.0;
-    if (NUMERIC && m.si) a_scale = m.si[irow];
-    u32 count = 0;
-    for (;;) {
+
+    // Next output column and its dot product; false when every list is exhausted.
+    __device__ __forceinline__ bool next(const MMOperands &m, i32 &k, double &sum) {
         i32 kmin = hk[0];
 #pragma unroll
         for (int l = 1; l < NL; ++l) kmin = min(kmin, hk[l]);
-        if (kmin == INT32_MAX) break;
-        double sum = 0.0;  // multiply_sparse.hpp:219
+        if (kmin == INT32_MAX) return false;
+        double acc = 0.0;  // multiply_sparse.hpp:219
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
             if (hk[l] == kmin) {
-                sum = __dadd_rn(sum, __dmul_rn(as[l], hv[l]));
+                acc = __dadd_rn(acc, __dmul_rn(as[l], hv[l]));
                 ++cur[l];
                 if (cur[l] < end[l]) {
                     hk[l] = __ldg(m.b_k + cur[l]);
@@ -137,44 +138,127 @@ __device__ __forceinline__ u32 merge_row(const MMOperands &m, u32 s, u32 len, i3
                 }
             }
         }
-        double b_scale = 1.0;
-        bool keep = (sum != 0.0);  // NaN != 0 -> kept, multiply_sparse.hpp:238
-        if (m.sk) {
-            b_scale = __ldg(m.sk + kmin);
-            keep = keep && (b_scale != 0.0);
-        }
-        if (keep) {
-            if (NUMERIC) {
-                u64 p = c_off + count;
-                c_i[p] = irow;
-                c_k[p] = kmin;
-                c_v[p] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
-            }
-            ++count;
-        }
+        k = kmin;
+        sum = acc;
+        return true;
     }
+};
+
+// keep iff sum != 0 (NaN kept, multiply_sparse.hpp:238) and the column's scale is present and non-zero
+__device__ __forceinline__ bool keep_output(const MMOperands &m, i32 k, double sum, double &b_scale) {
+    b_scale = 1.0;
+    bool keep = (sum != 0.0);
+    if (m.sk) {
+        b_scale = __ldg(m.sk + k);
+        keep = keep && (b_scale != 0.0);
+    }
+    return keep;
+}
+
+// symbolic: exact number of outputs of each short row
+template <int NL>
+__device__ __forceinline__ u32 count_row(const MMOperands &m, u32 s, u32 len) {
+    RowMerge<NL> st;
+    st.init(m, s, len);
+    u32 count = 0;
+    i32 k;
+    double sum, bs;
+    while (st.next(m, k, sum))
+        if (keep_output(m, k, sum, bs)) ++count;
     return count;
 }
 
-template <bool NUMERIC>
-__global__ void __launch_bounds__(128) k_merge_rows(MMOperands m, const unsigned char *__restrict__ row_cls,
-                                                    u32 *row_cnt, const u64 *__restrict__ c_ptr, i32 *c_i,
-                                                    i32 *c_k, double *c_v) {
+__global__ void __launch_bounds__(128) k_merge_count(MMOperands m, const unsigned char *__restrict__ row_cls,
+                                                     u32 *row_cnt) {
     u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= m.nrows) return;
-    if (row_cls[r] != ROW_MERGE) {
-        if (!NUMERIC && row_cls[r] == ROW_SKIP) row_cnt[r] = 0;
-        return;
-    }
+    if (row_cls[r] != ROW_MERGE) return;  // row_cnt is zero-initialised; ESC rows are filled later
     const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
-    const i32 irow = m.arow_id[r];
-    const u64 off = NUMERIC ? c_ptr[r] : 0;
     u32 c;
-    if (len <= 2) c = merge_row<2, NUMERIC>(m, s, len, irow, off, c_i, c_k, c_v);
-    else if (len <= 4) c = merge_row<4, NUMERIC>(m, s, len, irow, off, c_i, c_k, c_v);
-    else if (len <= 6) c = merge_row<6, NUMERIC>(m, s, len, irow, off, c_i, c_k, c_v);
-    else c = merge_row<8, NUMERIC>(m, s, len, irow, off, c_i, c_k, c_v);
-    if (!NUMERIC) row_cnt[r] = c;
+    if (len <= 2) c = count_row<2>(m, s, len);
+    else if (len <= 4) c = count_row<4>(m, s, len);
+    else if (len <= 6) c = count_row<6>(m, s, len);
+    else c = count_row<8>(m, s, len);
+    row_cnt[r] = c;
+}
+
+// numeric: the 32 rows of a warp advance in lock step; outputs are staged per lane in shared memory and
+// flushed as contiguous runs (lane l's run is written by 16 lanes at once), so C is written in full
+// sectors instead of one 4/8-byte store per thread per step.
+constexpr int MR_THREADS = 128;
+constexpr int MR_STAGE = 16;
+constexpr int MR_PITCH = MR_STAGE + 1;
+
+template <int NL>
+__device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, u32 s, u32 len, i32 irow,
+                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v) {
+    const u32 lane = lane_id();
+    RowMerge<NL> st;
+    st.init(m, s, mine ? len : 0);
+    double a_scale = 1.0;
+    if (mine && m.si) a_scale = m.si[irow];
+    u32 cnt = 0;
+    bool active = mine;
+    for (;;) {
+        if (active) {
+            i32 k;
+            double sum, b_scale;
+            if (!st.next(m, k, sum)) active = false;
+            else if (keep_output(m, k, sum, b_scale)) {
+                sk[lane * MR_PITCH + cnt] = k;
+                sv[lane * MR_PITCH + cnt] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
+                ++cnt;
+            }
+        }
+        const bool any_active = __any_sync(SPB_FULL_MASK, active);
+        if (__any_sync(SPB_FULL_MASK, cnt == (u32)MR_STAGE) || !any_active) {
+            __syncwarp();
+#pragma unroll 4
+            for (int l2 = 0; l2 < 16; ++l2) {
+                const int l = 2 * l2 + (int)(lane >> 4);
+                const u32 t = lane & 15;
+                const u32 n_l = __shfl_sync(SPB_FULL_MASK, cnt, l);
+                const u64 d_l = __shfl_sync(SPB_FULL_MASK, dst, l);
+                const i32 i_l = __shfl_sync(SPB_FULL_MASK, irow, l);
+                if (t < n_l) {
+                    c_k[d_l + t] = sk[l * MR_PITCH + t];
+                    c_v[d_l + t] = sv[l * MR_PITCH + t];
+                    c_i[d_l + t] = i_l;
+                }
+            }
+            dst += cnt;
+            cnt = 0;
+            __syncwarp();
+        }
+        if (!any_active) break;
+    }
+}
+
+__global__ void __launch_bounds__(MR_THREADS) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
+                                                              const u64 *__restrict__ c_ptr, i32 *c_i, i32 *c_k,
+                                                              double *c_v) {
+    __shared__ i32 s_k[MR_THREADS * MR_PITCH];
+    __shared__ double s_v[MR_THREADS * MR_PITCH];
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 warp = threadIdx.x >> 5;
+    const bool mine = (r < m.nrows) && (row_cls[r] == ROW_MERGE);
+    u32 s = 0, len = 0;
+    i32 irow = 0;
+    u64 dst = 0;
+    if (mine) {
+        s = m.arow_start[r];
+        len = m.arow_start[r + 1] - s;
+        irow = m.arow_id[r];
+        dst = c_ptr[r];
+    }
+    const u32 maxlen = __reduce_max_sync(SPB_FULL_MASK, len);
+    i32 *sk = s_k + warp * 32 * MR_PITCH;
+    double *sv = s_v + warp * 32 * MR_PITCH;
+    if (maxlen == 0) return;
+    if (maxlen <= 2) merge_rows_warp<2>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (maxlen <= 4) merge_rows_warp<4>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (maxlen <= 6) merge_rows_warp<6>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else merge_rows_warp<8>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
 }
 
 // ---- long rows: expand-sort-compress ------------------------------------------------------------
