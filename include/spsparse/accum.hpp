@@ -1,0 +1,4 @@
+// <spsparse/accum.hpp> -- same include path as the reference; the B200 implementation lives in
+// include/spsparse_b200/accum.hpp.
+#pragma once
+#include "../spsparse_b200/accum.hpp"

@@ -1,0 +1,4 @@
+// <spsparse/algorithm.hpp> -- same include path as the reference; the B200 implementation lives in
+// include/spsparse_b200/algorithm.hpp.
+#pragma once
+#include "../spsparse_b200/algorithm.hpp"

@@ -1,0 +1,4 @@
+// <spsparse/xiter.hpp> -- same include path as the reference; the B200 implementation lives in
+// include/spsparse_b200/xiter.hpp.
+#pragma once
+#include "../spsparse_b200/xiter.hpp"

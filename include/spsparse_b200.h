@@ -87,6 +87,11 @@ typedef struct {
 int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int policy, int zero_nan,
                     spb_coo **out, spb_consolidate_stats *stats /* may be NULL */);
 
+/* ---- sorted_permutation  (spsparse::sorted_permutation, algorithm.hpp:411-427) -----------
+ * perm[t] = position in `in` of the entry that a stable sort by sort_order puts at position t.
+ * Writes in->n values to host memory.  Nothing is dropped or merged. */
+int spb_sorted_permutation(spb_ctx *ctx, const spb_coo *in, const int *sort_order, uint64_t *perm);
+
 /* ---- dim_beginnings  (spsparse::dim_beginnings, algorithm.hpp:74-118) -------------------
  * Offsets of the first entry of every non-empty value of dimension sort_order[0], plus the
  * sentinel n.  Writes min(count, cap) offsets to host memory, returns the full count. */

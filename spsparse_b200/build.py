@@ -25,7 +25,8 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(os.path.dirname(HERE), "include", "spsparse_b200.h")]
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    deps = sources() + [os.path.join(inc, "spsparse_b200.h"), os.path.join(inc, "spsparse_b200", "base.hpp")]
     return any(os.path.getmtime(s) > t for s in deps)
 
 
@@ -33,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "spb_api.cu")]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "spb_api.cu"), os.path.join(CSRC, "host_symbols.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

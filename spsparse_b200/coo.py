@@ -129,6 +129,12 @@ class CooArray:
         check(self.ctx.lib.spb_coo_download(self.ctx.h, self.h, ptrs, val.ctypes.data_as(_lib.f64p)))
         return idx, val
 
+    def sorted_permutation(self, sort_order):
+        """spsparse::sorted_permutation (algorithm.hpp:411-427)."""
+        perm = np.empty(self.size(), dtype=np.uint64)
+        check(self.ctx.lib.spb_sorted_permutation(self.ctx.h, self.h, _order(sort_order), perm.ctypes.data_as(_lib.u64p)))
+        return perm.astype(np.int64)
+
     def dim_beginnings(self):
         """spsparse::dim_beginnings (algorithm.hpp:74-118)."""
         cnt = C.c_uint64()

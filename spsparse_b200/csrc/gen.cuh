@@ -81,3 +81,9 @@ __global__ void k_gen_vector(u64 seed, u64 dim, i32 *idx, double *val) {
         val[j] = 0.5 + u01(seed + j);
     }
 }
+
+// payload for sorted_permutation: the entry number itself, carried through the sort as 64 opaque bits
+__global__ void k_iota_bits(u64 n, double *out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        out[i] = __longlong_as_double((long long)i);
+}

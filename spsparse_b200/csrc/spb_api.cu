@@ -811,6 +811,33 @@ int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int 
     return consolidate_core(ctx, in, sort_order, sort_order, policy, true, zero_nan, out, stats);
 }
 
+int spb_sorted_permutation(spb_ctx *ctx, const spb_coo *in, const int *sort_order, uint64_t *perm) {
+    if (!ctx || !in || (in->n && !perm)) return spb_fail(SPB_ERR_ARG, "spb_sorted_permutation: null argument");
+    CKR(check_order(in, sort_order, "spb_sorted_permutation"));
+    if (in->n == 0) return SPB_OK;
+    CK(cudaSetDevice(ctx->device));
+    // the radix sort moves a 64-bit payload with every key: give it the entry numbers
+    Scratch ws(ctx);
+    double *iota;
+    CKR(ws.get(&iota, in->n));
+    ++ctx->launches, k_iota_bits<<<grid_for(in->n, 256, 1u << 16), 256, 0, ctx->stream>>>(in->n, iota);
+    CK(cudaGetLastError());
+    spb_coo tmp = *in;
+    tmp.val = iota;
+    tmp.owned = false;
+    spb_coo *sorted = nullptr;
+    CKR(consolidate_core(ctx, &tmp, sort_order, sort_order, POLICY_KEEP_ALL, false, 0, &sorted, nullptr));
+    int rc = SPB_OK;
+    if (sorted->n != in->n) rc = spb_fail(SPB_ERR_CUDA, "sorted_permutation: lost entries (%llu of %llu)", (ull)sorted->n, (ull)in->n);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(perm, sorted->val, in->n * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = spb_fail(SPB_ERR_CUDA, "sorted_permutation: %s", cudaGetErrorString(e));
+    }
+    spb_coo_free(ctx, sorted);
+    return rc;
+}
+
 int spb_dim_beginnings(spb_ctx *ctx, const spb_coo *a, uint64_t *out, uint64_t cap, uint64_t *count) {
     if (!ctx || !a || !count) return spb_fail(SPB_ERR_ARG, "spb_dim_beginnings: null argument");
     if (a->sort_order[0] < 0)
