@@ -1,0 +1,59 @@
+"""world_size-2 test of the N>1 path on CPU (gloo): the row partition and the shard replication of
+spsparse_b200/dist.py, with the oracle standing in for the device kernels.  Property checked: the
+ranks' row blocks of C, concatenated in rank order, equal the single-process product."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, m, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from spsparse_b200 import gen
+    from spsparse_b200.dist import replicate_start, replicate_wait, row_range
+    orc = O.port()
+    r0, r1 = row_range(m, rank, world)
+    a, b, w = gen.banded(5, m, r0, r1), gen.banded(6, m, r0, r1), gen.vector(7, m)
+    Ac = orc.consolidate(O.Coo(*a), (0, 1))
+    Bc = orc.consolidate(O.Coo(*b), (0, 1))
+    local = [torch.from_numpy(Bc.idx[0].copy()), torch.from_numpy(Bc.idx[1].copy()), torch.from_numpy(Bc.val.copy())]
+    fulls, works, sizes = replicate_start(local, rank, world)
+    replicate_wait(works)
+    Bf = O.Coo((m, m), [fulls[0].numpy(), fulls[1].numpy()], fulls[2].numpy(), None)
+    # rows of the gathered B must be globally sorted: shards are row ranges in rank order
+    key = Bf.idx[0].astype(np.int64) * m + Bf.idx[1]
+    assert np.all(np.diff(key) > 0)
+    Cb = orc.multiply_mm(1.0, None, Ac, ".", O.Coo(w[0], w[1], w[2], (0,)), Bf, ".", None)
+    np.savez(os.path.join(out_dir, f"c{rank}.npz"), i=Cb.idx[0], k=Cb.idx[1], v=Cb.val, sizes=np.array(sizes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_partition_matches_single_process(tmp_path):
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from spsparse_b200 import gen
+    from spsparse_b200.dist import row_range
+    m, world = 3001, 2
+    assert [row_range(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, m, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), f"c{r}.npz")) for r in range(world)]
+    got_i = np.concatenate([p["i"] for p in parts]); got_k = np.concatenate([p["k"] for p in parts])
+    got_v = np.concatenate([p["v"] for p in parts])
+    orc = O.port()
+    a, b, w = gen.banded(5, m, 0, m), gen.banded(6, m, 0, m), gen.vector(7, m)
+    # the full-size generator scrambles over all 5m slots, the shards scramble inside their own block:
+    # different insertion orders, same matrices -- consolidate() makes them identical.
+    want = orc.multiply_mm(1.0, None, O.Coo(*a), ".", O.Coo(w[0], w[1], w[2], (0,)), O.Coo(*b), ".", None)
+    assert np.array_equal(got_i, want.idx[0]) and np.array_equal(got_k, want.idx[1])
+    assert np.array_equal(got_v, want.val)
+    assert int(parts[0]["sizes"].sum()) == 5 * m - 6  # B shards together hold the consolidated B
