@@ -664,6 +664,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     MMOperands m;
     memset(&m, 0, sizeof m);
     m.C = C;
+    m.debug = getenv("SPB_MERGE_DEBUG") ? atoi(getenv("SPB_MERGE_DEBUG")) : 0;
     m.a_j = A->idx[a_in]; m.a_val = A->val; m.nnz_a = (u32)A->n;
     RowIndex ri;
     CKR(build_row_index(ctx, ws, A->idx[a_row_dim], (u32)A->n, &ri));
@@ -707,6 +708,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
 
     // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
     std::vector<EscChunk> chunks;
+    u64 esc_total = 0;
     u32 *esc_first = nullptr;
     if (h_stats[3]) {
         CKR(ws.get(&esc_off, (u64)nrows + 1));
@@ -745,6 +747,10 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
             u32 nout = 0;
             CKR(esc_sort_reduce(ctx, kA, vA, cnt, key_bits, kbits, m, r_lo, t_row, t_k, t_v, &nout));
             ws.release(kA); ws.release(vA);
+            esc_total += nout;
+            if (esc_total >= (1ull << 31))
+                return spb_fail(SPB_ERR_TOO_LARGE, "product has more than 2^31 entries; a VectorCooArray holds < 2^31 "
+                                "(algorithm.hpp:419) -- multiply row panels of A instead");
             EscChunk ch;
             ch.n = nout;
             // shrink the temporaries to what was produced
@@ -781,7 +787,14 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     out->owned = true;
     out->n = nnz_c;
     if (h_stats[1] && nnz_c)
-        ++ctx->launches, k_merge_numeric<<<(u32)div_up(nrows, MR_THREADS), MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
+        {
+        ++ctx->launches;
+        const u32 g = (u32)div_up(nrows, MR_THREADS);
+        const int stage = getenv("SPB_MERGE_STAGE") ? atoi(getenv("SPB_MERGE_STAGE")) : 16;
+        if (stage == 16) k_merge_numeric<16><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
+        else if (stage == 4) k_merge_numeric<4><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
+        else k_merge_numeric<8><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
+    }
     for (auto &ch : chunks)
         if (ch.n) ++ctx->launches, k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
     CK(cudaGetLastError());

@@ -40,6 +40,7 @@ struct MMOperands {
     const unsigned char *sj_mask; // [inner]          absent => term excluded
     const double *sk;             // [cols of op(B)]  absent = 0 => column excluded
     double C;
+    int debug;  // experiments only (SPB_MERGE_DEBUG): 1 = skip the global stores, 2 = plain (non-streaming) stores
 };
 
 // ---- per A entry: number of products it forms (0 if its row or its j is excluded) -------------
@@ -118,6 +119,18 @@ struct RowMerge {
         }
     }
 
+    // Sum of everything init() loaded.  Callers compare it against an impossible value before entering
+    // their merge loop: that one real consumer makes the loop-invariant registers (as[], the row scale)
+    // "arrived" for ptxas.  Without it every iteration re-waits on their scoreboard slot, which by then is
+    // shared with the freshly issued next-head loads -- the step then stalls a full L2 round trip on the
+    // loads it only needs in the NEXT step (profiles/r01_merge_numeric_notes.md).
+    __device__ __forceinline__ double touch() const {
+        double t = 0.0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) t += as[l];
+        return t;
+    }
+
     // Next output column and its dot product; false when every list is exhausted.
     __device__ __forceinline__ bool next(const MMOperands &m, i32 &k, double &sum) {
         i32 kmin = hk[0];
@@ -163,6 +176,7 @@ __device__ __forceinline__ u32 count_row(const MMOperands &m, u32 s, u32 len) {
     u32 count = 0;
     i32 k;
     double sum, bs;
+    if (st.touch() == -1.2345678e300) return 0;  // never true; see RowMerge::touch
     while (st.next(m, k, sum))
         if (keep_output(m, k, sum, bs)) ++count;
     return count;
@@ -186,12 +200,12 @@ __global__ void __launch_bounds__(128) k_merge_count(MMOperands m, const unsigne
 // flushed as contiguous runs (lane l's run is written by 16 lanes at once), so C is written in full
 // sectors instead of one 4/8-byte store per thread per step.
 constexpr int MR_THREADS = 128;
-constexpr int MR_STAGE = 16;
-constexpr int MR_PITCH = MR_STAGE + 1;
 
-template <int NL>
+template <int NL, int STAGE>
 __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, u32 s, u32 len, i32 irow,
                                                 u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v) {
+    constexpr int PITCH = STAGE + 1;
+    constexpr int RUNS = 32 / STAGE;  // lanes' runs written per flush iteration
     const u32 lane = lane_id();
     RowMerge<NL> st;
     st.init(m, s, mine ? len : 0);
@@ -199,31 +213,38 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
     if (mine && m.si) a_scale = m.si[irow];
     u32 cnt = 0;
     bool active = mine;
+    if (st.touch() + a_scale + (double)dst == -1.2345678e300) active = false;  // never true; see RowMerge::touch
     for (;;) {
         if (active) {
             i32 k;
             double sum, b_scale;
             if (!st.next(m, k, sum)) active = false;
             else if (keep_output(m, k, sum, b_scale)) {
-                sk[lane * MR_PITCH + cnt] = k;
-                sv[lane * MR_PITCH + cnt] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
+                sk[lane * PITCH + cnt] = k;
+                sv[lane * PITCH + cnt] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
                 ++cnt;
             }
         }
         const bool any_active = __any_sync(SPB_FULL_MASK, active);
-        if (__any_sync(SPB_FULL_MASK, cnt == (u32)MR_STAGE) || !any_active) {
+        if (__any_sync(SPB_FULL_MASK, cnt == (u32)STAGE) || !any_active) {
             __syncwarp();
 #pragma unroll 4
-            for (int l2 = 0; l2 < 16; ++l2) {
-                const int l = 2 * l2 + (int)(lane >> 4);
-                const u32 t = lane & 15;
+            for (int it = 0; it < 32 / RUNS; ++it) {
+                const int l = RUNS * it + (int)(lane / STAGE);
+                const u32 t = lane % STAGE;
                 const u32 n_l = __shfl_sync(SPB_FULL_MASK, cnt, l);
                 const u64 d_l = __shfl_sync(SPB_FULL_MASK, dst, l);
                 const i32 i_l = __shfl_sync(SPB_FULL_MASK, irow, l);
-                if (t < n_l) {
-                    c_k[d_l + t] = sk[l * MR_PITCH + t];
-                    c_v[d_l + t] = sv[l * MR_PITCH + t];
-                    c_i[d_l + t] = i_l;
+                if (t < n_l && m.debug != 1) {
+                    if (m.debug == 2) {
+                        c_k[d_l + t] = sk[l * PITCH + t];
+                        c_v[d_l + t] = sv[l * PITCH + t];
+                        c_i[d_l + t] = i_l;
+                    } else {  // streaming stores: C is written once and never re-read here; keep L1/L2 for B
+                        __stcs(c_k + d_l + t, sk[l * PITCH + t]);
+                        __stcs(c_v + d_l + t, sv[l * PITCH + t]);
+                        __stcs(c_i + d_l + t, i_l);
+                    }
                 }
             }
             dst += cnt;
@@ -234,11 +255,12 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
     }
 }
 
+template <int STAGE>
 __global__ void __launch_bounds__(MR_THREADS) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
                                                               const u64 *__restrict__ c_ptr, i32 *c_i, i32 *c_k,
                                                               double *c_v) {
-    __shared__ i32 s_k[MR_THREADS * MR_PITCH];
-    __shared__ double s_v[MR_THREADS * MR_PITCH];
+    __shared__ i32 s_k[MR_THREADS * (STAGE + 1)];
+    __shared__ double s_v[MR_THREADS * (STAGE + 1)];
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 warp = threadIdx.x >> 5;
     const bool mine = (r < m.nrows) && (row_cls[r] == ROW_MERGE);
@@ -252,13 +274,13 @@ __global__ void __launch_bounds__(MR_THREADS) k_merge_numeric(MMOperands m, cons
         dst = c_ptr[r];
     }
     const u32 maxlen = __reduce_max_sync(SPB_FULL_MASK, len);
-    i32 *sk = s_k + warp * 32 * MR_PITCH;
-    double *sv = s_v + warp * 32 * MR_PITCH;
+    i32 *sk = s_k + warp * 32 * (STAGE + 1);
+    double *sv = s_v + warp * 32 * (STAGE + 1);
     if (maxlen == 0) return;
-    if (maxlen <= 2) merge_rows_warp<2>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (maxlen <= 4) merge_rows_warp<4>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (maxlen <= 6) merge_rows_warp<6>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else merge_rows_warp<8>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (maxlen <= 4) merge_rows_warp<4, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (maxlen <= 6) merge_rows_warp<6, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else merge_rows_warp<8, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
 }
 
 // ---- long rows: expand-sort-compress ------------------------------------------------------------
