@@ -39,6 +39,11 @@ struct ReduceArgs {
     u32 *long_list;
     u32 *long_count;
     u32 long_cap;
+    // optional by-product (MODE_CONSOLIDATE, rank 2): compressed rows of the OUTPUT, i.e. dim_beginnings
+    // (algorithm.hpp:74-118) for free while the keys are in shared memory
+    u32 *row_start;   // [rows+1] offset of the first output entry of every non-empty leading index
+    i32 *row_id;      // [rows]
+    u32 *row_count;
     // MODE_ESC: key hi = compressed row number; emit (row number, k, scaled sum)
     const i32 *row_ids;  // compressed row -> row index i
     i32 row_base;        // key hi is relative to this compressed row number
@@ -51,10 +56,11 @@ template <int MODE>
 __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
     __shared__ u64 s_keys[RK_TILE + 1];
     __shared__ double s_vals[RK_TILE];
-    __shared__ u32 s_part[RK_IPT * RK_WARPS];
+    __shared__ u64 s_part[RK_IPT * RK_WARPS];  // low 32 bits: entries emitted, high 32 bits: row heads
     __shared__ u32 s_tile;
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool want_rows = (MODE == MODE_CONSOLIDATE) && (a.row_start != nullptr);
     if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
     __syncthreads();
     const u32 tile = s_tile;
@@ -77,7 +83,8 @@ __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
 
     const u32 lt = lanemask_lt();
     double acc[RK_IPT];
-    u32 emit_bits = 0, defer_bits = 0, rank_in_warp[RK_IPT];
+    u32 emit_bits = 0, defer_bits = 0, rhead_bits = 0, rank_in_warp[RK_IPT];
+    unsigned char rrank_in_warp[RK_IPT];
 #pragma unroll
     for (int k = 0; k < RK_IPT; ++k) {
         u32 p = (u32)k * RK_THREADS + tid;
@@ -122,31 +129,52 @@ __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
         u32 b = __ballot_sync(SPB_FULL_MASK, emit);
         rank_in_warp[k] = __popc(b & lt);
         if (emit) emit_bits |= 1u << k;
-        if (lane == 0) s_part[k * RK_WARPS + warp] = __popc(b);
+        u32 rb = 0;
+        if (want_rows) {
+            // first output entry of a new leading index: its predecessor (always a different key) has another hi
+            bool rhead = emit && (i == 0 || (s_keys[p + 1] >> a.bits_lo) != (s_keys[p] >> a.bits_lo));
+            rb = __ballot_sync(SPB_FULL_MASK, rhead);
+            rrank_in_warp[k] = (unsigned char)__popc(rb & lt);
+            if (rhead) rhead_bits |= 1u << k;
+        }
+        if (lane == 0) s_part[k * RK_WARPS + warp] = (u64)__popc(b) | ((u64)__popc(rb) << 32);
     }
     __syncthreads();
     if (warp == 0) {
-        u32 x = s_part[2 * lane], y = s_part[2 * lane + 1];
-        u32 s = warp_incl_scan(x + y);
-        u32 total = __shfl_sync(SPB_FULL_MASK, s, 31);
+        u64 x = s_part[2 * lane], y = s_part[2 * lane + 1];
+        u64 s = warp_incl_scan(x + y);  // both halves at once: neither can carry into the other
+        u64 total = __shfl_sync(SPB_FULL_MASK, s, 31);
         s_part[2 * lane] = s - x - y;
         s_part[2 * lane + 1] = s - y;
-        u64 excl = lookback_exclusive(a.state, tile, total);
+        // look-back value: entries in bits [0,31), rows in bits [31,62)
+        u64 packed = (total & 0xffffffffull) | ((total >> 32) << 31);
+        u64 excl = lookback_exclusive(a.state, tile, packed);
         if (lane == 0) {
             s_excl = excl;
-            if (base + RK_TILE >= n) *a.out_count = (u32)(excl + total);
+            if (base + RK_TILE >= n) {
+                u64 fin = excl + packed;
+                u32 n_out = (u32)(fin & 0x7fffffffull), n_rows = (u32)(fin >> 31);
+                *a.out_count = n_out;
+                if (want_rows) { *a.row_count = n_rows; a.row_start[n_rows] = n_out; }
+            }
         }
     }
     __syncthreads();
-    const u64 excl = s_excl;
+    const u64 excl_rows = s_excl >> 31;
+    const u64 excl = s_excl & 0x7fffffffull;
     const u64 lo_mask = (1ull << a.bits_lo) - 1;
 #pragma unroll
     for (int k = 0; k < RK_IPT; ++k) {
         if (!((emit_bits >> k) & 1u)) continue;
         u32 p = (u32)k * RK_THREADS + tid;
         u64 key = s_keys[p + 1];
-        u64 slot = excl + s_part[k * RK_WARPS + warp] + rank_in_warp[k];
+        u64 slot = excl + (u32)s_part[k * RK_WARPS + warp] + rank_in_warp[k];
         i32 hi = (i32)(key >> a.bits_lo), lo = (i32)(key & lo_mask);
+        if (want_rows && ((rhead_bits >> k) & 1u)) {
+            u64 rslot = excl_rows + (u32)(s_part[k * RK_WARPS + warp] >> 32) + rrank_in_warp[k];
+            a.row_start[rslot] = (u32)slot;
+            a.row_id[rslot] = hi;
+        }
         if (MODE == MODE_ESC) hi += a.row_base;
         if (MODE == MODE_CONSOLIDATE) {
             a.out_hi[slot] = hi;

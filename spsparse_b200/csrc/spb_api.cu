@@ -125,6 +125,13 @@ struct spb_coo {
     double *val;
     int sort_order[2];
     bool owned;
+    // lazily cached structure of a sorted array (the reference caches dim_beginnings the same way,
+    // VectorCooArray.hpp:323-335); valid for leading dimension sort_order[0]
+    u32 *row_start;  // [nrows+1] compressed row starts incl. sentinel
+    i32 *row_id;     // [nrows]
+    u32 nrows;
+    bool rows_valid;
+    u32 *dense_ptr;  // [extent+1] dense pointer over the leading index, or nullptr
 };
 
 // ---- stream-ordered scratch memory, released when the scope ends ---------------------------------
@@ -265,6 +272,11 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     a->sort_order[0] = -1;
     a->sort_order[1] = 0;
     a->owned = allocate;
+    a->row_start = nullptr;
+    a->row_id = nullptr;
+    a->nrows = 0;
+    a->rows_valid = false;
+    a->dense_ptr = nullptr;
     if (allocate) {
         CK(cudaSetDevice(ctx->device));
         size_t cnt = n ? n : 1;
@@ -273,6 +285,16 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     }
     *out = a;
     return SPB_OK;
+}
+
+static void drop_row_cache(spb_ctx *ctx, spb_coo *a) {
+    if (ctx) {
+        ctx->pool.release(a->row_start);
+        ctx->pool.release(a->row_id);
+        ctx->pool.release(a->dense_ptr);
+    }
+    a->row_start = nullptr; a->row_id = nullptr; a->dense_ptr = nullptr;
+    a->rows_valid = false; a->nrows = 0;
 }
 
 static void set_order(spb_coo *a, const int *so) {
@@ -334,6 +356,8 @@ int spb_coo_device_ptrs(const spb_coo *a, int32_t **d_idx, double **d_val) {
 
 int spb_coo_set_sorted(spb_coo *a, const int *sort_order) {
     if (!a) return spb_fail(SPB_ERR_ARG, "null array");
+    if (a->rows_valid || a->dense_ptr)
+        return spb_fail(SPB_ERR_ARG, "spb_coo_set_sorted: the array's row structure is already in use");
     set_order(a, sort_order);
     return SPB_OK;
 }
@@ -355,6 +379,7 @@ int spb_coo_free(spb_ctx *ctx, spb_coo *a) {
         for (int k = 0; k < 2; ++k) if (a->idx[k]) ctx->pool.release(a->idx[k]);
         if (a->val) ctx->pool.release(a->val);
     }
+    drop_row_cache(ctx, a);
     delete a;
     return SPB_OK;
 }
@@ -413,7 +438,8 @@ static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passe
 // Sorts job.in by (hi,lo), applies the drop rule and the duplicate policy, writes the result into
 // out_hi/out_lo/out_val (capacity in.n each) and returns the counts.
 static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_lo, double *out_val,
-                       u32 *h_kept, u32 *h_out, spb_consolidate_stats *st) {
+                       u32 *h_kept, u32 *h_out, spb_consolidate_stats *st, u32 *row_start = nullptr,
+                       i32 *row_id = nullptr, u32 *h_rows = nullptr) {
     const SortInput &in = job.in;
     const u32 n = in.n;
     const int key_bits = job.bits_hi + in.bits_lo;
@@ -461,18 +487,20 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     ra.long_cap = n / RK_LONG_RUN + 1;
     CKR(ws.get(&ra.long_list, 2ull * ra.long_cap));
     ra.long_count = counters + 3;
+    ra.row_start = row_start; ra.row_id = row_id; ra.row_count = counters + 4;
     ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
     if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
         ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
     CK(cudaGetLastError());
     const int t2 = tm.mark();
 
-    u32 h[4];
+    u32 h[5];
     CK(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (h[1]) return spb_fail(SPB_ERR_ARG, "Sparse index out of bounds (an index is negative or >= its extent)");
     *h_kept = h[0];
     *h_out = h[2];
+    if (h_rows) *h_rows = h[4];
     if (st) {
         st->n_in = n; st->n_kept = h[0]; st->n_out = h[2];
         st->key_bits = key_bits; st->passes = passes;
@@ -510,10 +538,24 @@ static int consolidate_core(spb_ctx *ctx, const spb_coo *in, const int *so, cons
     job.in.ref_bits_lo = r1 >= 0 ? bits_for(in->shape[r1]) : 0;
     job.bits_hi = bits_for(in->shape[d0]);
     job.policy = policy;
-    u32 kept = 0, nout = 0;
-    int rc = sort_reduce(ctx, job, r->idx[d0], d1 >= 0 ? r->idx[d1] : nullptr, r->val, &kept, &nout, st);
+    u32 kept = 0, nout = 0, nrows = 0;
+    if (in->rank == 2) {  // the reduce pass also emits the compressed row starts of its output
+        const u64 cap = (in->n < in->shape[d0] ? in->n : in->shape[d0]) + 1;
+        if (ctx->pool.alloc((void **)&r->row_start, cap * sizeof(u32)) != cudaSuccess ||
+            ctx->pool.alloc((void **)&r->row_id, cap * sizeof(i32)) != cudaSuccess) {
+            spb_coo_free(ctx, r);
+            return spb_fail(SPB_ERR_CUDA, "out of device memory");
+        }
+    }
+    int rc = sort_reduce(ctx, job, r->idx[d0], d1 >= 0 ? r->idx[d1] : nullptr, r->val, &kept, &nout, st,
+                         r->row_start, r->row_id, &nrows);
     if (rc) { spb_coo_free(ctx, r); return rc; }
     r->n = nout;
+    if (in->rank == 2) {
+        r->nrows = nrows;
+        r->rows_valid = true;
+        if (nout == 0) { const u32 z = 0; cudaMemcpyAsync(r->row_start, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream); }
+    }
     *out = r;
     return SPB_OK;
 }
@@ -536,21 +578,31 @@ struct RowIndex {   // compressed rows of a sorted array (scratch-owned)
     u32 nrows;
 };
 
-static int build_row_index(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, RowIndex *ri) {
-    CKR(ws.get(&ri->start, (u64)n + 1));
-    CKR(ws.get(&ri->id, (u64)n));
-    u32 *count, *ticket;
-    u64 *state;
-    const u32 tiles = (u32)div_up(n ? n : 1, RH_TILE);
-    CKR(ws.zeroed(&count, 1));
-    CKR(ws.zeroed(&ticket, 1));
-    CKR(ws.zeroed(&state, tiles));
-    if (n) ++ctx->launches, k_row_heads<<<tiles, RH_THREADS, 0, ctx->stream>>>(hi, n, ri->start, ri->id, count, state, ticket);
-    ++ctx->launches, k_row_sentinel<<<1, 1, 0, ctx->stream>>>(ri->start, count, n);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&ri->nrows, count, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ws.release(state);
+// Compressed rows of a sorted array, cached in the handle after the first request.
+static int build_row_index(spb_ctx *ctx, const spb_coo *a_const, RowIndex *ri) {
+    spb_coo *a = const_cast<spb_coo *>(a_const);  // lazy cache, as VectorCooArray::dim_beginnings does
+    if (!a->rows_valid) {
+        const u32 n = (u32)a->n;
+        const i32 *hi = a->idx[a->sort_order[0]];
+        Scratch ws(ctx);
+        CK(ctx->pool.alloc((void **)&a->row_start, ((u64)n + 1) * sizeof(u32)));
+        CK(ctx->pool.alloc((void **)&a->row_id, ((u64)n + 1) * sizeof(i32)));
+        u32 *count, *ticket;
+        u64 *state;
+        const u32 tiles = (u32)div_up(n ? n : 1, RH_TILE);
+        CKR(ws.zeroed(&count, 1));
+        CKR(ws.zeroed(&ticket, 1));
+        CKR(ws.zeroed(&state, tiles));
+        if (n) ++ctx->launches, k_row_heads<<<tiles, RH_THREADS, 0, ctx->stream>>>(hi, n, a->row_start, a->row_id, count, state, ticket);
+        ++ctx->launches, k_row_sentinel<<<1, 1, 0, ctx->stream>>>(a->row_start, count, n);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&a->nrows, count, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        a->rows_valid = true;
+    }
+    ri->start = a->row_start;
+    ri->id = a->row_id;
+    ri->nrows = a->nrows;
     return 0;
 }
 
@@ -567,20 +619,23 @@ static int exclusive_scan(spb_ctx *ctx, Scratch &ws, const InT *in, OutT *out, u
     return 0;
 }
 
-// dense pointer over `extent` values of the leading index of a sorted array
-static int build_dense_ptr(spb_ctx *ctx, Scratch &ws, const i32 *hi, u32 n, u64 extent, u32 **ptr_out) {
-    RowIndex ri;
-    CKR(build_row_index(ctx, ws, hi, n, &ri));
-    u32 *len, *ptr, *cnt;
-    CKR(ws.zeroed(&len, extent + 1));
-    CKR(ws.get(&ptr, extent + 2));
-    CKR(ws.get(&cnt, 1));
-    CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    if (ri.nrows) ++ctx->launches, k_scatter_row_len<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, len);
-    CKR((exclusive_scan<u32, u32>(ctx, ws, len, ptr, extent)));
-    CK(cudaStreamSynchronize(ctx->stream));  // &ri.nrows (host) was read by the async copy above
-    ws.release(ri.start); ws.release(ri.id); ws.release(len);
-    *ptr_out = ptr;
+// dense pointer over the `extent` values of the leading index of a sorted array (cached in the handle)
+static int build_dense_ptr(spb_ctx *ctx, const spb_coo *a_const, u64 extent, u32 **ptr_out) {
+    spb_coo *a = const_cast<spb_coo *>(a_const);
+    if (!a->dense_ptr) {
+        RowIndex ri;
+        CKR(build_row_index(ctx, a, &ri));
+        Scratch ws(ctx);
+        u32 *len, *cnt;
+        CKR(ws.zeroed(&len, extent + 1));
+        CKR(ws.get(&cnt, 1));
+        CK(ctx->pool.alloc((void **)&a->dense_ptr, (extent + 2) * sizeof(u32)));
+        CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        if (ri.nrows) ++ctx->launches, k_scatter_row_len<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, len);
+        CKR((exclusive_scan<u32, u32>(ctx, ws, len, a->dense_ptr, extent)));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *ptr_out = a->dense_ptr;
     return 0;
 }
 
@@ -667,10 +722,10 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     m.debug = getenv("SPB_MERGE_DEBUG") ? atoi(getenv("SPB_MERGE_DEBUG")) : 0;
     m.a_j = A->idx[a_in]; m.a_val = A->val; m.nnz_a = (u32)A->n;
     RowIndex ri;
-    CKR(build_row_index(ctx, ws, A->idx[a_row_dim], (u32)A->n, &ri));
+    CKR(build_row_index(ctx, A, &ri));
     m.arow_id = ri.id; m.arow_start = ri.start; m.nrows = ri.nrows;
     u32 *bptr;
-    CKR(build_dense_ptr(ctx, ws, B->idx[b_inner_dim], (u32)B->n, n_inner, &bptr));
+    CKR(build_dense_ptr(ctx, B, n_inner, &bptr));
     m.bptr = bptr; m.b_k = B->idx[b_col]; m.b_val = B->val;
     double *d;
     unsigned char *mask;
@@ -681,30 +736,35 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     double h0 = now_ms();
     if (tracing()) fprintf(stderr, "[spb] mm: prepare done (host), alloc so far %.2f ms\n", g_alloc_ms);
 
-    // ---- symbolic: products per entry / row, bins, output counts -------------------------------
+    // ---- symbolic: bin every row; short rows are counted exactly by the merge itself -----------------
     const u32 nrows = m.nrows;
-    u32 *ent_f, *row_cnt;
-    u64 *ent_off, *esc_f, *esc_off, *c_ptr;
+    u32 *row_cnt;
+    u64 *ent_off = nullptr, *esc_f = nullptr, *esc_off, *c_ptr;
     unsigned char *row_cls;
-    ull *stats;
-    CKR(ws.get(&ent_f, m.nnz_a));
-    CKR(ws.get(&ent_off, (u64)m.nnz_a + 1));
+    ull *stats;  // [0] F merged rows, [1] rows merged, [2] rows ESC, [3] F ESC rows
     CKR(ws.get(&row_cls, nrows));
-    CKR(ws.get(&esc_f, nrows));
     CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
     CKR(ws.zeroed(&stats, 4));
     const u32 cap = (u32)ctx->sm_count * 32;
-    ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
-    CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
-    ++ctx->launches, k_row_bins<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, ctx->merge_max_products, row_cls, esc_f, stats);
+    ++ctx->launches, k_merge_count<<<(u32)div_up(nrows ? nrows : 1, 128), 128, 0, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, stats);
     CK(cudaGetLastError());
     ull h_stats[4];
     CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ws.release(ent_f);
-
-    if (h_stats[1]) ++ctx->launches, k_merge_count<<<(u32)div_up(nrows, 128), 128, 0, ctx->stream>>>(m, row_cls, row_cnt);
-    CK(cudaGetLastError());
+    if (h_stats[2]) {
+        // long rows exist: products per A entry, their prefix sums, products per long row
+        u32 *ent_f;
+        CKR(ws.get(&ent_f, m.nnz_a));
+        CKR(ws.get(&ent_off, (u64)m.nnz_a + 1));
+        CKR(ws.get(&esc_f, nrows));
+        ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
+        CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
+        ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, stats);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ws.release(ent_f);
+    }
 
     // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
     std::vector<EscChunk> chunks;
@@ -802,7 +862,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaStreamSynchronize(ctx->stream));
     if (tracing()) fprintf(stderr, "[spb] mm: total host since prepare %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (st) {
-        st->products = h_stats[0]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2]; st->products_esc = h_stats[3];
+        st->products = h_stats[0] + h_stats[3]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2]; st->products_esc = h_stats[3];
         st->nnz_a = A->n; st->nnz_b = B->n; st->rows_a = nrows; st->nnz_c = nnz_c;
         st->ms_prepare = tm.ms(t_begin, t_prep);
         st->ms_symbolic = tm.ms(t_prep, t_sym);
@@ -858,9 +918,8 @@ int spb_dim_beginnings(spb_ctx *ctx, const spb_coo *a, uint64_t *out, uint64_t c
     *count = 0;
     if (a->n == 0) return SPB_OK;  // algorithm.hpp:89: empty array, empty list
     CK(cudaSetDevice(ctx->device));
-    Scratch ws(ctx);
     RowIndex ri;
-    CKR(build_row_index(ctx, ws, a->idx[a->sort_order[0]], (u32)a->n, &ri));
+    CKR(build_row_index(ctx, a, &ri));
     *count = (u64)ri.nrows + 1;
     u64 take = *count < cap ? *count : cap;
     if (out && take) {
@@ -993,7 +1052,7 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
         m.C = C;
         m.a_j = Ause->idx[a_so[1]]; m.a_val = Ause->val; m.nnz_a = (u32)Ause->n;
         RowIndex ri;
-        rc = build_row_index(ctx, ws, Ause->idx[a_so[0]], (u32)Ause->n, &ri);
+        rc = build_row_index(ctx, Ause, &ri);
         double *d, *vd, *row_val;
         unsigned char *mask, *vmask, *row_keep;
         u32 *slot;

@@ -54,36 +54,20 @@ __global__ void k_entry_products(MMOperands m, const i32 *__restrict__ a_row, u3
     }
 }
 
-// ---- per row: product count, bin ----------------------------------------------------------------
-// stats: [0] F total, [1] rows merged, [2] rows ESC, [3] F of ESC rows
-__global__ void k_row_bins(MMOperands m, const u64 *__restrict__ ent_off, u32 merge_max_products,
-                           unsigned char *row_cls, u64 *esc_f, ull *stats) {
-    u64 f_all = 0, f_esc = 0;
-    u32 n_merge = 0, n_esc = 0;
+// ---- long rows only: product count per row from the per-entry prefix sums -------------------------
+// stats: [0] F of merged rows, [1] rows merged, [2] rows ESC, [3] F of ESC rows
+__global__ void k_esc_row_products(MMOperands m, const u64 *__restrict__ ent_off, const unsigned char *__restrict__ row_cls,
+                                   u64 *esc_f, ull *stats) {
+    u64 f_esc = 0;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < m.nrows; r += (u64)gridDim.x * blockDim.x) {
-        u32 s = m.arow_start[r], e = m.arow_start[r + 1];
-        u64 f = ent_off[e] - ent_off[s];
-        unsigned char cls = ROW_SKIP;
-        if (f > 0) cls = (e - s <= (u32)MERGE_MAX_LISTS && f <= merge_max_products) ? ROW_MERGE : ROW_ESC;
-        row_cls[r] = cls;
-        esc_f[r] = (cls == ROW_ESC) ? f : 0;
-        f_all += f;
-        if (cls == ROW_MERGE) ++n_merge;
-        if (cls == ROW_ESC) { ++n_esc; f_esc += f; }
+        u64 f = 0;
+        if (row_cls[r] == ROW_ESC) f = ent_off[m.arow_start[r + 1]] - ent_off[m.arow_start[r]];
+        esc_f[r] = f;
+        f_esc += f;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        f_all += __shfl_xor_sync(SPB_FULL_MASK, f_all, o);
-        f_esc += __shfl_xor_sync(SPB_FULL_MASK, f_esc, o);
-        n_merge += __shfl_xor_sync(SPB_FULL_MASK, n_merge, o);
-        n_esc += __shfl_xor_sync(SPB_FULL_MASK, n_esc, o);
-    }
-    if (lane_id() == 0) {
-        if (f_all) atomicAdd(&stats[0], (ull)f_all);
-        if (n_merge) atomicAdd(&stats[1], (ull)n_merge);
-        if (n_esc) atomicAdd(&stats[2], (ull)n_esc);
-        if (f_esc) atomicAdd(&stats[3], (ull)f_esc);
-    }
+    for (int o = 16; o > 0; o >>= 1) f_esc += __shfl_xor_sync(SPB_FULL_MASK, f_esc, o);
+    if (lane_id() == 0 && f_esc) atomicAdd(&stats[3], (ull)f_esc);
 }
 
 // ---- short rows: k-way merge in registers, one thread per row -----------------------------------
@@ -168,32 +152,58 @@ __device__ __forceinline__ bool keep_output(const MMOperands &m, i32 k, double s
     return keep;
 }
 
-// symbolic: exact number of outputs of each short row
+// symbolic: bin the row and, for a short row, count its outputs exactly
 template <int NL>
-__device__ __forceinline__ u32 count_row(const MMOperands &m, u32 s, u32 len) {
+__device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u32 max_products, u32 &count, u64 &f) {
     RowMerge<NL> st;
     st.init(m, s, len);
-    u32 count = 0;
+    f = 0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) f += st.end[l] - st.cur[l];
+    count = 0;
+    if (f == 0) return ROW_SKIP;
+    if (f > max_products) return ROW_ESC;
     i32 k;
     double sum, bs;
-    if (st.touch() == -1.2345678e300) return 0;  // never true; see RowMerge::touch
+    if (st.touch() == -1.2345678e300) return ROW_SKIP;  // never true; see RowMerge::touch
     while (st.next(m, k, sum))
         if (keep_output(m, k, sum, bs)) ++count;
-    return count;
+    return ROW_MERGE;
 }
 
-__global__ void __launch_bounds__(128) k_merge_count(MMOperands m, const unsigned char *__restrict__ row_cls,
-                                                     u32 *row_cnt) {
-    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m.nrows) return;
-    if (row_cls[r] != ROW_MERGE) return;  // row_cnt is zero-initialised; ESC rows are filled later
-    const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
-    u32 c;
-    if (len <= 2) c = count_row<2>(m, s, len);
-    else if (len <= 4) c = count_row<4>(m, s, len);
-    else if (len <= 6) c = count_row<6>(m, s, len);
-    else c = count_row<8>(m, s, len);
-    row_cnt[r] = c;
+// stats: [0] F of merged rows, [1] rows merged, [2] rows ESC
+__global__ void __launch_bounds__(128) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
+                                                     u32 *row_cnt, ull *stats) {
+    const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = ROW_SKIP;
+    u32 c = 0;
+    u64 f = 0;
+    if (r < m.nrows) {
+        const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
+        const bool on = !m.si || m.si[m.arow_id[r]] != 0.0;  // row excluded by scalei (multiply_sparse.hpp:195)
+        if (on) {
+            if (len > (u32)MERGE_MAX_LISTS) cls = ROW_ESC;   // products counted later, from the per-entry prefix sums
+            else if (len <= 2) cls = count_row<2>(m, s, len, max_products, c, f);
+            else if (len <= 4) cls = count_row<4>(m, s, len, max_products, c, f);
+            else if (len <= 6) cls = count_row<6>(m, s, len, max_products, c, f);
+            else cls = count_row<8>(m, s, len, max_products, c, f);
+        }
+        row_cls[r] = (unsigned char)cls;
+        if (cls != ROW_ESC) row_cnt[r] = c;  // ESC rows are filled by the expand-sort-compress stage
+    }
+    u64 f_merge = (cls == ROW_MERGE) ? f : 0;
+    u32 n_merge = (cls == ROW_MERGE), n_esc = (cls == ROW_ESC);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        f_merge += __shfl_xor_sync(SPB_FULL_MASK, f_merge, o);
+        n_merge += __shfl_xor_sync(SPB_FULL_MASK, n_merge, o);
+        n_esc += __shfl_xor_sync(SPB_FULL_MASK, n_esc, o);
+    }
+    if (lane_id() == 0) {
+        if (f_merge) atomicAdd(&stats[0], (ull)f_merge);
+        if (n_merge) atomicAdd(&stats[1], (ull)n_merge);
+        if (n_esc) atomicAdd(&stats[2], (ull)n_esc);
+    }
 }
 
 // numeric: the 32 rows of a warp advance in lock step; outputs are staged per lane in shared memory and
