@@ -133,37 +133,56 @@ def run_ours(args):
         ctx.lib.spb_ctx_launch_count(ctx.h, ctypes.byref(n))
         return n.value
 
+    replicator = [None, False]  # (PeerReplicator or None, tried)
+
     def gather_b_start(Bc):
-        """Start replicating the row-sharded, consolidated B on every rank (spsparse_b200/dist.py): each
-        rank's shard is broadcast (NCCL over NVLink) into its slice of the full arrays.  Asynchronous, so
-        that consolidate(A) overlaps the transfers."""
+        """Start replicating the row-sharded, consolidated B on every rank (spsparse_b200/dist.py), in
+        compressed form: local row pointers of this rank's rows + column and value of every entry.
+        Asynchronous, so that consolidate(A) overlaps the NCCL transfers."""
         from spsparse_b200 import dist as spd
         n_local = Bc.size()
         (p0, p1), pv = Bc.device_ptrs()
-        views = [torch.as_tensor(DevView(p0, n_local, "<i4"), device="cuda"),
-                 torch.as_tensor(DevView(p1, n_local, "<i4"), device="cuda"),
-                 torch.as_tensor(DevView(pv, n_local, "<f8"), device="cuda")]
-        outs, works, sizes = spd.replicate_start(views, rank, world)
-        return outs, works, sum(sizes)
+        dptr, _ = Bc.dense_ptr()  # u32[m+1] over all rows; this rank's rows are [r0, r1)
+        local_ptr = torch.as_tensor(DevView(dptr + 4 * r0, r1 - r0, "<i4"), device="cuda")
+        cols = torch.as_tensor(DevView(p1, n_local, "<i4"), device="cuda")
+        vals = torch.as_tensor(DevView(pv, n_local, "<f8"), device="cuda")
+        if not replicator[1]:
+            replicator[1] = True
+            if not os.environ.get("SPB_NO_PEER_COPY"):
+                try:
+                    replicator[0] = spd.PeerReplicator(rank, world, 5 * (r1 - r0), r1 - r0, torch.device("cuda", local))
+                except Exception as e:  # noqa: BLE001 -- any failure: use the NCCL path
+                    print(f"[bench] symmetric-memory replication unavailable ({e!r}); using NCCL all-gather", file=sys.stderr)
+        if replicator[0] is not None:
+            return replicator[0].start(local_ptr, cols, vals)
+        return spd.replicate_csr_start(local_ptr, cols, vals, rank, world)
+
+    timeline = []  # per step: stream-event times (ms) between the phases of the hot path
 
     def hot_path(A_raw, B_raw, w):
         """consolidate(B shard) -> [replicate B, overlapped with] consolidate(A block) -> SpGEMM."""
+        from spsparse_b200 import dist as spd
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record(stream)
         Bc, sb = sp.consolidate(ctx, B_raw, sp.ROW_MAJOR, stats=True)
+        ev[1].record(stream)
         pending = gather_b_start(Bc) if world > 1 else None
+        ev[2].record(stream)
         Ac, sa = sp.consolidate(ctx, A_raw, sp.ROW_MAJOR, stats=True)
+        ev[3].record(stream)
         if pending:
-            outs, works, total = pending
-            for wk in works:
-                wk.wait()  # the library stream now waits for the NCCL stream
-            Bf = sp.CooArray.wrap_device(ctx, (m, m), [outs[0].data_ptr(), outs[1].data_ptr()], outs[2].data_ptr(),
-                                         total, (0, 1))
+            ptr, cols, vals, total = spd.replicate_csr_finish(pending)  # library stream now waits for NCCL
+            Bf = sp.CooArray.wrap_csr(ctx, (m, m), 0, ptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), total)
         else:
             Bf = Bc
+        ev[4].record(stream)
         Cm, st = sp.multiply_prepared(ctx, 1.0, None, Ac, 0, w, Bf, 0, None)
+        ev[5].record(stream)
+        stream.synchronize()
+        timeline.append([ev[i].elapsed_time(ev[i + 1]) for i in range(5)])
         if Bf is not Bc:
-            stream.synchronize()
             Bf.free()
-            del outs
+            del pending, ptr, cols, vals
         Ac.free(); Bc.free()
         return Cm, (sa, sb, st)
 
@@ -192,6 +211,21 @@ def run_ours(args):
         barrier()
         clocks = sampler.stop() if sampler else None
         l1 = launches()
+        # partition-independent fingerprints of C (one extra, untimed step): exact wrap-around checksum of the
+        # index structure and the fp64 sum of the values -- equal at every N if the row blocks tile C correctly
+        Cm, _ = hot_path(A_raw, B_raw, w)
+        (c0, c1), cv = Cm.device_ptrs()
+        nc = Cm.size()
+        ti = torch.as_tensor(DevView(c0, nc, "<i4"), device="cuda").to(torch.int64)
+        tk = torch.as_tensor(DevView(c1, nc, "<i4"), device="cuda").to(torch.int64)
+        fp = torch.stack([(ti * 1000003 + tk).sum(), torch.tensor(nc, device="cuda")])
+        vsum = torch.as_tensor(DevView(cv, nc, "<f8"), device="cuda").sum().reshape(1)
+        if world > 1:
+            dist.all_reduce(fp, op=dist.ReduceOp.SUM)
+            dist.all_reduce(vsum, op=dist.ReduceOp.SUM)
+        fingerprint = {"index_checksum": int(fp[0].item()), "nnz_c": int(fp[1].item()), "value_sum": float(vsum.item())}
+        del ti, tk
+        Cm.free()
         ms = e0.elapsed_time(e1) / args.steps
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         sa, sb, st = acc[-1]
@@ -276,9 +310,9 @@ def run_ours(args):
                                    "(consolidate A + consolidate B + allgather B + SpGEMM)" if m == 100_000_000 else
                                    f"REDUCED banded triple product, {m} rows (not the headline size)",
                        "rows": m, "nnz_a_raw": cons_in / 2, "nnz_c": nnzC, "products": F,
-                       "partition": f"A rows / B rows split over {world} rank(s); B replicated by NCCL broadcasts of the shards each step, overlapped with consolidate(A)",
+                       "partition": f"A rows / B rows split over {world} rank(s); B replicated each step in compressed form (row pointers + cols + vals, 12 B/entry): shards pulled from the peers' symmetric memory over NVLink by copy engines (NCCL grouped all-gather as fallback), overlapped with consolidate(A)",
                        "l2": "inputs (>= 2 GB per rank) are far larger than the 126 MB L2; no flush needed",
-                       "index_type": "int32", "value_type": "f64"},
+                       "index_type": "int32", "value_type": "f64", "result_fingerprint": fingerprint},
             "phases_rank0": {"ms_consolidate_a_plus_b": ms_cons, "ms_spgemm_symbolic_plus_numeric": ms_spgemm,
                              "ms_spgemm_prepare": ms_prep,
                              "consolidate_nnz_per_sec": (sa.n_out + sb.n_out) / (ms_cons * 1e-3),
@@ -287,7 +321,10 @@ def run_ours(args):
                              "spgemm_products_per_sec": st.products / (ms_spgemm * 1e-3),
                              "spgemm_model_bytes": spgemm_bytes,
                              "spgemm_model_frac": spgemm_bytes / (ms_spgemm * 1e-3) / 1e9 / hbm,
-                             "rows_merge": st.rows_merge, "rows_esc": st.rows_esc},
+                             "rows_merge": st.rows_merge, "rows_esc": st.rows_esc,
+                             "timeline_ms": dict(zip(["consolidate_b", "replicate_b_launch", "consolidate_a", "replicate_b_wait",
+                                                      "spgemm_incl_prepare"],
+                                                     [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)]))},
             "roofline": {"bound": "hbm", "kernel": "k_radix_pass<false> (one 8-bit LSD scatter pass, key+value)",
                          "achieved": pass_gbs, "peak": hbm, "unit": "GB/s", "frac": pass_gbs / hbm,
                          "traffic": None, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,

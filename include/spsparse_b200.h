@@ -69,6 +69,15 @@ int spb_coo_alloc(spb_ctx *ctx, int rank, const uint64_t *shape, uint64_t n, spb
 int spb_coo_info(const spb_coo *a, int *rank, uint64_t *shape /*[rank]*/, uint64_t *n,
                  int *sort_order /*[rank]*/);
 int spb_coo_device_ptrs(const spb_coo *a, int32_t **d_idx /*[rank]*/, double **d_val);
+/* Dense pointer over the leading sorted index of a consolidated rank-2 array: ptr[v] = offset of the first
+ * entry whose index[sort_order[0]] >= v, for v in [0, extent]; device memory owned by (and cached in) `a`. */
+int spb_coo_dense_ptr(spb_ctx *ctx, const spb_coo *a, uint32_t **d_ptr, uint64_t *extent);
+/* Wraps a consolidated matrix given in compressed form (caller-owned device memory, not copied): a dense
+ * pointer d_ptr[shape[lead_dim]+1] over dimension lead_dim, plus the other dimension's index and the value of
+ * every entry.  Only usable as the B operand of spb_multiply_mm_prepared (b_inner_dim = lead_dim) -- this is how
+ * the multi-GPU path hands over the replicated B without shipping its redundant row-index array. */
+int spb_coo_wrap_csr(spb_ctx *ctx, const uint64_t *shape, int lead_dim, uint32_t *d_ptr, int32_t *d_other_idx,
+                     double *d_val, uint64_t n, spb_coo **out);
 int spb_coo_set_sorted(spb_coo *a, const int *sort_order); /* VectorCooArray::set_sorted :131-135 */
 int spb_coo_download(spb_ctx *ctx, const spb_coo *a, int32_t *const *idx, double *val);
 int spb_coo_free(spb_ctx *ctx, spb_coo *a);

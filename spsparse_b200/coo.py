@@ -82,6 +82,21 @@ class CooArray:
                                           _order(sort_order), C.byref(h)))
         return cls(ctx, h)
 
+    @classmethod
+    def wrap_csr(cls, ctx, shape, lead_dim, ptr, other_idx, val, n):
+        """Consolidated matrix in compressed form (device pointers; see spb_coo_wrap_csr)."""
+        h = vp()
+        check(ctx.lib.spb_coo_wrap_csr(ctx.h, (C.c_uint64 * 2)(*[int(x) for x in shape]), int(lead_dim), vp(int(ptr)),
+                                       vp(int(other_idx)), vp(int(val)), int(n), C.byref(h)))
+        return cls(ctx, h)
+
+    def dense_ptr(self):
+        """(device pointer, extent) of the dense pointer over the leading sorted index (cached in the array)."""
+        p = vp()
+        ext = C.c_uint64()
+        check(self.ctx.lib.spb_coo_dense_ptr(self.ctx.h, self.h, C.byref(p), C.byref(ext)))
+        return p.value, int(ext.value)
+
     # -- accessors ----------------------------------------------------------------------------
     def _info(self):
         rank = C.c_int()

@@ -132,6 +132,7 @@ struct spb_coo {
     u32 nrows;
     bool rows_valid;
     u32 *dense_ptr;  // [extent+1] dense pointer over the leading index, or nullptr
+    bool dense_ptr_owned;
 };
 
 // ---- stream-ordered scratch memory, released when the scope ends ---------------------------------
@@ -277,6 +278,7 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     a->nrows = 0;
     a->rows_valid = false;
     a->dense_ptr = nullptr;
+    a->dense_ptr_owned = true;
     if (allocate) {
         CK(cudaSetDevice(ctx->device));
         size_t cnt = n ? n : 1;
@@ -291,7 +293,7 @@ static void drop_row_cache(spb_ctx *ctx, spb_coo *a) {
     if (ctx) {
         ctx->pool.release(a->row_start);
         ctx->pool.release(a->row_id);
-        ctx->pool.release(a->dense_ptr);
+        if (a->dense_ptr_owned) ctx->pool.release(a->dense_ptr);
     }
     a->row_start = nullptr; a->row_id = nullptr; a->dense_ptr = nullptr;
     a->rows_valid = false; a->nrows = 0;
@@ -562,6 +564,8 @@ static int consolidate_core(spb_ctx *ctx, const spb_coo *in, const int *so, cons
 
 static int check_order(const spb_coo *a, const int *so, const char *what) {
     if (!so) return spb_fail(SPB_ERR_ARG, "%s: sort_order is null", what);
+    for (int k = 0; k < a->rank; ++k)
+        if (a->n && !a->idx[k]) return spb_fail(SPB_ERR_ARG, "%s: array is in compressed (pointer) form", what);
     bool seen[2] = {false, false};
     for (int k = 0; k < a->rank; ++k) {
         if (so[k] < 0 || so[k] >= a->rank || seen[so[k]])
@@ -581,6 +585,8 @@ struct RowIndex {   // compressed rows of a sorted array (scratch-owned)
 // Compressed rows of a sorted array, cached in the handle after the first request.
 static int build_row_index(spb_ctx *ctx, const spb_coo *a_const, RowIndex *ri) {
     spb_coo *a = const_cast<spb_coo *>(a_const);  // lazy cache, as VectorCooArray::dim_beginnings does
+    if (!a->rows_valid && a->n && !a->idx[a->sort_order[0]])
+        return spb_fail(SPB_ERR_ARG, "array in compressed (pointer) form has no row list; use it as the B operand only");
     if (!a->rows_valid) {
         const u32 n = (u32)a->n;
         const i32 *hi = a->idx[a->sort_order[0]];
@@ -884,6 +890,33 @@ int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int 
     return consolidate_core(ctx, in, sort_order, sort_order, policy, true, zero_nan, out, stats);
 }
 
+int spb_coo_dense_ptr(spb_ctx *ctx, const spb_coo *a, uint32_t **d_ptr, uint64_t *extent) {
+    if (!ctx || !a || !d_ptr) return spb_fail(SPB_ERR_ARG, "spb_coo_dense_ptr: null argument");
+    if (a->rank != 2 || a->sort_order[0] < 0) return spb_fail(SPB_ERR_NOT_SORTED, "spb_coo_dense_ptr needs a consolidated rank-2 array");
+    CK(cudaSetDevice(ctx->device));
+    const u64 ext = a->shape[a->sort_order[0]];
+    u32 *p = nullptr;
+    CKR(build_dense_ptr(ctx, a, ext, &p));
+    *d_ptr = p;
+    if (extent) *extent = ext;
+    return SPB_OK;
+}
+
+int spb_coo_wrap_csr(spb_ctx *ctx, const uint64_t *shape, int lead_dim, uint32_t *d_ptr, int32_t *d_other_idx,
+                     double *d_val, uint64_t n, spb_coo **out) {
+    if (!d_ptr || (n && (!d_other_idx || !d_val)) || (lead_dim | 1) != 1) return spb_fail(SPB_ERR_ARG, "spb_coo_wrap_csr: bad argument");
+    CKR(coo_new(ctx, 2, shape, n, false, out));
+    spb_coo *a = *out;
+    a->idx[lead_dim] = nullptr;  // implicit in the pointer array
+    a->idx[1 - lead_dim] = d_other_idx;
+    a->val = d_val;
+    a->sort_order[0] = lead_dim;
+    a->sort_order[1] = 1 - lead_dim;
+    a->dense_ptr = d_ptr;
+    a->dense_ptr_owned = false;
+    return SPB_OK;
+}
+
 int spb_sorted_permutation(spb_ctx *ctx, const spb_coo *in, const int *sort_order, uint64_t *perm) {
     if (!ctx || !in || (in->n && !perm)) return spb_fail(SPB_ERR_ARG, "spb_sorted_permutation: null argument");
     CKR(check_order(in, sort_order, "spb_sorted_permutation"));
@@ -943,6 +976,7 @@ int spb_multiply_mm_prepared(spb_ctx *ctx, double C, const spb_coo *si, const sp
     if (A->rank != 2 || B->rank != 2) return spb_fail(SPB_ERR_ARG, "A and B must be rank-2 arrays");
     if ((a_row_dim | 1) != 1 || (b_inner_dim | 1) != 1) return spb_fail(SPB_ERR_ARG, "dimension must be 0 or 1");
     CKR(scale_ok(si, "scalei")); CKR(scale_ok(sj, "scalej")); CKR(scale_ok(sk, "scalek"));
+    if (A->n && (!A->idx[0] || !A->idx[1])) return spb_fail(SPB_ERR_ARG, "A must be a full COO array");
     if (A->sort_order[0] != a_row_dim || B->sort_order[0] != b_inner_dim)
         return spb_fail(SPB_ERR_NOT_SORTED, "prepared operands must be consolidated by (row, inner) and (inner, col)");
     CK(cudaSetDevice(ctx->device));

@@ -3,6 +3,9 @@ row ranges, B is sharded the same way (by its row = the inner index), consolidat
 replicated once on every rank.  Concatenating the ranks' consolidated blocks of C in rank order IS the
 reference's row-major order, so nothing is exchanged after the multiply.
 
+B travels in compressed form: per entry only its column and value (12 bytes instead of the 16 of COO),
+plus one local row pointer per row; the row-index array is redundant once the pointers exist.
+
 Device-agnostic on purpose: bench.py drives it with CUDA tensors over NCCL (NVLink), the CPU tests
 with gloo.  The reference itself has no counterpart (it is single-process)."""
 from __future__ import annotations
@@ -17,26 +20,125 @@ def row_range(m: int, rank: int, world: int) -> tuple[int, int]:
     return rank * m // world, (rank + 1) * m // world
 
 
+def _gather_uneven(full: torch.Tensor, offs, local: torch.Tensor, rank: int, world: int):
+    """Each rank's `local` lands in full[offs[g]:offs[g+1]] on every rank.  Returns pending works.
+    NCCL: one grouped call (torch coalesces the per-shard broadcasts into a single launch, so all links
+    are busy at once); other backends: one broadcast per shard."""
+    views = [full[int(offs[g]):int(offs[g + 1])] for g in range(world)]
+    if dist.get_backend() == "nccl":
+        return [dist.all_gather(views, local, async_op=True)]
+    views[rank].copy_(local)
+    return [dist.broadcast(views[g], src=g, async_op=True) for g in range(world) if views[g].numel()]
+
+
 def replicate_start(local: list[torch.Tensor], rank: int, world: int):
-    """Starts replicating per-rank shards (one tensor per array of the COO: idx0, idx1, val; all of the
-    same length on a rank, lengths may differ between ranks).  Each shard is broadcast straight into its
-    slice of the full array -- no padding, no compaction copy.  Returns (full_arrays, pending_works, sizes)."""
+    """Starts replicating per-rank shards of plain arrays (all of one length on a rank; lengths may differ
+    between ranks) straight into their slices of the full arrays -- no padding, no compaction copy.
+    Returns (full_arrays, pending_works, sizes)."""
     dev = local[0].device
     n_local = int(local[0].shape[0])
     sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(sizes_t, torch.tensor([n_local], dtype=torch.int64, device=dev))
     sizes = [int(x) for x in sizes_t.tolist()]
     offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    total = int(offs[-1])
     fulls, works = [], []
     for t in local:
-        full = torch.empty(total, dtype=t.dtype, device=dev)
-        full[offs[rank]:offs[rank + 1]] = t
-        for g in range(world):
-            if sizes[g]:
-                works.append(dist.broadcast(full[offs[g]:offs[g + 1]], src=g, async_op=True))
+        full = torch.empty(int(offs[-1]), dtype=t.dtype, device=dev)
+        works += _gather_uneven(full, offs, t, rank, world)
         fulls.append(full)
     return fulls, works, sizes
+
+
+def replicate_csr_start(local_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, rank: int, world: int):
+    """Starts replicating a row-sharded consolidated matrix in compressed form.
+      local_ptr[i]  offset, inside this rank's shard, of the first entry of its i-th row   (int32, rows_local)
+      cols, vals    column and value of every entry of the shard                            (n_local)
+    Returns a state for replicate_csr_finish."""
+    dev = cols.device
+    meta = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(meta, torch.tensor([int(cols.shape[0]), int(local_ptr.shape[0])], dtype=torch.int64, device=dev))
+    meta = meta.view(world, 2).tolist()
+    eoffs = np.concatenate([[0], np.cumsum([m[0] for m in meta])]).astype(np.int64)
+    roffs = np.concatenate([[0], np.cumsum([m[1] for m in meta])]).astype(np.int64)
+    full_ptr = torch.empty(int(roffs[-1]) + 1, dtype=torch.int32, device=dev)
+    full_cols = torch.empty(int(eoffs[-1]), dtype=cols.dtype, device=dev)
+    full_vals = torch.empty(int(eoffs[-1]), dtype=vals.dtype, device=dev)
+    works = _gather_uneven(full_ptr[:-1], roffs, local_ptr, rank, world)
+    works += _gather_uneven(full_cols, eoffs, cols, rank, world)
+    works += _gather_uneven(full_vals, eoffs, vals, rank, world)
+    return dict(ptr=full_ptr, cols=full_cols, vals=full_vals, works=works, eoffs=eoffs, roffs=roffs, world=world)
+
+
+def replicate_csr_finish(st):
+    """Waits for the transfers and turns the gathered local row pointers into global ones.
+    Returns (ptr int32[rows+1], cols, vals, nnz)."""
+    for w in st["works"]:
+        w.wait()
+    if st.get("event") is not None:
+        torch.cuda.current_stream().wait_event(st["event"])
+    ptr, eoffs, roffs = st["ptr"], st["eoffs"], st["roffs"]
+    for g in range(1, st["world"]):
+        if roffs[g + 1] > roffs[g] and eoffs[g]:
+            ptr[int(roffs[g]):int(roffs[g + 1])] += int(eoffs[g])
+    ptr[-1] = int(eoffs[-1])
+    return ptr, st["cols"], st["vals"], int(eoffs[-1])
+
+
+class PeerReplicator:
+    """Replicates the row-sharded compressed B by PULLING the peers' shards out of symmetric (peer-mapped)
+    memory with device-to-device copies over NVLink.  Copy engines move the data, so unlike an NCCL
+    collective it needs no SMs or shared memory and really overlaps consolidate(A) (measured on 4xB200: the
+    grouped NCCL all-gather got ~200 GB/s while the radix passes held every SM; the same bytes pulled by copy
+    engines arrive at ~680 GB/s).  Falls back to the NCCL path (replicate_csr_*) when symmetric memory is
+    unavailable (CPU/gloo, old torch)."""
+
+    def __init__(self, rank: int, world: int, cap_entries: int, cap_rows: int, device):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.world = rank, world
+        caps = torch.tensor([cap_entries, cap_rows], dtype=torch.int64, device=device)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX)  # symmetric buffers have one size on every rank
+        self.cap_entries, self.cap_rows = (int(x) for x in caps.tolist())
+        name = dist.group.WORLD.group_name
+        self.bufs, self.hdls = [], []
+        for n, dt in ((self.cap_rows, torch.int32), (self.cap_entries, torch.int32), (self.cap_entries, torch.float64)):
+            t = symm.empty(max(n, 1), dtype=dt, device=device)
+            self.bufs.append(t)
+            self.hdls.append(symm.rendezvous(t, name))
+        self.peers = [[h.get_buffer(g, (b.shape[0],), b.dtype) for g in range(world)] for h, b in zip(self.hdls, self.bufs)]
+        self.side = torch.cuda.Stream(device=device)
+        self.done = torch.cuda.Event()
+
+    def start(self, local_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor):
+        dev, rank, world = cols.device, self.rank, self.world
+        n_local, rows_local = int(cols.shape[0]), int(local_ptr.shape[0])
+        assert n_local <= self.cap_entries and rows_local <= self.cap_rows
+        meta = torch.zeros(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(meta, torch.tensor([n_local, rows_local], dtype=torch.int64, device=dev))
+        # publish this rank's shard (previous step's readers are past their "done" barrier, see below)
+        self.bufs[0][:rows_local].copy_(local_ptr)
+        self.bufs[1][:n_local].copy_(cols)
+        self.bufs[2][:n_local].copy_(vals)
+        meta = meta.view(world, 2).tolist()
+        eoffs = np.concatenate([[0], np.cumsum([m[0] for m in meta])]).astype(np.int64)
+        roffs = np.concatenate([[0], np.cumsum([m[1] for m in meta])]).astype(np.int64)
+        full = [torch.empty(int(roffs[-1]) + 1, dtype=torch.int32, device=dev),
+                torch.empty(int(eoffs[-1]), dtype=torch.int32, device=dev),
+                torch.empty(int(eoffs[-1]), dtype=torch.float64, device=dev)]
+        cur = torch.cuda.current_stream()
+        self.hdls[0].barrier(channel=0)          # every rank has published
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            for k in range(world):               # own shard first, then round the ring: spreads the load over the peers
+                g = (rank + k) % world
+                for a, offs in ((0, roffs), (1, eoffs), (2, eoffs)):
+                    cnt = int(offs[g + 1] - offs[g])
+                    if cnt:
+                        full[a][int(offs[g]):int(offs[g + 1])].copy_(self.peers[a][g][:cnt], non_blocking=True)
+            self.hdls[0].barrier(channel=1)      # every rank has finished pulling: buffers may be overwritten
+            self.done.record(self.side)
+        for t in full:
+            t.record_stream(self.side)
+        return dict(ptr=full[0], cols=full[1], vals=full[2], works=[], eoffs=eoffs, roffs=roffs, world=world, event=self.done)
 
 
 def replicate_wait(works) -> None:

@@ -198,3 +198,27 @@ def test_rmat_family_small(ctx, orc):
     assert gst.products == st["F"] and gst.rows_esc > 0 and gst.rows_merge > 0
     assert _cases.same_coo(down(R), want)
     dA.free(); R.free()
+
+
+def test_prepared_and_compressed_operands(ctx, orc):
+    """multiply() == consolidate + multiply_prepared, with B as COO and with B in compressed (pointer) form
+    -- the route the multi-GPU path takes."""
+    import spsparse_b200 as sp
+    from spsparse_b200 import gen
+    from _gpu import down
+    m = 3000
+    dA, dB, dW = sp.gen_banded(ctx, 0x51, m, 0, m), sp.gen_banded(ctx, 0x52, m, 0, m), sp.gen_vector(ctx, 0x53, m)
+    want = down(sp.multiply(ctx, 1.0, None, dA, ".", dW, dB, ".", None))
+    Ac, Bc = sp.consolidate(ctx, dA, (0, 1)), sp.consolidate(ctx, dB, (0, 1))
+    C1, st1 = sp.multiply_prepared(ctx, 1.0, None, Ac, 0, dW, Bc, 0, None)
+    assert _cases.same_coo(down(C1), want)
+    (p0, p1), pv = Bc.device_ptrs()
+    ptr, ext = Bc.dense_ptr()
+    assert ext == m
+    Bcsr = sp.CooArray.wrap_csr(ctx, (m, m), 0, ptr, p1, pv, Bc.size())
+    C2, st2 = sp.multiply_prepared(ctx, 1.0, None, Ac, 0, dW, Bcsr, 0, None)
+    assert _cases.same_coo(down(C2), want) and st2.products == st1.products
+    with pytest.raises(sp.SpbError):
+        sp.consolidate(ctx, Bcsr, (0, 1))  # a compressed-form array is a B operand only
+    for h in (dA, dB, dW, Ac, C1, C2, Bcsr, Bc):
+        h.free()

@@ -18,7 +18,7 @@ def _worker(rank, world, port, m, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as O
     from spsparse_b200 import gen
-    from spsparse_b200.dist import replicate_start, replicate_wait, row_range
+    from spsparse_b200.dist import replicate_csr_finish, replicate_csr_start, replicate_start, replicate_wait, row_range
     orc = O.port()
     r0, r1 = row_range(m, rank, world)
     a, b, w = gen.banded(5, m, r0, r1), gen.banded(6, m, r0, r1), gen.vector(7, m)
@@ -31,6 +31,12 @@ def _worker(rank, world, port, m, out_dir):
     # rows of the gathered B must be globally sorted: shards are row ranges in rank order
     key = Bf.idx[0].astype(np.int64) * m + Bf.idx[1]
     assert np.all(np.diff(key) > 0)
+    # compressed-form replication (what bench.py uses): local row pointers + cols + vals
+    lp = np.searchsorted(Bc.idx[0], np.arange(r0, r1)).astype(np.int32)
+    st = replicate_csr_start(torch.from_numpy(lp), local[1], local[2], rank, world)
+    ptr, cols, vals, total = replicate_csr_finish(st)
+    assert total == Bf.n and np.array_equal(cols.numpy(), Bf.idx[1]) and np.array_equal(vals.numpy(), Bf.val)
+    assert np.array_equal(ptr.numpy(), np.searchsorted(Bf.idx[0], np.arange(m + 1)))
     Cb = orc.multiply_mm(1.0, None, Ac, ".", O.Coo(w[0], w[1], w[2], (0,)), Bf, ".", None)
     np.savez(os.path.join(out_dir, f"c{rank}.npz"), i=Cb.idx[0], k=Cb.idx[1], v=Cb.val, sizes=np.array(sizes))
     dist.barrier()
