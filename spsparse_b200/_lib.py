@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libspsparse_b200.so")
+LIB_PATH = os.environ.get("SPB_LIB") or os.path.join(HERE, "lib", "libspsparse_b200.so")  # SPB_LIB: A/B experiments
 
 i32p = C.POINTER(C.c_int32)
 f64p = C.POINTER(C.c_double)

@@ -161,7 +161,7 @@ struct PassArgs {
     u32 *lookback;           // [tiles][256], zeroed
     u32 *ticket;             // zeroed
     int shift;               // digit = (key >> shift) & 255
-    int rank_mode;           // 0 ballots, 1 match.any, 2 timing-only fake (experiments; SPB_RANK_MODE)
+    int rank_mode;           // 0 ballots (default), 1 match.any (kept for A/B measurements; SPB_RANK_MODE)
 };
 
 template <bool PASS0>
@@ -244,10 +244,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
                 const u32 m = __ballot_sync(SPB_FULL_MASK, bit);
                 peers &= bit ? m : ~m;
             }
-        } else if (a.rank_mode == 1) {
-            peers = __match_any_sync(SPB_FULL_MASK, ok ? d : (u32)RS_RADIX);
         } else {
-            peers = 1u << lane;  // WRONG ranks: timing experiment only
+            peers = __match_any_sync(SPB_FULL_MASK, ok ? d : (u32)RS_RADIX);
         }
         u32 leader = ok ? (u32)(__ffs(peers) - 1) : lane;
         u32 before = 0;
