@@ -18,6 +18,9 @@ constexpr int RS_RADIX_BITS = 8;
 constexpr int RS_RADIX = 1 << RS_RADIX_BITS;
 constexpr int RS_NB = RS_RADIX + 1;  // +1: bucket of filtered / out-of-range items (never written)
 constexpr int RS_MAX_PASSES = 8;
+#ifndef RS_LOOKBACK
+#define RS_LOOKBACK 8  // predecessors read per look-back round trip
+#endif
 constexpr size_t RS_SMEM_BYTES =
     (size_t)RS_TILE * 16 + (size_t)RS_WARPS * RS_NB * sizeof(u32) + 64;
 
@@ -240,9 +243,12 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
             peers = __ballot_sync(SPB_FULL_MASK, ok);
 #pragma unroll
             for (int b = 0; b < RS_RADIX_BITS; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const u32 m = __ballot_sync(SPB_FULL_MASK, bit);
-                peers &= bit ? m : ~m;
+                // s = all-ones if bit b of the digit is set, else 0 (one sign-extending bit-field extract);
+                // lanes that agree with me on this bit are ~(m ^ s): a single three-input logic op
+                int sgn;
+                asm("bfe.s32 %0, %1, %2, 1;" : "=r"(sgn) : "r"(d), "r"(b));
+                const u32 m = __ballot_sync(SPB_FULL_MASK, sgn != 0);
+                peers &= ~(m ^ (u32)sgn);
             }
         } else {
             peers = __match_any_sync(SPB_FULL_MASK, ok ? d : (u32)RS_RADIX);
@@ -316,18 +322,18 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
         i64 p = (i64)tile - 1;
         bool done = false;
         while (!done) {
-            u32 w[4];
+            u32 w[RS_LOOKBACK];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < RS_LOOKBACK; ++u)
                 w[u] = (p - u >= 0) ? ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid) : RS_FLAG_INCL;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < RS_LOOKBACK; ++u) {
                 if (done) break;
                 while ((w[u] >> 30) == 0) w[u] = ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid);
                 excl += RS_VALUE(w[u]);
                 if ((w[u] >> 30) == 2) done = true;
             }
-            p -= 4;
+            p -= RS_LOOKBACK;
         }
         st_relaxed_u32(lb, RS_FLAG_INCL | (excl + total));
     }

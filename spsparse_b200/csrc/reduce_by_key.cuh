@@ -52,11 +52,17 @@ struct ReduceArgs {
     double C;
 };
 
+// Shared-memory layout of a tile: logical slot L holds entry (tile_base + L - 1), so L = 0 is the
+// predecessor of the tile and L = RK_TILE + 1 its successor.  One pad word every 8 slots makes the
+// per-thread blocks of 8 consecutive entries (stride 9 words) conflict-free.
+__device__ __forceinline__ u32 rk_phys(u32 L) { return L + (L >> 3); }
+constexpr int RK_SLOTS = RK_TILE + 2 + ((RK_TILE + 2) >> 3) + 1;
+
 template <int MODE>
 __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
-    __shared__ u64 s_keys[RK_TILE + 1];
-    __shared__ double s_vals[RK_TILE];
-    __shared__ u64 s_part[RK_IPT * RK_WARPS];  // low 32 bits: entries emitted, high 32 bits: row heads
+    __shared__ u64 s_keys[RK_SLOTS];     // input keys; later: staged output keys
+    __shared__ double s_vals[RK_SLOTS];  // input values; later: staged output values
+    __shared__ u64 s_warp[RK_WARPS];     // per-warp totals: entries | rows << 32
     __shared__ u32 s_tile;
     __shared__ u64 s_excl;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -67,90 +73,108 @@ __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
     const u32 n = *a.n_ptr;
     const u64 base = (u64)tile * RK_TILE;
     if (base >= n) return;
+    const u32 tile_n = (n - base < (u64)RK_TILE) ? (u32)(n - base) : (u32)RK_TILE;
 
-    // tile -> shared memory; s_keys[0] is the predecessor of the tile's first entry
+    // ---- coalesced load of the tile (+ predecessor and successor keys) ----------------------------
 #pragma unroll
     for (int k = 0; k < RK_IPT; ++k) {
         u32 p = (u32)k * RK_THREADS + tid;
-        u64 i = base + p;
-        if (i < n) {
-            s_keys[p + 1] = ld_stream_u64(a.keys + i);
-            s_vals[p] = ld_stream_f64(a.vals + i);
+        if (p < tile_n) {
+            s_keys[rk_phys(p + 1)] = ld_stream_u64(a.keys + base + p);
+            s_vals[rk_phys(p + 1)] = ld_stream_f64(a.vals + base + p);
         }
     }
     if (tid == 0) s_keys[0] = base ? a.keys[base - 1] : 0;
+    if (tid == 32 && base + RK_TILE < n) s_keys[rk_phys(RK_TILE + 1)] = a.keys[base + RK_TILE];
     __syncthreads();
 
-    const u32 lt = lanemask_lt();
+    // ---- each thread owns 8 consecutive entries -----------------------------------------------------
+    const u32 first = tid * RK_IPT;  // tile-local index of my first entry
+    const u32 mine = first < tile_n ? (tile_n - first < (u32)RK_IPT ? tile_n - first : (u32)RK_IPT) : 0;
+    u64 key[RK_IPT];
     double acc[RK_IPT];
-    u32 emit_bits = 0, defer_bits = 0, rhead_bits = 0, rank_in_warp[RK_IPT];
-    unsigned char rrank_in_warp[RK_IPT];
+    u32 head_bits = 0, rhead_bits = 0, defer_bits = 0;
+    if (mine) {
+        u64 prev = s_keys[rk_phys(first)];
 #pragma unroll
-    for (int k = 0; k < RK_IPT; ++k) {
-        u32 p = (u32)k * RK_THREADS + tid;
-        u64 i = base + p;
-        bool head = false;
-        double sum = 0.0;
-        if (i < n) {
-            const u64 key = s_keys[p + 1];
-            head = (a.policy == POLICY_KEEP_ALL) || (i == 0) || (key != s_keys[p]);
-            if (head) {
-                sum = s_vals[p];
-                if (a.policy == POLICY_ADD || a.policy == POLICY_REPLACE) {
-                    // fold the followers of this run, left to right
-                    u64 q = i + 1;
-                    u32 steps = 0;
-                    bool more = true;
-                    while (more && q < n) {
-                        u32 pq = (u32)(q - base);
-                        u64 kq;
-                        double vq;
-                        if (pq < RK_TILE) { kq = s_keys[pq + 1]; vq = s_vals[pq]; }
-                        else { kq = a.keys[q]; vq = (kq == key) ? a.vals[q] : 0.0; }
-                        if (kq != key) break;
-                        if (a.policy == POLICY_ADD) sum = __dadd_rn(sum, vq);
-                        else if (a.policy == POLICY_REPLACE) sum = vq;
-                        ++q;
-                        if (MODE == MODE_CONSOLIDATE && ++steps >= RK_LONG_RUN) {
-                            defer_bits |= 1u << k;  // finished by k_long_runs
-                            more = false;
+        for (int j = 0; j < RK_IPT; ++j) {
+            key[j] = s_keys[rk_phys(first + j + 1)];
+            acc[j] = s_vals[rk_phys(first + j + 1)];
+        }
+        int cur = -1;  // my open run (index of its head among my entries), -1: none yet
+#pragma unroll
+        for (int j = 0; j < RK_IPT; ++j) {
+            if ((u32)j < mine) {
+                const u64 before = j ? key[j - 1] : prev;
+                const bool head = (a.policy == POLICY_KEEP_ALL) || (base + first + j == 0) || (key[j] != before);
+                if (head) {
+                    head_bits |= 1u << j;
+                    if (want_rows && ((base + first + j == 0) || (key[j] >> a.bits_lo) != (before >> a.bits_lo)))
+                        rhead_bits |= 1u << j;
+                    cur = j;
+                } else if (cur >= 0) {  // follower of a run that started in my block: fold left to right
+                    double v = acc[j];
+#pragma unroll
+                    for (int h = 0; h < RK_IPT; ++h)
+                        if (h == cur) {
+                            if (a.policy == POLICY_ADD) acc[h] = __dadd_rn(acc[h], v);
+                            else if (a.policy == POLICY_REPLACE) acc[h] = v;
                         }
-                    }
                 }
             }
         }
-        bool emit = head;
-        if (MODE == MODE_ESC && head) {
-            // multiply_sparse.hpp:238: keep iff sum != 0 (NaN kept); masked columns never emitted
-            u32 kcol = (u32)(s_keys[p + 1] & ((1ull << a.bits_lo) - 1));
-            if (sum == 0.0 || (a.sk && a.sk[kcol] == 0.0)) emit = false;
+        // my last run may continue past my block: keep folding (shared memory, then global memory)
+        if (cur >= 0 && mine == (u32)RK_IPT && (a.policy == POLICY_ADD || a.policy == POLICY_REPLACE)) {
+            const u64 k0 = key[RK_IPT - 1];
+            double sum = 0.0;
+#pragma unroll
+            for (int h = 0; h < RK_IPT; ++h) if (h == cur) sum = acc[h];
+            u64 q = base + first + RK_IPT;  // global index of the next entry
+            u32 steps = 0;
+            while (q < n) {
+                const u32 L = (u32)(q - base) + 1;
+                u64 kq;
+                double vq = 0.0;
+                if (L <= (u32)RK_TILE) { kq = s_keys[rk_phys(L)]; vq = s_vals[rk_phys(L)]; }
+                else if (L == (u32)RK_TILE + 1) { kq = s_keys[rk_phys(L)]; if (kq == k0) vq = a.vals[q]; }
+                else { kq = a.keys[q]; if (kq == k0) vq = a.vals[q]; }
+                if (kq != k0) break;
+                if (a.policy == POLICY_ADD) sum = __dadd_rn(sum, vq); else sum = vq;
+                ++q;
+                if (MODE == MODE_CONSOLIDATE && ++steps >= RK_LONG_RUN) { defer_bits |= 1u << cur; break; }
+            }
+#pragma unroll
+            for (int h = 0; h < RK_IPT; ++h) if (h == cur) acc[h] = sum;
         }
-        acc[k] = sum;
-        u32 b = __ballot_sync(SPB_FULL_MASK, emit);
-        rank_in_warp[k] = __popc(b & lt);
-        if (emit) emit_bits |= 1u << k;
-        u32 rb = 0;
-        if (want_rows) {
-            // first output entry of a new leading index: its predecessor (always a different key) has another hi
-            bool rhead = emit && (i == 0 || (s_keys[p + 1] >> a.bits_lo) != (s_keys[p] >> a.bits_lo));
-            rb = __ballot_sync(SPB_FULL_MASK, rhead);
-            rrank_in_warp[k] = (unsigned char)__popc(rb & lt);
-            if (rhead) rhead_bits |= 1u << k;
-        }
-        if (lane == 0) s_part[k * RK_WARPS + warp] = (u64)__popc(b) | ((u64)__popc(rb) << 32);
     }
-    __syncthreads();
+    // ---- which heads are emitted ----------------------------------------------------------------------
+    u32 emit_bits = head_bits;
+    if (MODE == MODE_ESC) {
+        const u64 lo_mask = (1ull << a.bits_lo) - 1;
+#pragma unroll
+        for (int j = 0; j < RK_IPT; ++j)
+            if ((head_bits >> j) & 1u) {
+                // multiply_sparse.hpp:238: keep iff sum != 0 (NaN kept); masked columns never emitted
+                const u32 kcol = (u32)(key[j] & lo_mask);
+                if (acc[j] == 0.0 || (a.sk && a.sk[kcol] == 0.0)) emit_bits &= ~(1u << j);
+            }
+    }
+    // ---- slots: scan over threads, look-back over tiles --------------------------------------------------
+    const u64 my = (u64)__popc(emit_bits) | ((u64)__popc(rhead_bits) << 32);
+    const u64 incl = warp_incl_scan(my);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();  // also: every thread is done reading the input tile
     if (warp == 0) {
-        u64 x = s_part[2 * lane], y = s_part[2 * lane + 1];
-        u64 s = warp_incl_scan(x + y);  // both halves at once: neither can carry into the other
-        u64 total = __shfl_sync(SPB_FULL_MASK, s, 31);
-        s_part[2 * lane] = s - x - y;
-        s_part[2 * lane + 1] = s - y;
+        u64 w = lane < (u32)RK_WARPS ? s_warp[lane] : 0;
+        u64 ws = warp_incl_scan(w);
+        u64 total = __shfl_sync(SPB_FULL_MASK, ws, RK_WARPS - 1);
+        if (lane < (u32)RK_WARPS) s_warp[lane] = ws - w;
         // look-back value: entries in bits [0,31), rows in bits [31,62)
         u64 packed = (total & 0xffffffffull) | ((total >> 32) << 31);
         u64 excl = lookback_exclusive(a.state, tile, packed);
         if (lane == 0) {
             s_excl = excl;
+            s_tile = (u32)(total & 0xffffffffull);  // entries this tile emits
             if (base + RK_TILE >= n) {
                 u64 fin = excl + packed;
                 u32 n_out = (u32)(fin & 0x7fffffffull), n_rows = (u32)(fin >> 31);
@@ -162,36 +186,46 @@ __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
     __syncthreads();
     const u64 excl_rows = s_excl >> 31;
     const u64 excl = s_excl & 0x7fffffffull;
-    const u64 lo_mask = (1ull << a.bits_lo) - 1;
+    const u32 tile_out = s_tile;
+    const u64 before_me = s_warp[warp] + incl - my;
+    u32 slot = (u32)(before_me & 0xffffffffull);         // tile-local output slot of my first emitted head
+    u64 rslot = excl_rows + (before_me >> 32);
+    // ---- stage the outputs in shared memory (the input tile is dead now) --------------------------------
 #pragma unroll
-    for (int k = 0; k < RK_IPT; ++k) {
-        if (!((emit_bits >> k) & 1u)) continue;
-        u32 p = (u32)k * RK_THREADS + tid;
-        u64 key = s_keys[p + 1];
-        u64 slot = excl + (u32)s_part[k * RK_WARPS + warp] + rank_in_warp[k];
-        i32 hi = (i32)(key >> a.bits_lo), lo = (i32)(key & lo_mask);
-        if (want_rows && ((rhead_bits >> k) & 1u)) {
-            u64 rslot = excl_rows + (u32)(s_part[k * RK_WARPS + warp] >> 32) + rrank_in_warp[k];
-            a.row_start[rslot] = (u32)slot;
-            a.row_id[rslot] = hi;
-        }
-        if (MODE == MODE_ESC) hi += a.row_base;
-        if (MODE == MODE_CONSOLIDATE) {
-            a.out_hi[slot] = hi;
-            if (a.out_lo) a.out_lo[slot] = lo;
-            a.out_val[slot] = acc[k];
-            if ((defer_bits >> k) & 1u) {
-                u32 t = atomicAdd(a.long_count, 1u);
-                if (t < a.long_cap) { a.long_list[2 * t] = (u32)slot; a.long_list[2 * t + 1] = (u32)(base + p); }
+    for (int j = 0; j < RK_IPT; ++j) {
+        if ((emit_bits >> j) & 1u) {
+            double v = acc[j];
+            if (MODE == MODE_ESC) {
+                const u64 lo_mask = (1ull << a.bits_lo) - 1;
+                const i32 hi = (i32)(key[j] >> a.bits_lo) + a.row_base;
+                v = __dmul_rn(v, a.C);
+                v = __dmul_rn(v, a.si ? a.si[a.row_ids[hi]] : 1.0);
+                v = __dmul_rn(v, a.sk ? a.sk[(u32)(key[j] & lo_mask)] : 1.0);
             }
-        } else {
-            double v = __dmul_rn(acc[k], a.C);
-            v = __dmul_rn(v, a.si ? a.si[a.row_ids[hi]] : 1.0);
-            v = __dmul_rn(v, a.sk ? a.sk[lo] : 1.0);
-            a.out_hi[slot] = hi;  // compressed row number; mapped to i when copied into C
-            a.out_lo[slot] = lo;
-            a.out_val[slot] = v;
+            s_keys[slot] = key[j];
+            s_vals[slot] = v;
+            if (want_rows && ((rhead_bits >> j) & 1u)) {
+                a.row_start[rslot] = (u32)(excl + slot);
+                a.row_id[rslot] = (i32)(key[j] >> a.bits_lo);
+                ++rslot;
+            }
+            if (MODE == MODE_CONSOLIDATE && ((defer_bits >> j) & 1u)) {
+                u32 t = atomicAdd(a.long_count, 1u);
+                if (t < a.long_cap) { a.long_list[2 * t] = (u32)(excl + slot); a.long_list[2 * t + 1] = (u32)(base + first + j); }
+            }
+            ++slot;
         }
+    }
+    __syncthreads();
+    // ---- coalesced copy-out, unpacking the key into the two index vectors ----------------------------------
+    const u64 lo_mask = (1ull << a.bits_lo) - 1;
+    for (u32 t = tid; t < tile_out; t += RK_THREADS) {
+        const u64 k = s_keys[t];
+        i32 hi = (i32)(k >> a.bits_lo);
+        if (MODE == MODE_ESC) hi += a.row_base;
+        a.out_hi[excl + t] = hi;
+        if (a.out_lo) a.out_lo[excl + t] = (i32)(k & lo_mask);
+        a.out_val[excl + t] = s_vals[t];
     }
 }
 
