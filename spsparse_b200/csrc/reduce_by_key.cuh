@@ -58,8 +58,11 @@ struct ReduceArgs {
 __device__ __forceinline__ u32 rk_phys(u32 L) { return L + (L >> 3); }
 constexpr int RK_SLOTS = RK_TILE + 2 + ((RK_TILE + 2) >> 3) + 1;
 
+#ifndef RK_MIN_BLOCKS
+#define RK_MIN_BLOCKS 5
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
+__global__ void __launch_bounds__(RK_THREADS, RK_MIN_BLOCKS) k_reduce_by_key(ReduceArgs a) {
     __shared__ u64 s_keys[RK_SLOTS];     // input keys; later: staged output keys
     __shared__ double s_vals[RK_SLOTS];  // input values; later: staged output values
     __shared__ u64 s_warp[RK_WARPS];     // per-warp totals: entries | rows << 32
@@ -159,64 +162,78 @@ __global__ void __launch_bounds__(RK_THREADS) k_reduce_by_key(ReduceArgs a) {
                 if (acc[j] == 0.0 || (a.sk && a.sk[kcol] == 0.0)) emit_bits &= ~(1u << j);
             }
     }
-    // ---- slots: scan over threads, look-back over tiles --------------------------------------------------
+    // ---- slots inside the tile: scan over threads ---------------------------------------------------------
     const u64 my = (u64)__popc(emit_bits) | ((u64)__popc(rhead_bits) << 32);
     const u64 incl = warp_incl_scan(my);
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();  // also: every thread is done reading the input tile
+    u64 wbefore = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < RK_WARPS; ++w) {
+        const u64 t = s_warp[w];
+        if ((u32)w < warp) wbefore += t;
+        total += t;
+    }
+    const u64 before_me = wbefore + incl - my;
+    const u32 tile_out = (u32)(total & 0xffffffffull);
+    // ---- warp 0 chains the tiles (decoupled look-back) while the other warps already stage their outputs ----
     if (warp == 0) {
-        u64 w = lane < (u32)RK_WARPS ? s_warp[lane] : 0;
-        u64 ws = warp_incl_scan(w);
-        u64 total = __shfl_sync(SPB_FULL_MASK, ws, RK_WARPS - 1);
-        if (lane < (u32)RK_WARPS) s_warp[lane] = ws - w;
         // look-back value: entries in bits [0,31), rows in bits [31,62)
-        u64 packed = (total & 0xffffffffull) | ((total >> 32) << 31);
-        u64 excl = lookback_exclusive(a.state, tile, packed);
+        const u64 packed = (total & 0xffffffffull) | ((total >> 32) << 31);
+        const u64 excl0 = lookback_exclusive(a.state, tile, packed);
         if (lane == 0) {
-            s_excl = excl;
-            s_tile = (u32)(total & 0xffffffffull);  // entries this tile emits
+            s_excl = excl0;
             if (base + RK_TILE >= n) {
-                u64 fin = excl + packed;
-                u32 n_out = (u32)(fin & 0x7fffffffull), n_rows = (u32)(fin >> 31);
+                const u64 fin = excl0 + packed;
+                const u32 n_out = (u32)(fin & 0x7fffffffull), n_rows = (u32)(fin >> 31);
                 *a.out_count = n_out;
                 if (want_rows) { *a.row_count = n_rows; a.row_start[n_rows] = n_out; }
+            }
+        }
+    }
+    // stage the outputs in shared memory at their tile-local slots (the input tile is dead now)
+    {
+        u32 slot = (u32)(before_me & 0xffffffffull);
+#pragma unroll
+        for (int j = 0; j < RK_IPT; ++j) {
+            if ((emit_bits >> j) & 1u) {
+                double v = acc[j];
+                if (MODE == MODE_ESC) {
+                    const u64 lo_mask = (1ull << a.bits_lo) - 1;
+                    const i32 hi = (i32)(key[j] >> a.bits_lo) + a.row_base;
+                    v = __dmul_rn(v, a.C);
+                    v = __dmul_rn(v, a.si ? a.si[a.row_ids[hi]] : 1.0);
+                    v = __dmul_rn(v, a.sk ? a.sk[(u32)(key[j] & lo_mask)] : 1.0);
+                }
+                s_keys[slot] = key[j];
+                s_vals[slot] = v;
+                ++slot;
             }
         }
     }
     __syncthreads();
     const u64 excl_rows = s_excl >> 31;
     const u64 excl = s_excl & 0x7fffffffull;
-    const u32 tile_out = s_tile;
-    const u64 before_me = s_warp[warp] + incl - my;
-    u32 slot = (u32)(before_me & 0xffffffffull);         // tile-local output slot of my first emitted head
-    u64 rslot = excl_rows + (before_me >> 32);
-    // ---- stage the outputs in shared memory (the input tile is dead now) --------------------------------
+    // row starts and deferred long runs need the global slot
+    if (MODE == MODE_CONSOLIDATE && (rhead_bits | defer_bits)) {
+        u32 slot = (u32)(before_me & 0xffffffffull);
+        u64 rslot = excl_rows + (before_me >> 32);
 #pragma unroll
-    for (int j = 0; j < RK_IPT; ++j) {
-        if ((emit_bits >> j) & 1u) {
-            double v = acc[j];
-            if (MODE == MODE_ESC) {
-                const u64 lo_mask = (1ull << a.bits_lo) - 1;
-                const i32 hi = (i32)(key[j] >> a.bits_lo) + a.row_base;
-                v = __dmul_rn(v, a.C);
-                v = __dmul_rn(v, a.si ? a.si[a.row_ids[hi]] : 1.0);
-                v = __dmul_rn(v, a.sk ? a.sk[(u32)(key[j] & lo_mask)] : 1.0);
+        for (int j = 0; j < RK_IPT; ++j) {
+            if ((emit_bits >> j) & 1u) {
+                if ((rhead_bits >> j) & 1u) {
+                    a.row_start[rslot] = (u32)(excl + slot);
+                    a.row_id[rslot] = (i32)(key[j] >> a.bits_lo);
+                    ++rslot;
+                }
+                if ((defer_bits >> j) & 1u) {
+                    u32 t = atomicAdd(a.long_count, 1u);
+                    if (t < a.long_cap) { a.long_list[2 * t] = (u32)(excl + slot); a.long_list[2 * t + 1] = (u32)(base + first + j); }
+                }
+                ++slot;
             }
-            s_keys[slot] = key[j];
-            s_vals[slot] = v;
-            if (want_rows && ((rhead_bits >> j) & 1u)) {
-                a.row_start[rslot] = (u32)(excl + slot);
-                a.row_id[rslot] = (i32)(key[j] >> a.bits_lo);
-                ++rslot;
-            }
-            if (MODE == MODE_CONSOLIDATE && ((defer_bits >> j) & 1u)) {
-                u32 t = atomicAdd(a.long_count, 1u);
-                if (t < a.long_cap) { a.long_list[2 * t] = (u32)(excl + slot); a.long_list[2 * t + 1] = (u32)(base + first + j); }
-            }
-            ++slot;
         }
     }
-    __syncthreads();
     // ---- coalesced copy-out, unpacking the key into the two index vectors ----------------------------------
     const u64 lo_mask = (1ull << a.bits_lo) - 1;
     for (u32 t = tid; t < tile_out; t += RK_THREADS) {
