@@ -243,6 +243,12 @@ def run_ours(args):
         ms_spgemm = float(np.mean([s.ms_symbolic + s.ms_numeric for _, _, s in acc]))
         ms_prep = float(np.mean([s.ms_prepare for _, _, s in acc]))
         pass_bytes = 32.0 * sa.n_kept  # one radix pass: read 8B key + 8B value, write both
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tp):  # dram__bytes_read+write of this kernel from an `ncu --set full` capture of this command
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_per_entry"] * sa.n_kept
+            traffic_src = f"{tj['dram_bytes_per_entry']:.2f} B/entry measured by ncu at {tj['entries_per_launch']} entries/launch ({tj['report']})"
         pass_gbs = pass_bytes / (ms_pass * 1e-3) / 1e9 if ms_pass > 0 else 0.0
         spgemm_bytes = 16.0 * st.products + 56.0 * st.nnz_a + 16.0 * st.nnz_c + 16.0 * st.rows_a
         cons_bytes = lambda s: s.n_in * (8 + 16) + 32.0 * s.n_kept * s.passes + 16.0 * s.n_out  # noqa: E731
@@ -327,7 +333,7 @@ def run_ours(args):
                                                      [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)]))},
             "roofline": {"bound": "hbm", "kernel": "k_radix_pass<false> (one 8-bit LSD scatter pass, key+value)",
                          "achieved": pass_gbs, "peak": hbm, "unit": "GB/s", "frac": pass_gbs / hbm,
-                         "traffic": None, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
+                         "traffic": traffic, "traffic_source": traffic_src, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
                          "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": e2e,
