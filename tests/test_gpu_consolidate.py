@@ -165,3 +165,22 @@ def test_properties_at_scale(ctx):
     assert np.array_equal(idxc[0][o], idx[0]) and np.array_equal(idxc[1][o], idx[1]) and np.array_equal(valc[o], val)
     for x in (A, R, R2, Rc):
         x.free()
+
+
+def test_medium_scale_against_oracle(ctx, orc):
+    """4M entries of the config-2 family with input zeros, every policy and both orders, against the oracle."""
+    import spsparse_b200 as sp
+    from _gpu import down
+    n = 4_000_000
+    a = orc.gen_dup_coo(0x5EED0002, 0, n, int(0.7 * n), 16, 1024)
+    A = sp.gen_dup_coo(ctx, 0x5EED0002, 0, n, int(0.7 * n), 16, 1024)
+    for so, pol in (((0, 1), O.ADD), ((1, 0), O.ADD), ((0, 1), O.LEAVE_ALONE), ((1, 0), O.REPLACE)):
+        R = sp.consolidate(ctx, A, so, pol)
+        want = orc.consolidate(a, so, pol)
+        assert _cases.same_coo(down(R), want), (so, pol)
+        assert np.array_equal(R.dim_beginnings(), orc.dim_beginnings(want))
+        assert np.array_equal(R.sorted_permutation(so), np.arange(R.size()))  # already sorted: identity
+        R.free()
+    perm = A.sorted_permutation((0, 1))
+    assert np.array_equal(perm, orc.sorted_permutation(a, (0, 1)))
+    A.free()

@@ -222,3 +222,36 @@ def test_prepared_and_compressed_operands(ctx, orc):
         sp.consolidate(ctx, Bcsr, (0, 1))  # a compressed-form array is a B operand only
     for h in (dA, dB, dW, Ac, C1, C2, Bcsr, Bc):
         h.free()
+
+
+def test_medium_scale_against_oracle(ctx, orc):
+    """Mid-size members of BASELINE configs 3, 4 and 5 (10^5..10^6 rows, millions of products): full
+    bit-for-bit comparison with the CPU oracle's row-wise evaluation -- structure AND values."""
+    import spsparse_b200 as sp
+    from spsparse_b200 import gen
+    from _gpu import down
+    # config 5 family, 400k rows (2M entries per operand, ~10M products)
+    m = 400_000
+    a, b, w = gen.banded(0x5EED0005, m, 0, m), gen.banded(0x5EED0015, m, 0, m), gen.vector(0x5EED0025, m)
+    want, st = orc.multiply_mm(1.0, None, O.Coo(*a), ".", O.Coo(w[0], w[1], w[2], (0,)), O.Coo(*b), ".", None, want_stats=True)
+    dA, dB, dW = sp.gen_banded(ctx, 0x5EED0005, m, 0, m), sp.gen_banded(ctx, 0x5EED0015, m, 0, m), sp.gen_vector(ctx, 0x5EED0025, m)
+    R, gst = sp.multiply(ctx, 1.0, None, dA, ".", dW, dB, ".", None, stats=True)
+    assert gst.products == st["F"] and _cases.same_coo(down(R), want)
+    for h in (dA, dB, dW, R):
+        h.free()
+    # config 3 family, 320x312 fine grid on 100x100 coarse grid (~16M products)
+    shp, idx, val = gen.regrid(0x5EED0003, 320, 312, 100, 100)
+    s = gen.vector(0x5EED0013, shp[1])
+    want, st = orc.multiply_mm(1.0, None, O.Coo(shp, idx, val), ".", O.Coo(s[0], s[1], s[2], (0,)), O.Coo(shp, idx, val), "T", None, want_stats=True)
+    dA, dS = sp.gen_regrid(ctx, 0x5EED0003, 320, 312, 100, 100), sp.gen_vector(ctx, 0x5EED0013, shp[1])
+    R, gst = sp.multiply(ctx, 1.0, None, dA, ".", dS, dA, "T", None, stats=True)
+    assert gst.products == st["F"] and _cases.same_coo(down(R), want)
+    for h in (dA, dS, R):
+        h.free()
+    # config 4 family, R-MAT scale 15 (skewed: most products go through expand-sort-compress)
+    shp, idx, val = gen.rmat(0x5EED0004, 15, 4 << 15)
+    want, st = orc.multiply_mm(1.0, None, O.Coo(shp, idx, val), ".", None, O.Coo(shp, idx, val), ".", None, want_stats=True)
+    dA = sp.gen_rmat(ctx, 0x5EED0004, 15, 4 << 15)
+    R, gst = sp.multiply(ctx, 1.0, None, dA, ".", None, dA, ".", None, stats=True)
+    assert gst.products == st["F"] and gst.products_esc > 0 and _cases.same_coo(down(R), want)
+    dA.free(); R.free()
