@@ -467,6 +467,29 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
     }
     for x in (A, s, Ar, Bt):
         x.free()
+    # ---- config 4: R-MAT A*A, full multiply() incl. its consolidations (skewed rows: both bins in use) -----
+    sc = args.rmat_scale
+    A = sp.gen_rmat(ctx, 0x5EED0004, sc, 4 << sc)
+    for _ in range(max(1, args.warmup - 1)):
+        Cm, st = sp.multiply(ctx, 1.0, None, A, ".", None, A, ".", None, stats=True); Cm.free()
+    sts = []
+    for _ in range(args.steps):
+        Cm, st = sp.multiply(ctx, 1.0, None, A, ".", None, A, ".", None, stats=True)
+        sts.append(st); Cm.free()
+    ms_k = float(np.mean([x.ms_symbolic + x.ms_numeric for x in sts]))
+    model = 16.0 * st.products + 56.0 * st.nnz_a + 16.0 * st.nnz_c + 16.0 * st.rows_a
+    out["spgemm_config4"] = {
+        "workload": f"BASELINE config 4 family: R-MAT scale {sc} (a,b,c,d = .57,.19,.19,.05; edge factor 4) A*A",
+        "note": "scale 24 as named cannot be held by the reference's own container: its product has far more than 2^31 "
+                "entries (VectorCooArray offsets are int, algorithm.hpp:419; 16 B x nnzC would also exceed 180 GB); the "
+                "library returns SPB_ERR_TOO_LARGE there. Scale 20 is the largest power of two whose product fits.",
+        "products": st.products, "products_hash": st.products_hash, "products_esc": st.products_esc, "nnz_a": st.nnz_a, "nnz_c": st.nnz_c,
+        "rows_merge": st.rows_merge, "rows_hash": st.rows_hash, "rows_esc": st.rows_esc,
+        "ms_symbolic": float(np.mean([x.ms_symbolic for x in sts])),
+        "ms_numeric": float(np.mean([x.ms_numeric for x in sts])), "ms_prepare_incl_consolidate": float(np.mean([x.ms_prepare for x in sts])),
+        "products_per_sec": st.products / (ms_k * 1e-3), "model_bytes": model, "model_frac": model / (ms_k * 1e-3) / 1e9 / hbm,
+    }
+    A.free()
     return out
 
 
@@ -567,6 +590,7 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows of the banded problem (headline: 1e8)")
     ap.add_argument("--cons-entries", type=int, default=200_000_000)
     ap.add_argument("--regrid", type=int, nargs=4, default=[3200, 3125, 1000, 1000])
+    ap.add_argument("--rmat-scale", type=int, default=20)
     ap.add_argument("--cpu-rows", type=int, default=3000)
     ap.add_argument("--cpu-cons-entries", type=int, default=10_000_000)
     ap.add_argument("--ref-rows", type=int, default=2000)

@@ -120,6 +120,8 @@ typedef struct {
     uint64_t rows_esc;       /* rows done by expand-sort-compress */
     uint64_t products_esc;
     uint64_t nnz_c;
+    uint64_t rows_hash;      /* longer rows done by the bitmap + shared-memory hash-accumulator kernels */
+    uint64_t products_hash;
     float ms_prepare;        /* consolidations of A and B, CSR build, scale densify */
     float ms_symbolic, ms_numeric, ms_total;
 } spb_mm_stats;

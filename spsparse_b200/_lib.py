@@ -26,6 +26,7 @@ class MMStats(C.Structure):
     _fields_ = [("products", C.c_uint64), ("nnz_a", C.c_uint64), ("nnz_b", C.c_uint64),
                 ("rows_a", C.c_uint64), ("rows_merge", C.c_uint64), ("rows_esc", C.c_uint64),
                 ("products_esc", C.c_uint64), ("nnz_c", C.c_uint64),
+                ("rows_hash", C.c_uint64), ("products_hash", C.c_uint64),
                 ("ms_prepare", C.c_float), ("ms_symbolic", C.c_float), ("ms_numeric", C.c_float),
                 ("ms_total", C.c_float)]
 

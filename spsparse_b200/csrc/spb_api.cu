@@ -113,6 +113,8 @@ struct spb_ctx {
     int sm_count;
     u32 merge_max_products;  // bin threshold, env SPB_MERGE_MAX_PRODUCTS
     u64 esc_chunk;           // products per expand-sort-compress chunk, env SPB_ESC_CHUNK
+    u64 hash_min_products;   // long rows with at least this many products use the bitmap + hash-accumulator kernels; ~0 = never (SPB_HASH_MIN_PRODUCTS)
+    int hash_variant;        // 0: 1024 threads x 10240 outputs per item, 1: 512 x 5120 (two blocks per SM)  (SPB_HASH_VARIANT)
     u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
     DevPool pool;
 };
@@ -222,6 +224,14 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     s = getenv("SPB_ESC_CHUNK");
     c->esc_chunk = s ? strtoull(s, nullptr, 10) : (1ull << 27);
     c->launches = 0;
+    s = getenv("SPB_HASH_MIN_PRODUCTS");
+    c->hash_min_products = s ? (strcmp(s, "off") == 0 ? ~0ull : strtoull(s, nullptr, 10)) : 512ull;
+    s = getenv("SPB_HASH_VARIANT");
+    c->hash_variant = s ? atoi(s) : 0;
+    CK(cudaFuncSetAttribute(k_hash_symbolic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
+    CK(cudaFuncSetAttribute(k_hash_symbolic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
+    CK(cudaFuncSetAttribute(k_hash_numeric<1024, 10240, 16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<1024, 10240, 16384>)));
+    CK(cudaFuncSetAttribute(k_hash_numeric<512, 5120, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<512, 5120, 8192>)));
     if (c->esc_chunk < 1) c->esc_chunk = 1;
     *out = c;
     return SPB_OK;
@@ -747,14 +757,15 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     u32 *row_cnt;
     u64 *ent_off = nullptr, *esc_f = nullptr, *esc_off, *c_ptr;
     unsigned char *row_cls;
-    ull *stats;  // [0] F merged rows, [1] rows merged, [2] rows ESC, [3] F ESC rows
+    ull *stats;  // [0] F merged rows, [1] rows merged, [2] rows long, [3] F ESC rows, [4] F HASH rows, [5] rows HASH
     CKR(ws.get(&row_cls, nrows));
     CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
-    CKR(ws.zeroed(&stats, 4));
+    CKR(ws.zeroed(&stats, 8));
     const u32 cap = (u32)ctx->sm_count * 32;
     ++ctx->launches, k_merge_count<<<(u32)div_up(nrows ? nrows : 1, 128), 128, 0, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, stats);
     CK(cudaGetLastError());
-    ull h_stats[4];
+    ull h_stats[8];
+    u32 *hash_rows = nullptr;
     CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (h_stats[2]) {
@@ -765,11 +776,39 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         CKR(ws.get(&esc_f, nrows));
         ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
         CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
-        ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, stats);
+        // second-level bin: long rows with enough products use the bitmap + hash accumulators (needs the columns to fit the bitmap)
+        const bool hash_ok = n_cols <= HASH_MAX_COLS && ctx->hash_min_products != ~0ull;
+        if (hash_ok) CKR(ws.get(&hash_rows, h_stats[2]));
+        ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, ctx->hash_min_products, hash_rows, stats);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ws.release(ent_f);
+    }
+
+    // ---- longer rows: bitmap count pass (the emit pass and the hash-accumulator numeric pass follow the placement) ----
+    HashArgs ha;
+    memset(&ha, 0, sizeof ha);
+    u32 hs_grid = 0;
+    size_t hs_smem = 0;
+    u32 hash_cap = ctx->hash_variant == 1 ? 5120u : 10240u;
+    if (const char *e = getenv("SPB_HASH_ITEM_CAP")) {  // tests: cut rows into smaller work items
+        const u32 v = (u32)strtoul(e, nullptr, 10);
+        if (v >= 1 && v < hash_cap) hash_cap = v;
+    }
+    if (h_stats[5]) {
+        ha.rows = hash_rows;
+        ha.nrows = (u32)h_stats[5];
+        ha.wpw = (u32)(div_up(div_up(n_cols, 32), HS_WARPS) + 31) & ~31u;
+        ha.cap = hash_cap;
+        ha.row_cnt = row_cnt;
+        hs_grid = ha.nrows < (u32)ctx->sm_count ? ha.nrows : (u32)ctx->sm_count;
+        hs_smem = (size_t)HS_WARPS * ha.wpw * sizeof(u32);
+        CKR(ws.zeroed(&ha.next, 4));
+        ha.shrunk = ha.next + 1;
+        ha.n_items = ha.next + 2;
+        ++ctx->launches, k_hash_symbolic<false><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
+        CK(cudaGetLastError());
     }
 
     // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
@@ -863,12 +902,71 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     }
     for (auto &ch : chunks)
         if (ch.n) ++ctx->launches, k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
+    u32 h_shrunk = 0;
+    if (h_stats[5] && nnz_c) {
+        // emit pass: the bitmap again, now writing the rows' columns into C and cutting the rows into work items
+        u32 h_items = 0;
+        const u64 max_items = h_stats[5] + nnz_c / hash_cap + 1;
+        CKR(ws.get(&ha.items, max_items));
+        CK(cudaMemsetAsync(ha.next, 0, sizeof(u32), ctx->stream));
+        ha.c_ptr = c_ptr; ha.c_i = out->idx[0]; ha.c_k = out->idx[1]; ha.c_v = out->val;
+        ++ctx->launches, k_hash_symbolic<true><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync(ha.next, 0, sizeof(u32), ctx->stream));
+        CK(cudaMemcpyAsync(&h_items, ha.n_items, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (h_items) {
+            if (tracing()) CKR(ws.zeroed(&ha.dbg, 16));
+            ++ctx->launches;
+            if (ctx->hash_variant == 1) {
+                const u32 g = h_items < 2u * ctx->sm_count ? h_items : 2u * ctx->sm_count;
+                k_hash_numeric<512, 5120, 8192><<<g, 512, sizeof(HashSmem<512, 5120, 8192>), ctx->stream>>>(m, ha, h_items);
+            } else {
+                const u32 g = h_items < (u32)ctx->sm_count ? h_items : (u32)ctx->sm_count;
+                k_hash_numeric<1024, 10240, 16384><<<g, 1024, sizeof(HashSmem<1024, 10240, 16384>), ctx->stream>>>(m, ha, h_items);
+            }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&h_shrunk, ha.shrunk, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            if (ha.dbg) {
+                ull d[16];
+                CK(cudaMemcpyAsync(d, ha.dbg, sizeof d, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                fprintf(stderr, "[spb] mm hash numeric: %u items (%llu), %llu staged chunks, %llu steps (%llu warp-pipelined), %llu entry barriers\n", h_items, d[0], d[1], d[2], d[4], d[3]);
+                const double tot = (double)(d[5] + d[6] + d[7] + d[8] + d[9]) / 100.0;
+                fprintf(stderr, "[spb] mm hash numeric clocks: setup %.1f%%, staging %.1f%%, steps %.1f%%, warp-pipelined steps %.1f%%, output %.1f%%; %.0f clocks per item\n",
+                        d[5] / tot, d[6] / tot, d[7] / tot, d[8] / tot, d[9] / tot, tot * 100.0 / (double)d[0]);
+            }
+        }
+    }
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_shrunk) {
+        // some hash-accumulator outputs summed to exact zero and were dropped: close the gaps (rare)
+        unsigned char *keep;
+        u64 *slot;
+        CKR(ws.get(&keep, nnz_c));
+        CKR(ws.get(&slot, nnz_c + 1));
+        ++ctx->launches, k_live_flags<<<grid_for(nnz_c, 256, cap), 256, 0, ctx->stream>>>(out->idx[0], nnz_c, keep);
+        CKR((exclusive_scan<unsigned char, u64>(ctx, ws, keep, slot, nnz_c)));
+        const u64 nnz2 = nnz_c - h_shrunk;
+        i32 *i2, *k2;
+        double *v2;
+        size_t c2 = nnz2 ? nnz2 : 1;
+        CK(ctx->pool.alloc((void **)&i2, c2 * sizeof(i32)));
+        CK(ctx->pool.alloc((void **)&k2, c2 * sizeof(i32)));
+        CK(ctx->pool.alloc((void **)&v2, c2 * sizeof(double)));
+        ++ctx->launches, k_compact_entries<<<grid_for(nnz_c, 256, cap), 256, 0, ctx->stream>>>(nnz_c, keep, slot, out->idx[0], out->idx[1], out->val, i2, k2, v2);
+        CK(cudaGetLastError());
+        ctx->pool.release(out->idx[0]); ctx->pool.release(out->idx[1]); ctx->pool.release(out->val);
+        out->idx[0] = i2; out->idx[1] = k2; out->val = v2;
+        out->n = nnz_c = nnz2;
+    }
     const int t_num = tm.mark();
     CK(cudaStreamSynchronize(ctx->stream));
     if (tracing()) fprintf(stderr, "[spb] mm: total host since prepare %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (st) {
-        st->products = h_stats[0] + h_stats[3]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2]; st->products_esc = h_stats[3];
+        st->products = h_stats[0] + h_stats[3] + h_stats[4]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2] - h_stats[5];
+        st->products_esc = h_stats[3]; st->rows_hash = h_stats[5]; st->products_hash = h_stats[4];
         st->nnz_a = A->n; st->nnz_b = B->n; st->rows_a = nrows; st->nnz_c = nnz_c;
         st->ms_prepare = tm.ms(t_begin, t_prep);
         st->ms_symbolic = tm.ms(t_prep, t_sym);

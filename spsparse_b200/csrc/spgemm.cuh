@@ -20,7 +20,10 @@
 #include "common.cuh"
 
 constexpr int MERGE_MAX_LISTS = 8;
-enum { ROW_SKIP = 0, ROW_MERGE = 1, ROW_ESC = 2 };
+#ifndef MR_MIN_BLOCKS
+#define MR_MIN_BLOCKS 1
+#endif
+enum { ROW_SKIP = 0, ROW_MERGE = 1, ROW_ESC = 2, ROW_HASH = 3 };
 
 struct MMOperands {
     // op(A), consolidated, sorted by (row, inner): compressed rows
@@ -54,20 +57,36 @@ __global__ void k_entry_products(MMOperands m, const i32 *__restrict__ a_row, u3
     }
 }
 
-// ---- long rows only: product count per row from the per-entry prefix sums -------------------------
-// stats: [0] F of merged rows, [1] rows merged, [2] rows ESC, [3] F of ESC rows
-__global__ void k_esc_row_products(MMOperands m, const u64 *__restrict__ ent_off, const unsigned char *__restrict__ row_cls,
-                                   u64 *esc_f, ull *stats) {
-    u64 f_esc = 0;
+// ---- long rows only: product count per row from the per-entry prefix sums; second-level binning -----
+// Long rows with at least hash_min_products products go to the bitmap + hash-accumulator kernels (ROW_HASH; only
+// offered when the output columns fit the shared-memory bitmap), the rest stay with expand-sort-compress (ROW_ESC).
+// stats: [0] F merged rows, [1] rows merged, [2] rows long (ESC+HASH), [3] F ESC rows, [4] F HASH rows, [5] rows HASH
+__global__ void k_esc_row_products(MMOperands m, const u64 *__restrict__ ent_off, unsigned char *row_cls, u64 *esc_f,
+                                   u64 hash_min_products, u32 *hash_rows, ull *stats) {
+    u64 f_esc = 0, f_hash = 0;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < m.nrows; r += (u64)gridDim.x * blockDim.x) {
         u64 f = 0;
-        if (row_cls[r] == ROW_ESC) f = ent_off[m.arow_start[r + 1]] - ent_off[m.arow_start[r]];
+        if (row_cls[r] == ROW_ESC) {
+            f = ent_off[m.arow_start[r + 1]] - ent_off[m.arow_start[r]];
+            if (hash_rows && f >= hash_min_products) {
+                row_cls[r] = ROW_HASH;
+                hash_rows[atomicAdd(&stats[5], 1ull)] = (u32)r;
+                f_hash += f;
+                f = 0;
+            }
+        }
         esc_f[r] = f;
         f_esc += f;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) f_esc += __shfl_xor_sync(SPB_FULL_MASK, f_esc, o);
-    if (lane_id() == 0 && f_esc) atomicAdd(&stats[3], (ull)f_esc);
+    for (int o = 16; o > 0; o >>= 1) {
+        f_esc += __shfl_xor_sync(SPB_FULL_MASK, f_esc, o);
+        f_hash += __shfl_xor_sync(SPB_FULL_MASK, f_hash, o);
+    }
+    if (lane_id() == 0) {
+        if (f_esc) atomicAdd(&stats[3], (ull)f_esc);
+        if (f_hash) atomicAdd(&stats[4], (ull)f_hash);
+    }
 }
 
 // ---- short rows: k-way merge in registers, one thread per row -----------------------------------
@@ -172,7 +191,7 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
 }
 
 // stats: [0] F of merged rows, [1] rows merged, [2] rows ESC
-__global__ void __launch_bounds__(128) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
+__global__ void __launch_bounds__(128, MR_MIN_BLOCKS) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = ROW_SKIP;
@@ -266,7 +285,7 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
 }
 
 template <int STAGE>
-__global__ void __launch_bounds__(MR_THREADS) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
+__global__ void __launch_bounds__(MR_THREADS, MR_MIN_BLOCKS) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
                                                               const u64 *__restrict__ c_ptr, i32 *c_i, i32 *c_k,
                                                               double *c_v) {
     __shared__ i32 s_k[MR_THREADS * (STAGE + 1)];
@@ -291,6 +310,448 @@ __global__ void __launch_bounds__(MR_THREADS) k_merge_numeric(MMOperands m, cons
     else if (maxlen <= 4) merge_rows_warp<4, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
     else if (maxlen <= 6) merge_rows_warp<6, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
     else merge_rows_warp<8, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+}
+
+// ---- longer rows: shared-memory bitmap (symbolic) + shared-memory hash accumulators (numeric) ----------
+// Symbolic, one block per row: every product sets the bit of its column in a shared-memory bitmap (order-free,
+// so all warps work at once); scanning the bitmap yields the row's DISTINCT OUTPUT COLUMNS ALREADY IN ASCENDING
+// ORDER -- no sort.  The count pass stores their number; after the rows are placed, the emit pass repeats the
+// bitmap and writes the columns straight into C and cuts the row into work items of <= HASH_CAP outputs.
+//
+// Numeric, one block per item: the item's columns (sorted, read back from C) are inserted into a shared-memory
+// hash table that maps column -> output rank; the accumulators sit in shared memory in rank order.  The A
+// entries of the row are staged NT at a time (for an item that covers only part of the row, each B row is
+// narrowed to the item's column range by binary search), their products are packed NT per step (prefix sums +
+// search), looked up in the table and added.  Order: steps run in ascending (j, k); two products of one step that
+// hit the same output (different j, same k) are serialised by a claim word per output (atomicMin of the thread
+// number, lowest = smallest j first).  Every output therefore adds its terms in ascending j starting from 0 --
+// the reference's order (multiply_sparse.hpp:219-236) -- and the sums are bit-identical to the reference's.
+// An output whose sum is exactly 0 is dropped by the reference (:238); here it leaves a tombstone that the host
+// closes afterwards (rare: exact cancellation only).
+constexpr int HS_THREADS = 1024;            // symbolic (bitmap) kernel
+constexpr int HS_WARPS = HS_THREADS / 32;
+constexpr u32 HASH_MAX_COLS = 1572864;      // 192 KB of bitmap
+
+struct HashArgs {
+    const u32 *rows;     // compressed row numbers of the ROW_HASH rows
+    u32 nrows;
+    u32 *next;           // work counter (zeroed before every launch)
+    u32 wpw;             // bitmap words per warp of the symbolic kernel (multiple of 32; HS_WARPS * wpw * 32 >= columns)
+    u32 cap;             // outputs per numeric work item (HASH_CAP of the numeric kernel that will run)
+    u32 *row_cnt;        // count pass: number of distinct, unmasked output columns of the row
+    const u64 *c_ptr;    // emit + numeric
+    i32 *c_i, *c_k;
+    double *c_v;
+    u64 *items;          // emit: (row << 32 | part), appended in any order
+    u32 *n_items;
+    u32 *shrunk;         // numeric: number of outputs dropped (written as tombstones)
+    ull *dbg;            // numeric, tracing only: [0] items, [1] staged chunks, [2] steps, [3] barriers between entries, [4] warp-pipelined steps, [5..9] clocks per phase
+};
+
+// ---- staged entries ---------------------------------------------------------------------------------------------
+// Both kernels take the A entries of a row NT at a time: every thread looks up one entry's B row, entries without
+// products are squeezed out, and the products of the chunk are numbered 0..T-1 in (entry, position) order
+// (pre[x] = number of the first product of staged entry x, strictly increasing, pre[nE] = T).  Threads then take
+// products, not entries -- a 13000-entry hub row and a 1-entry row cost the same per product.
+//
+// Entry of product p_first + lane, for a warp whose first product is p_first: a two-level 32-ary search by the whole
+// warp finds the entry of p_first (from xs, an entry known to start at or before p_first), one more probe per lane
+// finds the (at most 32, entries are non-empty) entry boundaries inside the warp's 32 products.
+__device__ __forceinline__ u32 staged_entry(const u32 *pre, u32 nE, u32 xs, u32 p_first) {
+    const u32 lane = lane_id();
+    u32 idx = xs + lane * 32;
+    const u32 c1 = __popc(__ballot_sync(SPB_FULL_MASK, idx < nE && pre[idx] <= p_first));
+    const u32 blk = xs + (c1 ? c1 - 1 : 0) * 32;
+    idx = blk + lane;
+    const u32 c2 = __popc(__ballot_sync(SPB_FULL_MASK, idx < nE && pre[idx] <= p_first));
+    const u32 x_first = blk + (c2 ? c2 - 1 : 0);
+    idx = x_first + 1 + lane;
+    const u32 d = (idx <= nE ? pre[idx] : 0xffffffffu) - p_first;
+    const u32 bounds = __reduce_or_sync(SPB_FULL_MASK, d < 32 ? 1u << d : 0u);
+    return x_first + __popc(bounds & (0xffffffffu >> (31 - lane)));
+}
+
+// Squeezes the (bs, len) pairs of the NT threads into st_bs/st_pre (and calls keep(slot) for the survivors);
+// returns the number of staged entries and products.  Two barriers.
+template <int NT, typename Keep>
+__device__ __forceinline__ void stage_entries(u32 bs, u32 len, u32 *st_bs, u32 *st_pre, u32 (*wsum)[NT / 32], u32 &nE, u32 &T, Keep keep) {
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 incl = warp_incl_scan(len);
+    const u32 live = __ballot_sync(SPB_FULL_MASK, len != 0);
+    if (lane == 31) { wsum[0][warp] = incl; wsum[1][warp] = __popc(live); }
+    __syncthreads();
+    u32 pre = incl - len, slot = __popc(live & lanemask_lt());
+    T = 0; nE = 0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) {
+        const u32 t = wsum[0][w], c = wsum[1][w];
+        if ((u32)w < warp) { pre += t; slot += c; }
+        T += t;
+        nE += c;
+    }
+    if (len) { st_bs[slot] = bs; st_pre[slot] = pre; keep(slot); }
+    if (tid == 0) st_pre[nE] = T;
+    __syncthreads();
+}
+
+// ---- symbolic: bitmap --------------------------------------------------------------------------------------------
+template <bool EMIT>
+__global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, HashArgs a) {
+    extern __shared__ u32 s_bitmap[];  // HS_WARPS * a.wpw words
+    __shared__ u32 s_row, s_item0;
+    __shared__ u32 s_wsum[2][HS_WARPS];
+    __shared__ u32 s_bs[HS_THREADS], s_pre[HS_THREADS + 1];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 wbase = warp * a.wpw;  // this warp scans bitmap words [wbase, wbase + wpw): lane l reads word wbase + 32*it + l
+    for (u32 w = tid; w < HS_WARPS * a.wpw; w += HS_THREADS) s_bitmap[w] = 0;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_row = atomicAdd(a.next, 1u);
+        __syncthreads();
+        if (s_row >= a.nrows) return;
+        const u32 r = a.rows[s_row];
+        const u32 s = m.arow_start[r], e = m.arow_start[r + 1];
+        // ---- products: bits of their columns.  Consecutive lanes hold consecutive products, i.e. (within one B row)
+        //      ascending columns, so lanes that hit the same bitmap word form a contiguous run: one ATOMS per run
+        //      instead of one per lane (power-law rows pack their columns densely). -------------------------------
+        for (u32 c0 = s; c0 < e; c0 += HS_THREADS) {
+            const u32 ent = c0 + tid;
+            u32 bs = 0, len = 0;
+            if (ent < e) {
+                const i32 j = m.a_j[ent];
+                if (!m.sj_mask || m.sj_mask[j]) { bs = m.bptr[j]; len = m.bptr[j + 1] - bs; }
+            }
+            u32 nE, T;
+            if (c0 != s) __syncthreads();  // previous chunk's staging no longer read
+            stage_entries<HS_THREADS>(bs, len, s_bs, s_pre, s_wsum, nE, T, [](u32) {});
+            u32 xs = 0;
+            for (u32 b0 = 0; b0 < T; b0 += 4 * HS_THREADS) {
+                u32 k[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const u32 p0 = b0 + u * HS_THREADS;  // first product of this sub-step (block-uniform)
+                    k[u] = 0xffffffffu;
+                    if (p0 < T) {
+                        if (s_pre[xs + 1] <= p0) xs = __shfl_sync(SPB_FULL_MASK, staged_entry(s_pre, nE, xs, p0), 0);
+                        const u32 p = p0 + tid;
+                        u32 x = xs;
+                        if (s_pre[xs + 1] < min(p0 + (u32)HS_THREADS, T)) x = staged_entry(s_pre, nE, xs, p0 + warp * 32);
+                        if (p < T) k[u] = (u32)ld_stream_i32(m.b_k + s_bs[x] + (p - s_pre[x]));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (b0 + u * HS_THREADS >= T) break;  // block-uniform
+                    const u32 word = k[u] >> 5;             // 0x7ffffff for the lanes past the end
+                    const u32 prev = __shfl_up_sync(SPB_FULL_MASK, word, 1);
+                    const u32 heads = __ballot_sync(SPB_FULL_MASK, lane == 0 || prev != word);
+                    const u32 le = 0xffffffffu >> (31 - lane);               // lanes at or below mine
+                    const u32 first = 31 - __clz(heads & le);
+                    const u32 above = heads & ~le;
+                    const u32 last = above ? (u32)__ffs(above) - 2 : 31u;    // last lane of my run
+                    u32 bits = k[u] != 0xffffffffu ? 1u << (k[u] & 31) : 0u;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {  // OR of the run, gathered at its first lane
+                        const u32 t = __shfl_down_sync(SPB_FULL_MASK, bits, o);
+                        if (lane + o <= last) bits |= t;
+                    }
+                    if (lane == first && bits) atomicOr(&s_bitmap[word], bits);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- outputs = set bits, in ascending column order.  Columns excluded by scalek are cleared first
+        //      (multiply_sparse.hpp:208-213); every warp counts its stretch of the bitmap ... ---------------------------
+        u32 mine = 0;
+        for (u32 w = wbase + lane; w < wbase + a.wpw; w += 32) {
+            u32 bits = s_bitmap[w];
+            if (m.sk && bits) {
+                u32 live = bits;
+                for (u32 t = bits; t; t &= t - 1) {
+                    const u32 b = __ffs(t) - 1;
+                    if (m.sk[w * 32 + b] == 0.0) live &= ~(1u << b);
+                }
+                if (EMIT && live != bits) s_bitmap[w] = live;
+                bits = live;
+            }
+            if (!EMIT) s_bitmap[w] = 0;
+            mine += __popc(bits);
+        }
+        mine = __reduce_add_sync(SPB_FULL_MASK, mine);
+        if (lane == 0) s_wsum[0][warp] = mine;
+        __syncthreads();
+        u32 before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < HS_WARPS; ++w) {
+            const u32 t = s_wsum[0][w];
+            if ((u32)w < warp) before += t;
+            total += t;
+        }
+        if (!EMIT) {
+            if (tid == 0) a.row_cnt[r] = total;
+            continue;
+        }
+        const u32 n_items = (total + a.cap - 1) / a.cap;
+        if (tid == 0) s_item0 = atomicAdd(a.n_items, n_items);
+        // ---- ... and writes its columns: the lanes of a warp hold 32 consecutive words, so their outputs are
+        //      consecutive in C ---------------------------------------------------------------------------------------
+        const i32 irow = m.arow_id[r];
+        u64 pos0 = a.c_ptr[r] + before;
+        for (u32 w = wbase + lane; w < wbase + a.wpw; w += 32) {
+            u32 bits = s_bitmap[w];
+            s_bitmap[w] = 0;
+            const u32 c = __popc(bits);
+            const u32 incl = warp_incl_scan(c);
+            u64 pos = pos0 + incl - c;
+            for (; bits; bits &= bits - 1, ++pos) {
+                a.c_i[pos] = irow;
+                a.c_k[pos] = (i32)(w * 32 + __ffs(bits) - 1);
+            }
+            pos0 += __shfl_sync(SPB_FULL_MASK, incl, 31);
+        }
+        __syncthreads();
+        for (u32 p = tid; p < n_items; p += HS_THREADS) a.items[s_item0 + p] = ((u64)r << 32) | p;
+    }
+}
+
+// ---- numeric: hash accumulators ------------------------------------------------------------------------------------
+// first position in [lo, hi) of the sorted run b_k whose column is >= key.  Four-way: three probes in flight per
+// level halve the chain of dependent L2 round trips of a binary search (the staging of windowed items is
+// latency-bound on exactly this chain).
+__device__ __forceinline__ u32 hn_lower_bound(const i32 *__restrict__ b_k, u32 lo, u32 hi, i32 key) {
+    while (hi - lo > 3) {
+        const u32 q = (hi - lo) / 4;
+        const u32 m1 = lo + q, m2 = lo + 2 * q, m3 = lo + 3 * q;
+        const i32 v1 = __ldg(b_k + m1), v2 = __ldg(b_k + m2), v3 = __ldg(b_k + m3);
+        if (v1 >= key) hi = m1;
+        else if (v2 >= key) { lo = m1 + 1; hi = m2; }
+        else if (v3 >= key) { lo = m2 + 1; hi = m3; }
+        else lo = m3 + 1;
+    }
+    while (lo < hi && __ldg(b_k + lo) < key) ++lo;
+    return lo;
+}
+
+template <int NT, int CAP, int SLOTS>
+struct HashSmem {
+    u32 keys[SLOTS];
+    double acc[CAP];
+    double st_as[NT];
+    u32 st_bs[NT];
+    u32 st_pre[NT + 1];
+    unsigned short rank[SLOTS];
+    u32 wsum[2][NT / 32];
+};
+
+// one step's products, fetched ahead of their use
+struct HashStep {
+    u32 k;        // column (valid lanes)
+    double b;     // B value
+    double as;    // scaled A value of the product's entry
+    u32 x;        // staged entry of the product
+    u32 x_first, x_last;  // staged entries of the step's first and last product (block-uniform)
+    bool valid;
+};
+
+template <int NT, int CAP, int SLOTS>
+__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : 2) k_hash_numeric(MMOperands m, HashArgs a, u32 total_items) {
+    extern __shared__ __align__(16) unsigned char hn_raw[];
+    typedef HashSmem<NT, CAP, SLOTS> Smem;
+    Smem &sm = *reinterpret_cast<Smem *>(hn_raw);
+    constexpr u32 EMPTY = 0xffffffffu;
+    constexpr u32 NO_ENTRY = 0xffffffffu;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 dropped = 0;
+    ull n_chunks = 0, n_steps = 0, n_rounds = 0, n_done = 0, n_piped = 0;
+    long long c_setup = 0, c_stage = 0, c_steps = 0, c_piped = 0, c_out = 0, t0 = 0, t1;  // tracing: clocks per phase
+#define HN_TICK(acc) do { if (a.dbg) { t1 = clock64(); acc += t1 - t0; t0 = t1; } } while (0)
+    // items are dealt round-robin: ~10^3 items per block average their very different sizes out, and no block ever
+    // waits for a work counter
+    for (u32 item = blockIdx.x; item < total_items; item += gridDim.x) {
+        __syncthreads();
+        if (a.dbg) t0 = clock64();
+        ++n_done;
+        const u64 it = a.items[item];
+        const u32 r = (u32)(it >> 32), part = (u32)it;
+        const u32 s = m.arow_start[r], e = m.arow_start[r + 1];
+        const u64 base = a.c_ptr[r];
+        const u32 total = (u32)(a.c_ptr[r + 1] - base);
+        const u32 n_items = (total + a.cap - 1) / a.cap;  // a.cap <= CAP (smaller only in tests)
+        const u32 per = (total + n_items - 1) / n_items;
+        const u32 o_lo = part * per, o_hi = min(o_lo + per, total);
+        const u32 n_out = o_hi - o_lo;   // >= 1
+        const bool windowed = n_items > 1;
+        // table size: power of two >= 2 * n_out, at most SLOTS (load factor <= CAP / SLOTS)
+        u32 slots = 64;
+        while (slots < 2 * n_out && slots < (u32)SLOTS) slots <<= 1;
+        const u32 mask = slots - 1;
+        const int hshift = 32 - (31 - __clz(slots));
+        // the item's columns (sorted; written by the emit pass): loads first, the table is cleared under them
+        constexpr int KPT = (CAP + NT - 1) / NT;
+        u32 mykey[KPT];
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            const u32 t = tid + u * NT;
+            mykey[u] = t < n_out ? (u32)a.c_k[base + o_lo + t] : EMPTY;
+        }
+        const i32 k_lo = a.c_k[base + o_lo], k_hi = a.c_k[base + o_hi - 1];
+        for (u32 t = tid; t < slots; t += NT) sm.keys[t] = EMPTY;
+        for (u32 t = tid; t < n_out; t += NT) sm.acc[t] = 0.0;  // sum starts at 0 (:219)
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            const u32 t = tid + u * NT;
+            if (t < n_out) {
+                u32 h = (mykey[u] * 0x9E3779B1u) >> hshift;
+                while (atomicCAS(&sm.keys[h], EMPTY, mykey[u]) != EMPTY) h = (h + 1) & mask;
+                sm.rank[h] = (unsigned short)t;
+            }
+        }
+        for (u32 c0 = s; c0 < e; c0 += NT) {
+            __syncthreads();  // table built / previous chunk's adds done, its staging no longer read
+            if (c0 == s) HN_TICK(c_setup);
+            ++n_chunks;
+            // ---- stage NT entries of the row: scaled value, start and length of (the item's window of) the B row ----
+            const u32 ent = c0 + tid;
+            u32 bs = 0, len = 0;
+            double as = 0.0;
+            if (ent < e) {
+                const i32 j = m.a_j[ent];
+                if (!m.sj_mask || m.sj_mask[j]) {
+                    bs = m.bptr[j];
+                    u32 be = m.bptr[j + 1];
+                    if (windowed && bs < be) {
+                        bs = hn_lower_bound(m.b_k, bs, be, k_lo);
+                        be = (k_hi == INT32_MAX) ? be : hn_lower_bound(m.b_k, bs, be, k_hi + 1);
+                    }
+                    len = be - bs;
+                    as = m.a_val[ent];
+                    if (m.sj) as = __dmul_rn(as, m.sj[j]);  // (a*s) first, :228
+                }
+            }
+            u32 nE, T;
+            stage_entries<NT>(bs, len, sm.st_bs, sm.st_pre, sm.wsum, nE, T, [&](u32 slot) { sm.st_as[slot] = as; });
+            HN_TICK(c_stage);
+            // ---- the chunk's T products, NT per step, in (entry, position) order; the loads of step i+1 are issued
+            //      before step i is applied.  xs = entry of the next fetch's first product (block-uniform). ------------
+            u32 xs = 0;
+            auto fetch = [&](u32 b0, HashStep &st) {
+                const u32 end = min(b0 + (u32)NT, T);
+                if (sm.st_pre[xs + 1] <= b0) xs = __shfl_sync(SPB_FULL_MASK, staged_entry(sm.st_pre, nE, xs, b0), 0);
+                st.x_first = st.x_last = st.x = xs;
+                const u32 p = b0 + tid;
+                st.valid = p < end;
+                if (sm.st_pre[xs + 1] < end) {  // more than one entry in the step
+                    st.x_last = __shfl_sync(SPB_FULL_MASK, staged_entry(sm.st_pre, nE, xs, end - 1), 0);
+                    st.x = staged_entry(sm.st_pre, nE, xs, b0 + warp * 32);
+                }
+                if (st.valid) {
+                    const u32 q = sm.st_bs[st.x] + (p - sm.st_pre[st.x]);
+                    st.k = (u32)ld_stream_i32(m.b_k + q);
+                    st.b = ld_stream_f64(m.b_val + q);
+                    st.as = sm.st_as[st.x];
+                }
+            };
+            HashStep cur, nxt;
+            nxt.valid = false; nxt.x = nxt.x_first = nxt.x_last = 0; nxt.k = 0; nxt.b = 0.0; nxt.as = 0.0;
+            if (T) fetch(0, nxt);
+            u32 last_x = NO_ENTRY;  // entry whose products were added last (block-uniform)
+            for (u32 b0 = 0; b0 < T; b0 += NT) {
+                cur = nxt;
+                if (b0 + NT < T) fetch(b0 + NT, nxt);
+                ++n_steps;
+                bool pending = cur.valid;
+                u32 rk = 0;
+                double v = 0.0;
+                if (pending) {
+                    v = __dmul_rn(cur.as, cur.b);
+                    u32 h = (cur.k * 0x9E3779B1u) >> hshift;
+                    for (;;) {
+                        const u32 kk = sm.keys[h];
+                        if (kk == cur.k) break;
+                        if (kk == EMPTY) { pending = false; break; }  // column excluded by scalek: not an output
+                        h = (h + 1) & mask;
+                    }
+                    rk = sm.rank[h];
+                }
+                // Order.  The products of ONE entry have distinct columns: its threads add at once.  Two entries may
+                // share an output, and the one with the smaller j must add first (reference order, :219-236):
+                if (cur.x_last - cur.x_first < 32) {
+                    // a few entries in the step: one after the other, a barrier wherever the entry changes
+                    for (u32 xi = cur.x_first; xi <= cur.x_last; ++xi) {
+                        if (last_x != xi) { __syncthreads(); ++n_rounds; }
+                        last_x = xi;
+                        if (pending && cur.x == xi) sm.acc[rk] = __dadd_rn(sm.acc[rk], v);
+                    }
+                    HN_TICK(c_steps);
+                } else {
+                    // many short entries: one warp after the other (ascending j across warps); inside a warp the
+                    // lanes that share an output add in lane order (ascending j again)
+                    ++n_piped;
+                    u32 peers = 0, myrank = 0;
+                    const u32 pend = __ballot_sync(SPB_FULL_MASK, pending);
+                    if (pending) {
+                        peers = __match_any_sync(pend, rk);
+                        myrank = __popc(peers & lanemask_lt());
+                    }
+                    const u32 rounds = __reduce_max_sync(SPB_FULL_MASK, (u32)__popc(peers));
+                    for (u32 w = 0; w < (u32)(NT / 32); ++w) {
+                        __syncthreads();
+                        if (warp == w) {
+                            for (u32 i = 0; i < rounds; ++i) {
+                                if (pending && myrank == i) sm.acc[rk] = __dadd_rn(sm.acc[rk], v);
+                                __syncwarp();
+                            }
+                        }
+                    }
+                    last_x = NO_ENTRY;
+                    HN_TICK(c_piped);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- outputs, in rank (= ascending column) order ---------------------------------------------------------------
+        const i32 irow = m.arow_id[r];
+        double a_scale = 1.0;
+        if (m.si) a_scale = m.si[irow];
+        for (u32 t = tid; t < n_out; t += NT) {
+            const double sum = sm.acc[t];
+            double b_scale = 1.0;
+            if (m.sk) b_scale = m.sk[a.c_k[base + o_lo + t]];
+            __stcs(a.c_v + base + o_lo + t, __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale));  // :242
+            if (!(sum != 0.0)) {  // :238 (NaN != 0 is kept).  Tombstone: the host closes the gaps afterwards
+                a.c_i[base + o_lo + t] = -1;
+                ++dropped;
+            }
+        }
+        HN_TICK(c_out);
+    }
+#undef HN_TICK
+    if (dropped) atomicAdd(a.shrunk, dropped);
+    if (a.dbg && tid == 0) {
+        atomicAdd(a.dbg + 0, n_done); atomicAdd(a.dbg + 1, n_chunks); atomicAdd(a.dbg + 2, n_steps); atomicAdd(a.dbg + 3, n_rounds);
+        atomicAdd(a.dbg + 4, n_piped);
+        atomicAdd(a.dbg + 5, (ull)c_setup); atomicAdd(a.dbg + 6, (ull)c_stage); atomicAdd(a.dbg + 7, (ull)c_steps);
+        atomicAdd(a.dbg + 8, (ull)c_piped); atomicAdd(a.dbg + 9, (ull)c_out);
+    }
+}
+
+// Rare: outputs of hash-accumulator rows that summed to exact zero were written as
+// tombstones (row index -1).  keep[t] = 1 for live entries; after a scan of keep[], k_compact_entries moves them.
+__global__ void k_live_flags(const i32 *__restrict__ c_i, u64 n, unsigned char *keep) {
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) keep[t] = c_i[t] >= 0;
+}
+__global__ void k_compact_entries(u64 n, const unsigned char *__restrict__ keep, const u64 *__restrict__ slot,
+                                  const i32 *__restrict__ i_old, const i32 *__restrict__ k_old, const double *__restrict__ v_old,
+                                  i32 *i_new, i32 *k_new, double *v_new) {
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
+        if (keep[t]) {
+            const u64 d = slot[t];
+            i_new[d] = i_old[t];
+            k_new[d] = k_old[t];
+            v_new[d] = v_old[t];
+        }
+    }
 }
 
 // ---- long rows: expand-sort-compress ------------------------------------------------------------

@@ -72,6 +72,25 @@ def test_mm_fixtures_from_the_reference(ctx):
         assert _cases.same_coo(got, want), f"mm case {s}"
 
 
+@pytest.mark.parametrize("variant,item_cap", [(0, 0), (1, 0), (0, 7), (1, 64)])
+def test_mm_fixtures_through_the_hash_accumulator_bin(monkeypatch, variant, item_cap):
+    """Same fixtures with every row forced through the bitmap + shared-memory hash-accumulator kernels (both block
+    shapes; with rows cut into many small work items so that the column windows are exercised): the sums are
+    formed in ascending j, so every value is still bit-identical to the reference."""
+    import spsparse_b200 as sp
+    _esc_env(monkeypatch, 0, 1 << 27, hash_min=0)
+    monkeypatch.setenv("SPB_HASH_VARIANT", str(variant))
+    if item_cap:
+        monkeypatch.setenv("SPB_HASH_ITEM_CAP", str(item_cap))
+    p = _golden.pack("multiply_mm_cases")
+    with sp.Context(0) as c2:
+        for s in range(variant, int(p["count"]), 2 if item_cap == 0 else 5):
+            si, A, sj, B, sk, want = (_golden.get_coo(p, f"m{s}_{x}") for x in ("si", "A", "sj", "B", "sk", "out"))
+            Cst, tA, tB, pol, zn = p[f"m{s}_args"]
+            got = gpu_mm(c2, float(Cst), si, A, chr(int(tA)), sj, B, chr(int(tB)), sk, int(pol), int(zn))
+            assert _cases.same_coo(got, want), f"mm case {s}"
+
+
 def test_mv_fixtures_from_the_reference(ctx):
     p = _golden.pack("multiply_mv_cases")
     for s in range(int(p["count"])):
@@ -105,9 +124,10 @@ def test_errors_and_empties(ctx):
     assert gpu_mm(ctx, 1.0, None, allzero, ".", None, B, ".", None).n == 0
 
 
-def _esc_env(monkeypatch, merge_max, chunk):
+def _esc_env(monkeypatch, merge_max, chunk, hash_min="off"):
     monkeypatch.setenv("SPB_MERGE_MAX_PRODUCTS", str(merge_max))
     monkeypatch.setenv("SPB_ESC_CHUNK", str(chunk))
+    monkeypatch.setenv("SPB_HASH_MIN_PRODUCTS", str(hash_min))  # "off": long rows all go through expand-sort-compress
 
 
 def test_expand_sort_compress_path(orc, monkeypatch):
@@ -195,7 +215,7 @@ def test_rmat_family_small(ctx, orc):
     want, st = orc.multiply_mm(1.0, None, A, ".", None, A, ".", None, want_stats=True)
     dA = sp.gen_rmat(ctx, 0x5EED0004, 12, 4 << 12)
     R, gst = sp.multiply(ctx, 1.0, None, dA, ".", None, dA, ".", None, stats=True)
-    assert gst.products == st["F"] and gst.rows_esc > 0 and gst.rows_merge > 0
+    assert gst.products == st["F"] and gst.rows_hash > 0 and gst.rows_merge > 0
     assert _cases.same_coo(down(R), want)
     dA.free(); R.free()
 
@@ -248,10 +268,60 @@ def test_medium_scale_against_oracle(ctx, orc):
     assert gst.products == st["F"] and _cases.same_coo(down(R), want)
     for h in (dA, dS, R):
         h.free()
-    # config 4 family, R-MAT scale 15 (skewed: most products go through expand-sort-compress)
+    # config 4 family, R-MAT scale 15 (skewed: most products go through the hash-accumulator bin, the hub rows in
+    # several column windows)
     shp, idx, val = gen.rmat(0x5EED0004, 15, 4 << 15)
     want, st = orc.multiply_mm(1.0, None, O.Coo(shp, idx, val), ".", None, O.Coo(shp, idx, val), ".", None, want_stats=True)
     dA = sp.gen_rmat(ctx, 0x5EED0004, 15, 4 << 15)
     R, gst = sp.multiply(ctx, 1.0, None, dA, ".", None, dA, ".", None, stats=True)
-    assert gst.products == st["F"] and gst.products_esc > 0 and _cases.same_coo(down(R), want)
+    assert gst.products == st["F"] and gst.products_hash > 0 and _cases.same_coo(down(R), want)
     dA.free(); R.free()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_hash_accumulator_bin(orc, monkeypatch, variant):
+    """Long rows through the bitmap + hash-accumulator kernels: all three bins side by side, scale vectors, a row
+    wider than one work item, and rows whose sums cancel exactly (they emit fewer entries than the symbolic
+    bound -> gap compaction).  Bit-identical values throughout."""
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    rng = np.random.default_rng(21)
+    m, nj, nk = 400, 300, 30000
+    # ordinary sparse part
+    n = 1200
+    ai, aj = rng.integers(0, m, n), rng.integers(0, nj, n)
+    av = rng.integers(1, 4, n).astype(np.float64)
+    nb, nb2 = 20000, 40000  # inner indices 200..299 hold most of B: the heavy rows below use only those
+    bj, bk = np.concatenate([rng.integers(0, nj, nb), rng.integers(200, nj, nb2)]), rng.integers(0, nk, nb + nb2)
+    bv = rng.integers(1, 4, nb + nb2).astype(np.float64)
+    # rows 0..3 of A: +1 on inner index 10, -1 on inner index 11; B rows 10 and 11 identical => exact cancellation
+    canc = rng.choice(nk, 700, replace=False)
+    keep_b = (bj != 10) & (bj != 11)
+    bj, bk, bv = bj[keep_b], bk[keep_b], bv[keep_b]
+    bj = np.concatenate([bj, np.full(700, 10), np.full(700, 11)]); bk = np.concatenate([bk, canc, canc])
+    bv = np.concatenate([bv, np.full(1400, 2.0)])
+    keep_a = ai > 3
+    ai, aj, av = ai[keep_a], aj[keep_a], av[keep_a]
+    ai = np.concatenate([ai, np.repeat(np.arange(4), 2), [2, 3]]); aj = np.concatenate([aj, np.tile([10, 11], 4), [50, 60]])
+    av = np.concatenate([av, np.tile([1.0, -1.0], 4), [5.0, 7.0]])
+    # a few heavy rows with real-valued data
+    heavy = np.arange(100, 104)
+    ai = np.concatenate([ai, np.repeat(heavy, 120)]); aj = np.concatenate([aj, rng.integers(200, nj, 480)])  # ~20k outputs each
+    av = np.concatenate([av, 0.5 + rng.random(480)])
+    A = O.Coo((m, nj), [ai, aj], av)
+    B = O.Coo((nj, nk), [bj, bk], bv)
+    si = O.Coo((m,), [np.arange(0, m, 2)], 1.0 + np.arange(0, m, 2) % 3, (0,))
+    sk = O.Coo((nk,), [np.arange(1, nk)], np.where(np.arange(1, nk) % 7 == 0, 0.0, 2.0), (0,))
+    for scales in ((None, None), (si, sk)):
+        want, st = orc.multiply_mm(1.5, scales[0], A, ".", None, B, ".", scales[1], want_stats=True)
+        _esc_env(monkeypatch, 256, 4000, hash_min=512)
+        monkeypatch.setenv("SPB_HASH_VARIANT", str(variant))
+        with sp.Context(0) as c2:
+            hs = [up(c2, x) for x in (scales[0], A, B, scales[1])]
+            R, gst = sp.multiply(c2, 1.5, hs[0], hs[1], ".", None, hs[2], ".", hs[3], stats=True)
+            got = down(R)
+            assert gst.products == st["F"] and gst.rows_hash >= 4 and gst.rows_merge > 0 and gst.rows_esc > 0
+            assert _cases.same_coo(got, want), scales[0] is not None
+            for h in hs + [R]:
+                if h is not None:
+                    h.free()
