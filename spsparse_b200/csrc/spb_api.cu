@@ -807,6 +807,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         CKR(ws.zeroed(&ha.next, 4));
         ha.shrunk = ha.next + 1;
         ha.n_items = ha.next + 2;
+        CKR(ws.zeroed(&ha.split_total, 1));
+        CKR(ws.get(&ha.row_split, ha.nrows));
         ++ctx->launches, k_hash_symbolic<false><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());
     }
@@ -912,9 +914,18 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         ha.c_ptr = c_ptr; ha.c_i = out->idx[0]; ha.c_k = out->idx[1]; ha.c_v = out->val;
         ++ctx->launches, k_hash_symbolic<true><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());
-        CK(cudaMemsetAsync(ha.next, 0, sizeof(u32), ctx->stream));
+        ull h_split = 0;
         CK(cudaMemcpyAsync(&h_items, ha.n_items, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&h_split, ha.split_total, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (h_split) {
+            // rows cut into several items: where every item's column window begins in every B row of the row
+            u32 *split;
+            CKR(ws.get(&split, h_split));
+            ++ctx->launches, k_hash_splits<<<h_items < cap * 4 ? h_items : cap * 4, 256, 0, ctx->stream>>>(m, ha, h_items, split);
+            CK(cudaGetLastError());
+            ha.split = split;
+        }
         if (h_items) {
             if (tracing()) CKR(ws.zeroed(&ha.dbg, 16));
             ++ctx->launches;

@@ -342,8 +342,11 @@ struct HashArgs {
     const u64 *c_ptr;    // emit + numeric
     i32 *c_i, *c_k;
     double *c_v;
-    u64 *items;          // emit: (row << 32 | part), appended in any order
+    u64 *items;          // emit: (index into rows[] << 32 | part), appended in any order
     u32 *n_items;
+    u64 *row_split;      // emit: per ROW_HASH row cut into W > 1 items, the offset of its (W-1) x (row entries) block in split[]
+    ull *split_total;    // emit: entries of split[] handed out
+    const u32 *split;    // numeric: split[row_split + (p-1)*len + x] = first position of entry x's B row inside item p's window
     u32 *shrunk;         // numeric: number of outputs dropped (written as tombstones)
     ull *dbg;            // numeric, tracing only: [0] items, [1] staged chunks, [2] steps, [3] barriers between entries, [4] warp-pipelined steps, [5..9] clocks per phase
 };
@@ -401,8 +404,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
     __shared__ u32 s_row, s_item0;
     __shared__ u32 s_wsum[2][HS_WARPS];
     __shared__ u32 s_bs[HS_THREADS], s_pre[HS_THREADS + 1];
+    __shared__ u32 s_gcnt[HASH_MAX_COLS / 1024];  // set bits per group of 32 bitmap words, then their exclusive prefix
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 wbase = warp * a.wpw;  // this warp scans bitmap words [wbase, wbase + wpw): lane l reads word wbase + 32*it + l
     for (u32 w = tid; w < HS_WARPS * a.wpw; w += HS_THREADS) s_bitmap[w] = 0;
     for (;;) {
         __syncthreads();
@@ -461,9 +464,13 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
         }
         __syncthreads();
         // ---- outputs = set bits, in ascending column order.  Columns excluded by scalek are cleared first
-        //      (multiply_sparse.hpp:208-213); every warp counts its stretch of the bitmap ... ---------------------------
+        //      (multiply_sparse.hpp:208-213).  The bitmap is walked in groups of 32 words dealt round-robin to the warps:
+        //      power-law rows pack their columns into one end of the bitmap, a contiguous stretch per warp would leave
+        //      one warp with all the work. -------------------------------------------------------------------------------
+        const u32 ngroups = HS_WARPS * a.wpw / 32;
         u32 mine = 0;
-        for (u32 w = wbase + lane; w < wbase + a.wpw; w += 32) {
+        for (u32 g = warp; g < ngroups; g += HS_WARPS) {
+            const u32 w = g * 32 + lane;
             u32 bits = s_bitmap[w];
             if (m.sk && bits) {
                 u32 live = bits;
@@ -475,42 +482,68 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
                 bits = live;
             }
             if (!EMIT) s_bitmap[w] = 0;
-            mine += __popc(bits);
-        }
-        mine = __reduce_add_sync(SPB_FULL_MASK, mine);
-        if (lane == 0) s_wsum[0][warp] = mine;
-        __syncthreads();
-        u32 before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < HS_WARPS; ++w) {
-            const u32 t = s_wsum[0][w];
-            if ((u32)w < warp) before += t;
-            total += t;
+            const u32 c = __popc(bits);
+            if (EMIT) {
+                const u32 gc = __reduce_add_sync(SPB_FULL_MASK, c);
+                if (lane == 0) s_gcnt[g] = gc;
+            } else {
+                mine += c;
+            }
         }
         if (!EMIT) {
-            if (tid == 0) a.row_cnt[r] = total;
+            mine = __reduce_add_sync(SPB_FULL_MASK, mine);
+            if (lane == 0) s_wsum[0][warp] = mine;
+            __syncthreads();
+            if (tid == 0) {
+                u32 total = 0;
+                for (int w = 0; w < HS_WARPS; ++w) total += s_wsum[0][w];
+                a.row_cnt[r] = total;
+            }
             continue;
         }
+        __syncthreads();
+        // exclusive prefix of the group counts (two groups per thread)
+        u32 total;
+        {
+            const u32 g0 = 2 * tid, g1 = 2 * tid + 1;
+            const u32 v0 = g0 < ngroups ? s_gcnt[g0] : 0, v1 = g1 < ngroups ? s_gcnt[g1] : 0;
+            const u32 incl = warp_incl_scan(v0 + v1);
+            if (lane == 31) s_wsum[0][warp] = incl;
+            __syncthreads();
+            u32 before = incl - (v0 + v1);
+            total = 0;
+#pragma unroll
+            for (int w = 0; w < HS_WARPS; ++w) {
+                const u32 t = s_wsum[0][w];
+                if ((u32)w < warp) before += t;
+                total += t;
+            }
+            if (g0 < ngroups) s_gcnt[g0] = before;
+            if (g1 < ngroups) s_gcnt[g1] = before + v0;
+        }
         const u32 n_items = (total + a.cap - 1) / a.cap;
-        if (tid == 0) s_item0 = atomicAdd(a.n_items, n_items);
-        // ---- ... and writes its columns: the lanes of a warp hold 32 consecutive words, so their outputs are
+        if (tid == 0) {
+            s_item0 = atomicAdd(a.n_items, n_items);
+            if (n_items > 1) a.row_split[s_row] = atomicAdd(a.split_total, (ull)(n_items - 1) * (e - s));
+        }
+        __syncthreads();
+        // ---- ... and the columns are written: the lanes of a warp hold 32 consecutive words, so their outputs are
         //      consecutive in C ---------------------------------------------------------------------------------------
         const i32 irow = m.arow_id[r];
-        u64 pos0 = a.c_ptr[r] + before;
-        for (u32 w = wbase + lane; w < wbase + a.wpw; w += 32) {
+        const u64 base = a.c_ptr[r];
+        for (u32 g = warp; g < ngroups; g += HS_WARPS) {
+            const u32 w = g * 32 + lane;
             u32 bits = s_bitmap[w];
             s_bitmap[w] = 0;
             const u32 c = __popc(bits);
             const u32 incl = warp_incl_scan(c);
-            u64 pos = pos0 + incl - c;
+            u64 pos = base + s_gcnt[g] + incl - c;
             for (; bits; bits &= bits - 1, ++pos) {
                 a.c_i[pos] = irow;
                 a.c_k[pos] = (i32)(w * 32 + __ffs(bits) - 1);
             }
-            pos0 += __shfl_sync(SPB_FULL_MASK, incl, 31);
         }
-        __syncthreads();
-        for (u32 p = tid; p < n_items; p += HS_THREADS) a.items[s_item0 + p] = ((u64)r << 32) | p;
+        for (u32 p = tid; p < n_items; p += HS_THREADS) a.items[s_item0 + p] = ((u64)s_row << 32) | p;
     }
 }
 
@@ -530,6 +563,31 @@ __device__ __forceinline__ u32 hn_lower_bound(const i32 *__restrict__ b_k, u32 l
     }
     while (lo < hi && __ldg(b_k + lo) < key) ++lo;
     return lo;
+}
+
+// Column windows.  A row with more outputs than one item holds is cut into W items by output rank; item p covers
+// the columns from its first output to just before item p+1's first output.  For every entry x of the row, the
+// position in its B row where item p's window begins is found HERE, by one independent thread per (item, entry)
+// -- millions of searches in flight -- instead of inside the numeric kernel, where the same searches were a chain
+// of dependent L2 round trips in front of every item (29 % of its time).
+__global__ void __launch_bounds__(256) k_hash_splits(MMOperands m, HashArgs a, u32 total_items, u32 *split) {
+    for (u32 item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const u64 it = a.items[item];
+        const u32 sr = (u32)(it >> 32), part = (u32)it;
+        if (part == 0) continue;
+        const u32 r = a.rows[sr];
+        const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
+        const u64 base = a.c_ptr[r];
+        const u32 total = (u32)(a.c_ptr[r + 1] - base);
+        const u32 n_items = (total + a.cap - 1) / a.cap;
+        const u32 per = (total + n_items - 1) / n_items;
+        const i32 key = a.c_k[base + (u64)part * per];
+        u32 *dst = split + a.row_split[sr] + (u64)(part - 1) * len;
+        for (u32 x = threadIdx.x; x < len; x += blockDim.x) {
+            const i32 j = m.a_j[s + x];
+            dst[x] = hn_lower_bound(m.b_k, m.bptr[j], m.bptr[j + 1], key);
+        }
+    }
 }
 
 template <int NT, int CAP, int SLOTS>
@@ -572,7 +630,8 @@ __global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : 2) k_hash_numeric(MMOpe
         if (a.dbg) t0 = clock64();
         ++n_done;
         const u64 it = a.items[item];
-        const u32 r = (u32)(it >> 32), part = (u32)it;
+        const u32 sr = (u32)(it >> 32), part = (u32)it;
+        const u32 r = a.rows[sr];
         const u32 s = m.arow_start[r], e = m.arow_start[r + 1];
         const u64 base = a.c_ptr[r];
         const u32 total = (u32)(a.c_ptr[r + 1] - base);
@@ -594,7 +653,13 @@ __global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : 2) k_hash_numeric(MMOpe
             const u32 t = tid + u * NT;
             mykey[u] = t < n_out ? (u32)a.c_k[base + o_lo + t] : EMPTY;
         }
-        const i32 k_lo = a.c_k[base + o_lo], k_hi = a.c_k[base + o_hi - 1];
+        // windows of the B rows (k_hash_splits): where this item starts / the next one starts
+        const u32 *split_lo = nullptr, *split_hi = nullptr;
+        if (windowed) {
+            const u32 *rs = a.split + a.row_split[sr];
+            if (part > 0) split_lo = rs + (u64)(part - 1) * (e - s);
+            if (part + 1 < n_items) split_hi = rs + (u64)part * (e - s);
+        }
         for (u32 t = tid; t < slots; t += NT) sm.keys[t] = EMPTY;
         for (u32 t = tid; t < n_out; t += NT) sm.acc[t] = 0.0;  // sum starts at 0 (:219)
         __syncthreads();
@@ -617,13 +682,12 @@ __global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : 2) k_hash_numeric(MMOpe
             double as = 0.0;
             if (ent < e) {
                 const i32 j = m.a_j[ent];
+                u32 w_lo = 0, w_hi = 0;
+                if (split_lo) w_lo = split_lo[ent - s];
+                if (split_hi) w_hi = split_hi[ent - s];
                 if (!m.sj_mask || m.sj_mask[j]) {
-                    bs = m.bptr[j];
-                    u32 be = m.bptr[j + 1];
-                    if (windowed && bs < be) {
-                        bs = hn_lower_bound(m.b_k, bs, be, k_lo);
-                        be = (k_hi == INT32_MAX) ? be : hn_lower_bound(m.b_k, bs, be, k_hi + 1);
-                    }
+                    bs = split_lo ? w_lo : m.bptr[j];
+                    const u32 be = split_hi ? w_hi : m.bptr[j + 1];
                     len = be - bs;
                     as = m.a_val[ent];
                     if (m.sj) as = __dmul_rn(as, m.sj[j]);  // (a*s) first, :228
