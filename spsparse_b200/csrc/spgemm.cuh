@@ -401,10 +401,11 @@ __device__ __forceinline__ void stage_entries(u32 bs, u32 len, u32 *st_bs, u32 *
 template <bool EMIT>
 __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, HashArgs a) {
     extern __shared__ u32 s_bitmap[];  // HS_WARPS * a.wpw words
-    __shared__ u32 s_row, s_item0;
+    __shared__ u32 s_row, s_item0, s_grab;
     __shared__ u32 s_wsum[2][HS_WARPS];
     __shared__ u32 s_bs[HS_THREADS], s_pre[HS_THREADS + 1];
     __shared__ u32 s_gcnt[HASH_MAX_COLS / 1024];  // set bits per group of 32 bitmap words, then their exclusive prefix
+    __shared__ unsigned short s_glist[HASH_MAX_COLS / 1024];  // the non-empty groups
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (u32 w = tid; w < HS_WARPS * a.wpw; w += HS_THREADS) s_bitmap[w] = 0;
     for (;;) {
@@ -502,36 +503,47 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             continue;
         }
         __syncthreads();
-        // exclusive prefix of the group counts (two groups per thread)
-        u32 total;
+        // exclusive prefix of the group counts, and the list of the non-empty groups (two groups per thread)
+        u32 total, n_live;
         {
             const u32 g0 = 2 * tid, g1 = 2 * tid + 1;
             const u32 v0 = g0 < ngroups ? s_gcnt[g0] : 0, v1 = g1 < ngroups ? s_gcnt[g1] : 0;
-            const u32 incl = warp_incl_scan(v0 + v1);
-            if (lane == 31) s_wsum[0][warp] = incl;
+            const u32 l0 = v0 != 0, l1 = v1 != 0;
+            const u32 incl = warp_incl_scan(v0 + v1), lincl = warp_incl_scan(l0 + l1);
+            if (lane == 31) { s_wsum[0][warp] = incl; s_wsum[1][warp] = lincl; }
             __syncthreads();
-            u32 before = incl - (v0 + v1);
-            total = 0;
+            u32 before = incl - (v0 + v1), lbefore = lincl - (l0 + l1);
+            total = 0; n_live = 0;
 #pragma unroll
             for (int w = 0; w < HS_WARPS; ++w) {
-                const u32 t = s_wsum[0][w];
-                if ((u32)w < warp) before += t;
+                const u32 t = s_wsum[0][w], c = s_wsum[1][w];
+                if ((u32)w < warp) { before += t; lbefore += c; }
                 total += t;
+                n_live += c;
             }
             if (g0 < ngroups) s_gcnt[g0] = before;
             if (g1 < ngroups) s_gcnt[g1] = before + v0;
+            if (l0) s_glist[lbefore] = (unsigned short)g0;
+            if (l1) s_glist[lbefore + l0] = (unsigned short)g1;
         }
         const u32 n_items = (total + a.cap - 1) / a.cap;
         if (tid == 0) {
             s_item0 = atomicAdd(a.n_items, n_items);
             if (n_items > 1) a.row_split[s_row] = atomicAdd(a.split_total, (ull)(n_items - 1) * (e - s));
+            s_grab = 0;
         }
         __syncthreads();
-        // ---- ... and the columns are written: the lanes of a warp hold 32 consecutive words, so their outputs are
-        //      consecutive in C ---------------------------------------------------------------------------------------
+        // ---- ... and the columns are written, one non-empty group per warp at a time (grabbed from a counter: the
+        //      groups of a power-law row differ in weight by orders of magnitude): the lanes hold 32 consecutive
+        //      words, so their outputs are consecutive in C ------------------------------------------------------------
         const i32 irow = m.arow_id[r];
         const u64 base = a.c_ptr[r];
-        for (u32 g = warp; g < ngroups; g += HS_WARPS) {
+        for (;;) {
+            u32 i = 0;
+            if (lane == 0) i = atomicAdd(&s_grab, 1u);
+            i = __shfl_sync(SPB_FULL_MASK, i, 0);
+            if (i >= n_live) break;
+            const u32 g = s_glist[i];
             const u32 w = g * 32 + lane;
             u32 bits = s_bitmap[w];
             s_bitmap[w] = 0;
