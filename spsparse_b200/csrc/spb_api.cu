@@ -114,7 +114,7 @@ struct spb_ctx {
     u32 merge_max_products;  // bin threshold, env SPB_MERGE_MAX_PRODUCTS
     u64 esc_chunk;           // products per expand-sort-compress chunk, env SPB_ESC_CHUNK
     u64 hash_min_products;   // long rows with at least this many products use the bitmap + hash-accumulator kernels; ~0 = never (SPB_HASH_MIN_PRODUCTS)
-    int hash_variant;        // 0: 1024 threads x 10240 outputs per item, 1: 512 x 5120 (two blocks per SM)  (SPB_HASH_VARIANT)
+    int hash_variant;        // 0: 1024 threads x 10240 outputs per item, 1: 512 x 5120 (two blocks per SM), 2: 256 x 2560 (four)  (SPB_HASH_VARIANT)
     u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
     DevPool pool;
 };
@@ -227,11 +227,12 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     s = getenv("SPB_HASH_MIN_PRODUCTS");
     c->hash_min_products = s ? (strcmp(s, "off") == 0 ? ~0ull : strtoull(s, nullptr, 10)) : 512ull;
     s = getenv("SPB_HASH_VARIANT");
-    c->hash_variant = s ? atoi(s) : 1;  // two 512-thread blocks per SM measured 10 % faster than one of 1024 (R-MAT scale 20)
+    c->hash_variant = s ? atoi(s) : 2;  // R-MAT scale 20, numeric pass: 1 x 1024 threads 82 ms, 2 x 512 72.9 ms, 4 x 256 70.3 ms
     CK(cudaFuncSetAttribute(k_hash_symbolic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
     CK(cudaFuncSetAttribute(k_hash_symbolic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
     CK(cudaFuncSetAttribute(k_hash_numeric<1024, 10240, 16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<1024, 10240, 16384>)));
     CK(cudaFuncSetAttribute(k_hash_numeric<512, 5120, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<512, 5120, 8192>)));
+    CK(cudaFuncSetAttribute(k_hash_numeric<256, 2560, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<256, 2560, 4096>)));
     if (c->esc_chunk < 1) c->esc_chunk = 1;
     *out = c;
     return SPB_OK;
@@ -791,7 +792,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     memset(&ha, 0, sizeof ha);
     u32 hs_grid = 0;
     size_t hs_smem = 0;
-    u32 hash_cap = ctx->hash_variant == 1 ? 5120u : 10240u;
+    u32 hash_cap = ctx->hash_variant == 2 ? 2560u : ctx->hash_variant == 1 ? 5120u : 10240u;
     if (const char *e = getenv("SPB_HASH_ITEM_CAP")) {  // tests: cut rows into smaller work items
         const u32 v = (u32)strtoul(e, nullptr, 10);
         if (v >= 1 && v < hash_cap) hash_cap = v;
@@ -929,7 +930,10 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         if (h_items) {
             if (tracing()) CKR(ws.zeroed(&ha.dbg, 16));
             ++ctx->launches;
-            if (ctx->hash_variant == 1) {
+            if (ctx->hash_variant == 2) {
+                const u32 g = h_items < 4u * ctx->sm_count ? h_items : 4u * ctx->sm_count;
+                k_hash_numeric<256, 2560, 4096><<<g, 256, sizeof(HashSmem<256, 2560, 4096>), ctx->stream>>>(m, ha, h_items);
+            } else if (ctx->hash_variant == 1) {
                 const u32 g = h_items < 2u * ctx->sm_count ? h_items : 2u * ctx->sm_count;
                 k_hash_numeric<512, 5120, 8192><<<g, 512, sizeof(HashSmem<512, 5120, 8192>), ctx->stream>>>(m, ha, h_items);
             } else {

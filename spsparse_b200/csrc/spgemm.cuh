@@ -12,10 +12,14 @@
 //   short rows (<= MERGE_MAX_LISTS inner indices, <= merge_max_products products): one THREAD per
 //     row runs a k-way merge of the (already column-sorted) B rows entirely in registers -- the
 //     heads of the lists are compared, equal columns are summed in list (= ascending j) order.
-//     Deterministic and bit-identical to the reference's sums.  A symbolic pass counts, a scan
-//     places the rows, the numeric pass repeats the merge and writes.
-//   long rows: expand-sort-compress through global memory with the radix sort / duplicate-reduce
-//     kernels of consolidate (keys (row number, k), stable => terms still in ascending j).
+//     A symbolic pass counts, a scan places the rows, the numeric pass repeats the merge and writes.
+//   longer rows (>= hash_min_products products; output columns must fit the shared-memory bitmap):
+//     symbolic = bitmap of the products' columns, whose set bits in order are the sorted outputs;
+//     numeric = shared-memory hash table column -> output rank with accumulators in rank order,
+//     products added entry after entry (ascending j).
+//   everything else: expand-sort-compress through global memory with the radix sort / duplicate-
+//     reduce kernels of consolidate (keys (row number, k), stable => terms still in ascending j).
+// Every bin is deterministic and its sums are bit-identical to the reference's.
 #pragma once
 #include "common.cuh"
 
@@ -624,7 +628,7 @@ struct HashStep {
 };
 
 template <int NT, int CAP, int SLOTS>
-__global__ void __launch_bounds__(NT, (NT >= 1024) ? 1 : 2) k_hash_numeric(MMOperands m, HashArgs a, u32 total_items) {
+__global__ void __launch_bounds__(NT, 1024 / NT) k_hash_numeric(MMOperands m, HashArgs a, u32 total_items) {
     extern __shared__ __align__(16) unsigned char hn_raw[];
     typedef HashSmem<NT, CAP, SLOTS> Smem;
     Smem &sm = *reinterpret_cast<Smem *>(hn_raw);

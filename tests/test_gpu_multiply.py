@@ -72,7 +72,7 @@ def test_mm_fixtures_from_the_reference(ctx):
         assert _cases.same_coo(got, want), f"mm case {s}"
 
 
-@pytest.mark.parametrize("variant,item_cap", [(0, 0), (1, 0), (0, 7), (1, 64)])
+@pytest.mark.parametrize("variant,item_cap", [(0, 0), (1, 0), (2, 0), (0, 7), (1, 64), (2, 3)])
 def test_mm_fixtures_through_the_hash_accumulator_bin(monkeypatch, variant, item_cap):
     """Same fixtures with every row forced through the bitmap + shared-memory hash-accumulator kernels (both block
     shapes; with rows cut into many small work items so that the column windows are exercised): the sums are
@@ -84,7 +84,7 @@ def test_mm_fixtures_through_the_hash_accumulator_bin(monkeypatch, variant, item
         monkeypatch.setenv("SPB_HASH_ITEM_CAP", str(item_cap))
     p = _golden.pack("multiply_mm_cases")
     with sp.Context(0) as c2:
-        for s in range(variant, int(p["count"]), 2 if item_cap == 0 else 5):
+        for s in range(variant, int(p["count"]), 3 if item_cap == 0 else 5):
             si, A, sj, B, sk, want = (_golden.get_coo(p, f"m{s}_{x}") for x in ("si", "A", "sj", "B", "sk", "out"))
             Cst, tA, tB, pol, zn = p[f"m{s}_args"]
             got = gpu_mm(c2, float(Cst), si, A, chr(int(tA)), sj, B, chr(int(tB)), sk, int(pol), int(zn))
@@ -278,7 +278,7 @@ def test_medium_scale_against_oracle(ctx, orc):
     dA.free(); R.free()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_hash_accumulator_bin(orc, monkeypatch, variant):
     """Long rows through the bitmap + hash-accumulator kernels: all three bins side by side, scale vectors, a row
     wider than one work item, and rows whose sums cancel exactly (they emit fewer entries than the symbolic
