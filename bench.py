@@ -135,7 +135,7 @@ def run_ours(args):
 
     replicator = [None, False]  # (PeerReplicator or None, tried)
 
-    def gather_b_start(Bc):
+    def gather_b_start(Bc, need=None):
         """Start replicating the row-sharded, consolidated B on every rank (spsparse_b200/dist.py), in
         compressed form: local row pointers of this rank's rows + column and value of every entry.
         Asynchronous, so that consolidate(A) overlaps the NCCL transfers."""
@@ -154,10 +154,11 @@ def run_ours(args):
                 except Exception as e:  # noqa: BLE001 -- any failure: use the NCCL path
                     print(f"[bench] symmetric-memory replication unavailable ({e!r}); using NCCL all-gather", file=sys.stderr)
         if replicator[0] is not None:
-            return replicator[0].start(local_ptr, cols, vals)
+            return replicator[0].start(local_ptr, cols, vals, None if os.environ.get("SPB_FULL_REPLICATE") else need)
         return spd.replicate_csr_start(local_ptr, cols, vals, rank, world)
 
     timeline = []  # per step: stream-event times (ms) between the phases of the hot path
+    pulled = [None]  # rows of B this rank fetched in the last step (None: everything)
 
     def hot_path(A_raw, B_raw, w):
         """consolidate(B shard) -> [replicate B, overlapped with] consolidate(A block) -> SpGEMM."""
@@ -166,11 +167,18 @@ def run_ours(args):
         ev[0].record(stream)
         Bc, sb = sp.consolidate(ctx, B_raw, sp.ROW_MAJOR, stats=True)
         ev[1].record(stream)
-        pending = gather_b_start(Bc) if world > 1 else None
+        need = None
+        if world > 1:
+            # interval hull of the inner indices this rank's block of A references: only those rows of B are fetched
+            (_, a1), _ = A_raw.device_ptrs()
+            lo, hi = torch.aminmax(torch.as_tensor(DevView(a1, A_raw.size(), "<i4"), device="cuda"))
+            need = (int(lo.item()), int(hi.item()))
+        pending = gather_b_start(Bc, need) if world > 1 else None
         ev[2].record(stream)
         Ac, sa = sp.consolidate(ctx, A_raw, sp.ROW_MAJOR, stats=True)
         ev[3].record(stream)
         if pending:
+            pulled[0] = pending.get("pulled_rows")
             ptr, cols, vals, total = spd.replicate_csr_finish(pending)  # library stream now waits for NCCL
             Bf = sp.CooArray.wrap_csr(ctx, (m, m), 0, ptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), total)
         else:
@@ -373,7 +381,7 @@ def run_ours(args):
                                    "(consolidate A + consolidate B + allgather B + SpGEMM)" if m == 100_000_000 else
                                    f"REDUCED banded triple product, {m} rows (not the headline size)",
                        "rows": m, "nnz_a_raw": cons_in / 2, "nnz_c": nnzC, "products": F,
-                       "partition": f"A rows / B rows split over {world} rank(s); B replicated each step in compressed form (row pointers + cols + vals, 12 B/entry): shards pulled from the peers' symmetric memory over NVLink by copy engines (NCCL grouped all-gather as fallback), overlapped with consolidate(A)",
+                       "partition": f"A rows / B rows split over {world} rank(s); each step every rank fetches, in compressed form (row pointers + cols + vals, 12 B/entry), the rows of B inside the interval hull of the inner indices its block of A references (rank 0 fetched {pulled[0] if pulled[0] is not None else m} of {m} rows; a block whose columns span everything fetches all of B = the plain replicate, SPB_FULL_REPLICATE=1 forces it): pulled from the peers' symmetric memory over NVLink by copy engines (NCCL grouped all-gather of whole shards as fallback), overlapped with consolidate(A)",
                        "l2": "inputs (>= 2 GB per rank) are far larger than the 126 MB L2; no flush needed",
                        "index_type": "int32", "value_type": "f64", "result_fingerprint": fingerprint},
             "phases_rank0": {"ms_consolidate_a_plus_b": ms_cons, "ms_spgemm_symbolic_plus_numeric": ms_spgemm,

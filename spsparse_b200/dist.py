@@ -1,7 +1,8 @@
 """Multi-GPU plumbing for the row-partitioned multiply: A is split by contiguous
 row ranges, B is sharded the same way (by its row = the inner index), consolidated locally, and then
-replicated once on every rank.  Concatenating the ranks' consolidated blocks of C in rank order IS the
-reference's row-major order, so nothing is exchanged after the multiply.
+replicated once on every rank -- or, when a rank's block of A only references an interval of inner indices
+(plan_pulls), just that interval of B's rows is fetched.  Concatenating the ranks' consolidated blocks of C
+in rank order IS the reference's row-major order, so nothing is exchanged after the multiply.
 
 B travels in compressed form: per entry only its column and value (12 bytes instead of the 16 of COO),
 plus one local row pointer per row; the row-index array is redundant once the pointers exist.
@@ -76,12 +77,48 @@ def replicate_csr_finish(st):
         w.wait()
     if st.get("event") is not None:
         torch.cuda.current_stream().wait_event(st["event"])
+    if st.get("final"):  # pruned pull: the pointer is already global
+        return st["ptr"], st["cols"], st["vals"], st["total"]
     ptr, eoffs, roffs = st["ptr"], st["eoffs"], st["roffs"]
     for g in range(1, st["world"]):
         if roffs[g + 1] > roffs[g] and eoffs[g]:
             ptr[int(roffs[g]):int(roffs[g + 1])] += int(eoffs[g])
     ptr[-1] = int(eoffs[-1])
     return ptr, st["cols"], st["vals"], int(eoffs[-1])
+
+
+def plan_pulls(roffs, need_lo: int, need_hi: int):
+    """Which rows of which peer a rank must fetch when its block of A only references the inner indices
+    need_lo..need_hi (inclusive; the interval hull of its column support).  roffs[g]..roffs[g+1] are the global
+    rows of peer g's shard.  Returns [(g, a, b)]: local rows [a, b) of peer g, in rank (= row) order.
+    A block whose columns span everything gets every shard whole -- the plain replicate; a banded block gets its
+    own shard plus a halo."""
+    out = []
+    for g in range(len(roffs) - 1):
+        lo, hi = max(int(need_lo), int(roffs[g])), min(int(need_hi) + 1, int(roffs[g + 1]))
+        if lo < hi:
+            out.append((g, lo - int(roffs[g]), hi - int(roffs[g])))
+    return out
+
+
+def assemble_pruned_ptr(rows_total: int, roffs, pulls, ptr_chunks, e_los, counts, device):
+    """Global row pointer (int32[rows_total + 1]) over the concatenation of the pulled entry ranges: rows that
+    were not fetched are empty.  ptr_chunks[i] = peer rows' LOCAL pointers for pulls[i]; e_los[i] = local offset
+    of the first pulled entry of that peer; counts[i] = entries pulled from it."""
+    ptr = torch.empty(rows_total + 1, dtype=torch.int32, device=device)
+    if not pulls:
+        ptr.zero_()
+        return ptr, 0
+    g0, a0, _ = pulls[0]
+    gl, _, bl = pulls[-1]
+    first, end = int(roffs[g0]) + a0, int(roffs[gl]) + bl
+    ptr[:first] = 0
+    pos = 0
+    for (g, a, b), chunk, e_lo, cnt in zip(pulls, ptr_chunks, e_los, counts):
+        torch.add(chunk, int(pos) - int(e_lo), out=ptr[int(roffs[g]) + a:int(roffs[g]) + b])
+        pos += int(cnt)
+    ptr[end:] = pos
+    return ptr, pos
 
 
 class PeerReplicator:
@@ -100,7 +137,7 @@ class PeerReplicator:
         self.cap_entries, self.cap_rows = (int(x) for x in caps.tolist())
         name = dist.group.WORLD.group_name
         self.bufs, self.hdls = [], []
-        for n, dt in ((self.cap_rows, torch.int32), (self.cap_entries, torch.int32), (self.cap_entries, torch.float64)):
+        for n, dt in ((self.cap_rows + 1, torch.int32), (self.cap_entries, torch.int32), (self.cap_entries, torch.float64)):
             t = symm.empty(max(n, 1), dtype=dt, device=device)
             self.bufs.append(t)
             self.hdls.append(symm.rendezvous(t, name))
@@ -108,17 +145,23 @@ class PeerReplicator:
         self.side = torch.cuda.Stream(device=device)
         self.done = torch.cuda.Event()
 
-    def start(self, local_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor):
+    def start(self, local_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, need=None):
+        """need = (lo, hi): inclusive range of inner indices this rank's block of A references, or None for
+        everything.  Only the rows of B inside it are fetched (plan_pulls), and only the rows some peer asked for
+        are published."""
         dev, rank, world = cols.device, self.rank, self.world
         n_local, rows_local = int(cols.shape[0]), int(local_ptr.shape[0])
         assert n_local <= self.cap_entries and rows_local <= self.cap_rows
-        meta = torch.zeros(2 * world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(meta, torch.tensor([n_local, rows_local], dtype=torch.int64, device=dev))
+        meta = torch.zeros(4 * world, dtype=torch.int64, device=dev)
+        lo, hi = need if need is not None else (0, (1 << 62))
+        dist.all_gather_into_tensor(meta, torch.tensor([n_local, rows_local, lo, hi], dtype=torch.int64, device=dev))
+        meta = meta.view(world, 4).tolist()
+        if need is not None:
+            return self._start_pruned(meta, local_ptr, cols, vals, dev)
         # publish this rank's shard (previous step's readers are past their "done" barrier, see below)
         self.bufs[0][:rows_local].copy_(local_ptr)
         self.bufs[1][:n_local].copy_(cols)
         self.bufs[2][:n_local].copy_(vals)
-        meta = meta.view(world, 2).tolist()
         eoffs = np.concatenate([[0], np.cumsum([m[0] for m in meta])]).astype(np.int64)
         roffs = np.concatenate([[0], np.cumsum([m[1] for m in meta])]).astype(np.int64)
         full = [torch.empty(int(roffs[-1]) + 1, dtype=torch.int32, device=dev),
@@ -139,6 +182,68 @@ class PeerReplicator:
         for t in full:
             t.record_stream(self.side)
         return dict(ptr=full[0], cols=full[1], vals=full[2], works=[], eoffs=eoffs, roffs=roffs, world=world, event=self.done)
+
+
+def _peer_start_pruned(self, meta, local_ptr, cols, vals, dev):
+    rank, world = self.rank, self.world
+    n_local, rows_local = int(cols.shape[0]), int(local_ptr.shape[0])
+    roffs = np.concatenate([[0], np.cumsum([m[1] for m in meta])]).astype(np.int64)
+    pulls = plan_pulls(roffs, meta[rank][2], meta[rank][3])
+    # publish the rows of this shard that some peer will fetch (their hull), at their usual offsets
+    mine = [p for q in range(world) if q != rank for p in plan_pulls(roffs, meta[q][2], meta[q][3]) if p[0] == rank]
+    own = [p for p in pulls if p[0] == rank]
+    want = sorted({x for (_, a, b) in mine + own for x in (a, b)})  # local rows whose pointer value the host needs
+    ptr_at = {}
+    if want:
+        inside = [x for x in want if x < rows_local]
+        got = local_ptr[torch.tensor(inside, dtype=torch.int64, device=dev)].cpu().tolist() if inside else []
+        ptr_at = dict(zip(inside, got))
+        ptr_at[rows_local] = n_local
+    if mine:
+        u_lo, u_hi = min(a for _, a, _ in mine), max(b for _, _, b in mine)
+        e0, e1 = int(ptr_at[u_lo]), int(ptr_at[u_hi])
+        self.bufs[0][u_lo:u_hi].copy_(local_ptr[u_lo:u_hi])
+        self.bufs[0][u_hi:u_hi + 1].fill_(e1)    # pointer one past the last published row
+        self.bufs[1][e0:e1].copy_(cols[e0:e1])
+        self.bufs[2][e0:e1].copy_(vals[e0:e1])
+    cur = torch.cuda.current_stream()
+    self.hdls[0].barrier(channel=0)              # every rank has published
+    self.side.wait_stream(cur)
+    with torch.cuda.stream(self.side):
+        # where the wanted rows start and end inside each peer's shard: two pointers per peer, read from its memory
+        remote = [(g, a, b) for (g, a, b) in pulls if g != rank]
+        rem = torch.stack([self.peers[0][g][x] for (g, a, b) in remote for x in (a, b)]).cpu().tolist() if remote else []
+        ends = {}
+        for i, (g, a, b) in enumerate(remote):
+            ends[g] = (int(rem[2 * i]), int(rem[2 * i + 1]))
+        for (g, a, b) in own:
+            ends[g] = (int(ptr_at[a]), int(ptr_at[b]))
+        e_los = [ends[g][0] for (g, _, _) in pulls]
+        counts = [ends[g][1] - ends[g][0] for (g, _, _) in pulls]
+        total = int(sum(counts))
+        fc = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        fv = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
+        starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        order = sorted(range(len(pulls)), key=lambda i: (pulls[i][0] - rank) % world)  # own shard first, then round the ring
+        chunks = []
+        for i in order:
+            g, a, b = pulls[i]
+            src_c, src_v = (cols, vals) if g == rank else (self.peers[1][g], self.peers[2][g])
+            if counts[i]:
+                fc[int(starts[i]):int(starts[i + 1])].copy_(src_c[e_los[i]:e_los[i] + counts[i]], non_blocking=True)
+                fv[int(starts[i]):int(starts[i + 1])].copy_(src_v[e_los[i]:e_los[i] + counts[i]], non_blocking=True)
+        for (g, a, b) in pulls:
+            chunks.append(local_ptr[a:b] if g == rank else self.peers[0][g][a:b])
+        ptr, total = assemble_pruned_ptr(int(roffs[-1]), roffs, pulls, chunks, e_los, counts, dev)
+        self.hdls[0].barrier(channel=1)          # every rank has finished pulling: buffers may be overwritten
+        self.done.record(self.side)
+    for t in (ptr, fc, fv):
+        t.record_stream(self.side)
+    return dict(ptr=ptr, cols=fc, vals=fv, works=[], final=True, total=total, world=world, event=self.done,
+                pulled_rows=int(sum(b - a for _, a, b in pulls)))
+
+
+PeerReplicator._start_pruned = _peer_start_pruned
 
 
 def replicate_wait(works) -> None:

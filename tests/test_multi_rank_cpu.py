@@ -38,6 +38,28 @@ def _worker(rank, world, port, m, out_dir):
     assert total == Bf.n and np.array_equal(cols.numpy(), Bf.idx[1]) and np.array_equal(vals.numpy(), Bf.val)
     assert np.array_equal(ptr.numpy(), np.searchsorted(Bf.idx[0], np.arange(m + 1)))
     Cb = orc.multiply_mm(1.0, None, Ac, ".", O.Coo(w[0], w[1], w[2], (0,)), Bf, ".", None)
+    # pruned replication: only the rows of B inside the hull of this block's column support are fetched.  The
+    # transport (peer memory on the GPU) is emulated by slicing the gathered shards; plan and assembly are real.
+    from spsparse_b200.dist import assemble_pruned_ptr, plan_pulls
+    roffs, eoffs = st["roffs"], st["eoffs"]
+    need = (int(Ac.idx[1].min()), int(Ac.idx[1].max()))
+    pulls = plan_pulls(roffs, *need)
+    assert 0 < sum(b_ - a_ for _, a_, b_ in pulls) <= (r1 - r0) + 4  # own shard + a halo of 2 rows either side
+    gptr = ptr.numpy().astype(np.int64)
+    chunks, e_los, counts, pc, pv = [], [], [], [], []
+    for g, a_, b_ in pulls:
+        lo, hi = gptr[roffs[g] + a_], gptr[roffs[g] + b_]
+        chunks.append(torch.from_numpy((gptr[roffs[g] + a_:roffs[g] + b_] - eoffs[g]).astype(np.int32)))  # peer-local pointers
+        e_los.append(int(lo - eoffs[g])); counts.append(int(hi - lo))
+        pc.append(cols.numpy()[lo:hi]); pv.append(vals.numpy()[lo:hi])
+    pptr, ptotal = assemble_pruned_ptr(m, roffs, pulls, chunks, e_los, counts, "cpu")
+    pptr = pptr.numpy()
+    assert ptotal == sum(counts) and np.all(np.diff(pptr) >= 0) and pptr[-1] == ptotal
+    rows_p = np.repeat(np.arange(m), np.diff(pptr))
+    Bp = O.Coo((m, m), [rows_p.astype(np.int32), np.concatenate(pc)], np.concatenate(pv), None)
+    Cp = orc.multiply_mm(1.0, None, Ac, ".", O.Coo(w[0], w[1], w[2], (0,)), Bp, ".", None)
+    assert np.array_equal(Cp.idx[0], Cb.idx[0]) and np.array_equal(Cp.idx[1], Cb.idx[1]) and np.array_equal(Cp.val, Cb.val)
+    assert plan_pulls(roffs, 0, m - 1) == [(g, 0, int(roffs[g + 1] - roffs[g])) for g in range(world)]  # global support: whole shards
     np.savez(os.path.join(out_dir, f"c{rank}.npz"), i=Cb.idx[0], k=Cb.idx[1], v=Cb.val, sizes=np.array(sizes))
     dist.barrier()
     dist.destroy_process_group()
