@@ -135,17 +135,23 @@ def run_ours(args):
 
     replicator = [None, False]  # (PeerReplicator or None, tried)
 
-    def gather_b_start(Bc, need=None):
-        """Start replicating the row-sharded, consolidated B on every rank (spsparse_b200/dist.py), in
-        compressed form: local row pointers of this rank's rows + column and value of every entry.
-        Asynchronous, so that consolidate(A) overlaps the NCCL transfers."""
-        from spsparse_b200 import dist as spd
+    def gather_b_prepare(Bc):
+        """Library calls of the replication (main thread only: a context is not re-entrant): views of the
+        consolidated shard's arrays and its row pointers."""
         n_local = Bc.size()
         (p0, p1), pv = Bc.device_ptrs()
-        dptr, _ = Bc.dense_ptr()  # u32[m+1] over all rows; this rank's rows are [r0, r1)
-        local_ptr = torch.as_tensor(DevView(dptr + 4 * r0, r1 - r0, "<i4"), device="cuda")
+        dptr = Bc.dense_ptr_range(r0, r1)  # row pointers of this rank's rows [r0, r1) only: O(shard), not O(m)
+        local_ptr = torch.as_tensor(DevView(dptr, r1 - r0, "<i4"), device="cuda")
         cols = torch.as_tensor(DevView(p1, n_local, "<i4"), device="cuda")
         vals = torch.as_tensor(DevView(pv, n_local, "<f8"), device="cuda")
+        return local_ptr, cols, vals
+
+    def gather_b_start(shard, need=None):
+        """Start replicating the row-sharded, consolidated B on every rank (spsparse_b200/dist.py), in
+        compressed form: local row pointers of this rank's rows + column and value of every entry.
+        Asynchronous, so that consolidate(A) overlaps the transfers."""
+        from spsparse_b200 import dist as spd
+        local_ptr, cols, vals = shard
         if not replicator[1]:
             replicator[1] = True
             if not os.environ.get("SPB_NO_PEER_COPY"):
@@ -167,13 +173,14 @@ def run_ours(args):
         ev[0].record(stream)
         Bc, sb = sp.consolidate(ctx, B_raw, sp.ROW_MAJOR, stats=True)
         ev[1].record(stream)
-        need = None
+        pending = None
         if world > 1:
-            # interval hull of the inner indices this rank's block of A references: only those rows of B are fetched
+            # interval hull of the inner indices this rank's block of A references: only those rows of B are fetched.
+            # (Starting the replication from a helper thread, so that its host round trips overlap consolidate(A), was
+            # tried: kernels of the second stream then waited for the sort on one of the ranks; see profiles/r01_notes.md.)
             (_, a1), _ = A_raw.device_ptrs()
             lo, hi = torch.aminmax(torch.as_tensor(DevView(a1, A_raw.size(), "<i4"), device="cuda"))
-            need = (int(lo.item()), int(hi.item()))
-        pending = gather_b_start(Bc, need) if world > 1 else None
+            pending = gather_b_start(gather_b_prepare(Bc), (int(lo.item()), int(hi.item())))
         ev[2].record(stream)
         Ac, sa = sp.consolidate(ctx, A_raw, sp.ROW_MAJOR, stats=True)
         ev[3].record(stream)

@@ -72,6 +72,10 @@ int spb_coo_device_ptrs(const spb_coo *a, int32_t **d_idx /*[rank]*/, double **d
 /* Dense pointer over the leading sorted index of a consolidated rank-2 array: ptr[v] = offset of the first
  * entry whose index[sort_order[0]] >= v, for v in [0, extent]; device memory owned by (and cached in) `a`. */
 int spb_coo_dense_ptr(spb_ctx *ctx, const spb_coo *a, uint32_t **d_ptr, uint64_t *extent);
+/* The same pointer for the leading-index values lo..hi only: d_ptr[v - lo] for v in [lo, hi], hi - lo + 1 values,
+ * offsets absolute within `a`.  Costs O(rows of a + hi - lo) instead of O(extent): what a rank of the
+ * row-partitioned multiply uses for its own shard of B. */
+int spb_coo_dense_ptr_range(spb_ctx *ctx, const spb_coo *a, uint64_t lo, uint64_t hi, uint32_t **d_ptr);
 /* Wraps a consolidated matrix given in compressed form (caller-owned device memory, not copied): a dense
  * pointer d_ptr[shape[lead_dim]+1] over dimension lead_dim, plus the other dimension's index and the value of
  * every entry.  Only usable as the B operand of spb_multiply_mm_prepared (b_inner_dim = lead_dim) -- this is how

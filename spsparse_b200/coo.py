@@ -97,6 +97,12 @@ class CooArray:
         check(self.ctx.lib.spb_coo_dense_ptr(self.ctx.h, self.h, C.byref(p), C.byref(ext)))
         return p.value, int(ext.value)
 
+    def dense_ptr_range(self, lo, hi):
+        """Device pointer to the hi - lo + 1 values of the dense pointer for leading-index values lo..hi."""
+        p = vp()
+        check(self.ctx.lib.spb_coo_dense_ptr_range(self.ctx.h, self.h, int(lo), int(hi), C.byref(p)))
+        return p.value
+
     # -- accessors ----------------------------------------------------------------------------
     def _info(self):
         rank = C.c_int()

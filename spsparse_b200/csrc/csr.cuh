@@ -79,6 +79,19 @@ __global__ void k_scatter_row_len(const u32 *__restrict__ row_start, const i32 *
         len[row_id[r]] = row_start[r + 1] - row_start[r];
 }
 
+// Same for the leading-index values lo..hi-1 only: len[1 + id - lo] = entries of that row, len[0] = entries of the
+// rows below lo (so that the exclusive scan of len[] yields absolute offsets from its second element on).
+__global__ void k_scatter_row_len_range(const u32 *__restrict__ row_start, const i32 *__restrict__ row_id,
+                                        const u32 *count, u64 lo, u64 hi, u32 *len) {
+    const u32 nr = *count;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += (u64)gridDim.x * blockDim.x) {
+        const u64 id = (u64)row_id[r];
+        const u32 c = row_start[r + 1] - row_start[r];
+        if (id < lo) atomicAdd(&len[0], c);
+        else if (id < hi) len[1 + id - lo] = c;
+    }
+}
+
 // Sparse scale vector -> dense values (absent = 0) and presence mask.
 // Entries whose index is beyond `dim` can never join a row/column and are ignored.
 __global__ void k_densify(const i32 *__restrict__ idx, const double *__restrict__ val, u64 n, u64 dim,

@@ -135,6 +135,8 @@ struct spb_coo {
     bool rows_valid;
     u32 *dense_ptr;  // [extent+1] dense pointer over the leading index, or nullptr
     bool dense_ptr_owned;
+    u32 *range_ptr;  // [1 + (hi-lo) + 1] scan behind spb_coo_dense_ptr_range (its answer starts at range_ptr + 1), or nullptr
+    u64 range_lo, range_hi;
 };
 
 // ---- stream-ordered scratch memory, released when the scope ends ---------------------------------
@@ -290,6 +292,8 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     a->rows_valid = false;
     a->dense_ptr = nullptr;
     a->dense_ptr_owned = true;
+    a->range_ptr = nullptr;
+    a->range_lo = a->range_hi = 0;
     if (allocate) {
         CK(cudaSetDevice(ctx->device));
         size_t cnt = n ? n : 1;
@@ -305,8 +309,9 @@ static void drop_row_cache(spb_ctx *ctx, spb_coo *a) {
         ctx->pool.release(a->row_start);
         ctx->pool.release(a->row_id);
         if (a->dense_ptr_owned) ctx->pool.release(a->dense_ptr);
+        ctx->pool.release(a->range_ptr);
     }
-    a->row_start = nullptr; a->row_id = nullptr; a->dense_ptr = nullptr;
+    a->row_start = nullptr; a->row_id = nullptr; a->dense_ptr = nullptr; a->range_ptr = nullptr;
     a->rows_valid = false; a->nrows = 0;
 }
 
@@ -1012,6 +1017,34 @@ int spb_coo_dense_ptr(spb_ctx *ctx, const spb_coo *a, uint32_t **d_ptr, uint64_t
     CKR(build_dense_ptr(ctx, a, ext, &p));
     *d_ptr = p;
     if (extent) *extent = ext;
+    return SPB_OK;
+}
+
+int spb_coo_dense_ptr_range(spb_ctx *ctx, const spb_coo *a_const, uint64_t lo, uint64_t hi, uint32_t **d_ptr) {
+    if (!ctx || !a_const || !d_ptr) return spb_fail(SPB_ERR_ARG, "spb_coo_dense_ptr_range: null argument");
+    spb_coo *a = const_cast<spb_coo *>(a_const);
+    if (a->rank != 2 || a->sort_order[0] < 0) return spb_fail(SPB_ERR_NOT_SORTED, "spb_coo_dense_ptr_range needs a consolidated rank-2 array");
+    if (lo > hi || hi > a->shape[a->sort_order[0]]) return spb_fail(SPB_ERR_ARG, "spb_coo_dense_ptr_range: bad range");
+    if (!a->idx[a->sort_order[0]]) return spb_fail(SPB_ERR_ARG, "spb_coo_dense_ptr_range: compressed-form array");
+    CK(cudaSetDevice(ctx->device));
+    if (!a->range_ptr || a->range_lo != lo || a->range_hi != hi) {
+        ctx->pool.release(a->range_ptr);
+        a->range_ptr = nullptr;
+        RowIndex ri;
+        CKR(build_row_index(ctx, a, &ri));
+        Scratch ws(ctx);
+        const u64 span = hi - lo;
+        u32 *len, *cnt;
+        CKR(ws.zeroed(&len, span + 2));
+        CKR(ws.get(&cnt, 1));
+        CK(ctx->pool.alloc((void **)&a->range_ptr, (span + 3) * sizeof(u32)));
+        CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        if (ri.nrows) ++ctx->launches, k_scatter_row_len_range<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, lo, hi, len);
+        CKR((exclusive_scan<u32, u32>(ctx, ws, len, a->range_ptr, span + 1)));  // writes span + 2 values
+        CK(cudaStreamSynchronize(ctx->stream));
+        a->range_lo = lo; a->range_hi = hi;
+    }
+    *d_ptr = a->range_ptr + 1;
     return SPB_OK;
 }
 

@@ -142,7 +142,12 @@ class PeerReplicator:
             self.bufs.append(t)
             self.hdls.append(symm.rendezvous(t, name))
         self.peers = [[h.get_buffer(g, (b.shape[0],), b.dtype) for g in range(world)] for h, b in zip(self.hdls, self.bufs)]
-        self.side = torch.cuda.Stream(device=device)
+        # per-step metadata travels through peer memory too: a NCCL collective launched while the radix sort holds
+        # every SM waits for the tail of the running pass (milliseconds); these are plain loads on a high-priority stream
+        self.meta_buf = symm.empty(4, dtype=torch.int64, device=device)
+        self.meta_hdl = symm.rendezvous(self.meta_buf, name)
+        self.meta_peers = [self.meta_hdl.get_buffer(g, (4,), torch.int64) for g in range(world)]
+        self.side = torch.cuda.Stream(device=device, priority=-1)  # tiny kernels + copies: ahead of the sort's blocks
         self.done = torch.cuda.Event()
 
     def start(self, local_ptr: torch.Tensor, cols: torch.Tensor, vals: torch.Tensor, need=None):
@@ -152,10 +157,11 @@ class PeerReplicator:
         dev, rank, world = cols.device, self.rank, self.world
         n_local, rows_local = int(cols.shape[0]), int(local_ptr.shape[0])
         assert n_local <= self.cap_entries and rows_local <= self.cap_rows
-        meta = torch.zeros(4 * world, dtype=torch.int64, device=dev)
         lo, hi = need if need is not None else (0, (1 << 62))
-        dist.all_gather_into_tensor(meta, torch.tensor([n_local, rows_local, lo, hi], dtype=torch.int64, device=dev))
-        meta = meta.view(world, 4).tolist()
+        self.meta_buf.copy_(torch.tensor([n_local, rows_local, lo, hi], dtype=torch.int64), non_blocking=False)
+        self.meta_hdl.barrier(channel=0)         # every rank has written its numbers
+        meta = torch.stack(self.meta_peers).cpu().tolist()
+        self.meta_hdl.barrier(channel=1)         # ... and every rank has read them (the buffer is rewritten next step)
         if need is not None:
             return self._start_pruned(meta, local_ptr, cols, vals, dev)
         # publish this rank's shard (previous step's readers are past their "done" barrier, see below)
@@ -185,6 +191,11 @@ class PeerReplicator:
 
 
 def _peer_start_pruned(self, meta, local_ptr, cols, vals, dev):
+    import os
+    import time
+    trace = bool(os.environ.get("SPB_DIST_TRACE"))
+    t0 = time.perf_counter()
+    marks = []
     rank, world = self.rank, self.world
     n_local, rows_local = int(cols.shape[0]), int(local_ptr.shape[0])
     roffs = np.concatenate([[0], np.cumsum([m[1] for m in meta])]).astype(np.int64)
@@ -206,13 +217,22 @@ def _peer_start_pruned(self, meta, local_ptr, cols, vals, dev):
         self.bufs[0][u_hi:u_hi + 1].fill_(e1)    # pointer one past the last published row
         self.bufs[1][e0:e1].copy_(cols[e0:e1])
         self.bufs[2][e0:e1].copy_(vals[e0:e1])
+    marks.append(("published", time.perf_counter() - t0))
     cur = torch.cuda.current_stream()
+    if trace:
+        cur.synchronize()
+        marks.append(("publish done", time.perf_counter() - t0))
     self.hdls[0].barrier(channel=0)              # every rank has published
-    self.side.wait_stream(cur)
-    with torch.cuda.stream(self.side):
+    if trace:
+        cur.synchronize()
+        marks.append(("barrier0 done", time.perf_counter() - t0))
+    side = cur if os.environ.get("SPB_DIST_ONE_STREAM") else self.side
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
         # where the wanted rows start and end inside each peer's shard: two pointers per peer, read from its memory
         remote = [(g, a, b) for (g, a, b) in pulls if g != rank]
         rem = torch.stack([self.peers[0][g][x] for (g, a, b) in remote for x in (a, b)]).cpu().tolist() if remote else []
+        marks.append(("peer pointers read", time.perf_counter() - t0))
         ends = {}
         for i, (g, a, b) in enumerate(remote):
             ends[g] = (int(rem[2 * i]), int(rem[2 * i + 1]))
@@ -236,9 +256,15 @@ def _peer_start_pruned(self, meta, local_ptr, cols, vals, dev):
             chunks.append(local_ptr[a:b] if g == rank else self.peers[0][g][a:b])
         ptr, total = assemble_pruned_ptr(int(roffs[-1]), roffs, pulls, chunks, e_los, counts, dev)
         self.hdls[0].barrier(channel=1)          # every rank has finished pulling: buffers may be overwritten
-        self.done.record(self.side)
+        self.done.record(side)
+        if trace:
+            marks.append(("enqueued", time.perf_counter() - t0))
+            self.done.synchronize()
+            marks.append(("done", time.perf_counter() - t0))
+            import sys
+            print(f"[dist] rank {rank} pruned pull, ms since start: " + ", ".join(f"{k} {v * 1e3:.2f}" for k, v in marks), file=sys.stderr)
     for t in (ptr, fc, fv):
-        t.record_stream(self.side)
+        t.record_stream(side)
     return dict(ptr=ptr, cols=fc, vals=fv, works=[], final=True, total=total, world=world, event=self.done,
                 pulled_rows=int(sum(b - a for _, a, b in pulls)))
 

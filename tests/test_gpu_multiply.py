@@ -240,6 +240,12 @@ def test_prepared_and_compressed_operands(ctx, orc):
     assert _cases.same_coo(down(C2), want) and st2.products == st1.products
     with pytest.raises(sp.SpbError):
         sp.consolidate(ctx, Bcsr, (0, 1))  # a compressed-form array is a B operand only
+    # ranged pointer == the same stretch of the full one (what a rank of the row-partitioned multiply asks for)
+    from _gpu import dev_to_numpy
+    full = dev_to_numpy(ptr, m + 1, "<i4")
+    for lo, hi in ((0, m), (17, 1203), (m - 5, m), (40, 40)):
+        part = dev_to_numpy(Bc.dense_ptr_range(lo, hi), hi - lo + 1, "<i4")
+        assert np.array_equal(part, full[lo:hi + 1]), (lo, hi)
     for h in (dA, dB, dW, Ac, C1, C2, Bcsr, Bc):
         h.free()
 
