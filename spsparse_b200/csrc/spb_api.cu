@@ -137,6 +137,7 @@ struct spb_coo {
     bool dense_ptr_owned;
     u32 *range_ptr;  // [1 + (hi-lo) + 1] scan behind spb_coo_dense_ptr_range (its answer starts at range_ptr + 1), or nullptr
     u64 range_lo, range_hi;
+    u32 max_row_len;  // longest compressed row, 0 = not computed yet (cached with the row structure)
 };
 
 // ---- stream-ordered scratch memory, released when the scope ends ---------------------------------
@@ -294,6 +295,7 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     a->dense_ptr_owned = true;
     a->range_ptr = nullptr;
     a->range_lo = a->range_hi = 0;
+    a->max_row_len = 0;
     if (allocate) {
         CK(cudaSetDevice(ctx->device));
         size_t cnt = n ? n : 1;
@@ -312,7 +314,7 @@ static void drop_row_cache(spb_ctx *ctx, spb_coo *a) {
         ctx->pool.release(a->range_ptr);
     }
     a->row_start = nullptr; a->row_id = nullptr; a->dense_ptr = nullptr; a->range_ptr = nullptr;
-    a->rows_valid = false; a->nrows = 0;
+    a->rows_valid = false; a->nrows = 0; a->max_row_len = 0;
 }
 
 static void set_order(spb_coo *a, const int *so) {
@@ -731,6 +733,23 @@ static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key
 
 struct EscChunk { i32 *row; i32 *k; double *v; u32 n; };
 
+// Dynamic shared memory that a kernel does not use but that caps how many of its blocks share an SM.  The merge
+// kernels are sensitive to it in both directions: more rows in flight hide the L2 latency of their dependent loads,
+// but also spread L1/L2 over more partially written output sectors and more distinct B rows.
+static size_t ballast_for_blocks(int blocks_per_sm, size_t static_smem) {
+    if (blocks_per_sm <= 0) return 0;
+    const size_t per = (size_t)(227 * 1024) / (size_t)blocks_per_sm;
+    return per > static_smem + 1024 ? per - static_smem - 1024 : 0;
+}
+template <typename K> static int allow_ballast(K kernel) {
+    static thread_local const void *done[16];
+    static thread_local int n = 0;
+    for (int i = 0; i < n; ++i) if (done[i] == (const void *)kernel) return 0;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (n < 16) done[n++] = (const void *)kernel;
+    return 0;
+}
+
 // A: consolidated, sorted by (a_row_dim, other).  B: consolidated, sorted by (b_inner_dim, other).
 static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, int a_row_dim,
                          const spb_coo *sj, const spb_coo *B, int b_inner_dim, const spb_coo *sk,
@@ -768,7 +787,44 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
     CKR(ws.zeroed(&stats, 8));
     const u32 cap = (u32)ctx->sm_count * 32;
-    ++ctx->launches, k_merge_count<<<(u32)div_up(nrows ? nrows : 1, 128), 128, 0, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, stats);
+    // longest row of op(A): picks the leanest register-merge kernels that still cover every mergeable row
+    {
+        spb_coo *Am = const_cast<spb_coo *>(A);
+        if (!Am->max_row_len && nrows) {
+            u32 *mx;
+            CKR(ws.zeroed(&mx, 1));
+            ++ctx->launches, k_row_maxlen<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m.arow_start, nrows, mx);
+            CK(cudaMemcpyAsync(&Am->max_row_len, mx, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    const u32 a_maxlen = A->max_row_len;
+    const int nl_fit = a_maxlen <= 2 ? 2 : a_maxlen <= 4 ? 4 : a_maxlen <= 6 ? 6 : 8;
+    // Measured (tools/merge_sweep.py): the lean builds win where B rows are long (config 3: count 2.92 -> 2.35 ms);
+    // with 5-entry B rows (config 5) the count kernel is fastest as the 8-list build (7.0 ms against 9.8 ms for the
+    // 6-list one at a third more warps), while the numeric kernel still prefers the lean one (10.9 -> 8.8 ms).
+    const double avg_b_len = n_inner ? (double)B->n / (double)n_inner : 0.0;
+    const int nl_count = getenv("SPB_MERGE_NL_COUNT") ? atoi(getenv("SPB_MERGE_NL_COUNT")) : (avg_b_len > 16.0 ? nl_fit : 8);
+    const int nl_num = getenv("SPB_MERGE_NL_NUMERIC") ? atoi(getenv("SPB_MERGE_NL_NUMERIC")) : nl_fit;
+    const int blk_count = getenv("SPB_MERGE_BLOCKS_COUNT") ? atoi(getenv("SPB_MERGE_BLOCKS_COUNT")) : 0;
+    const int blk_num = getenv("SPB_MERGE_BLOCKS_NUMERIC") ? atoi(getenv("SPB_MERGE_BLOCKS_NUMERIC")) : 0;
+    {
+        const u32 g = (u32)div_up(nrows ? nrows : 1, 128);
+        const size_t bal = ballast_for_blocks(blk_count, 0);
+        ++ctx->launches;
+        // L1 / shared-memory split (profiles/r01_notes.md, merge sweep): long B rows are read sequentially by every
+        // thread and want the larger L1; short ones keep the driver's default
+        const double avg_b_row = n_inner ? (double)B->n / (double)n_inner : 0.0;
+        const int carve_c = getenv("SPB_MERGE_CARVEOUT_COUNT") ? atoi(getenv("SPB_MERGE_CARVEOUT_COUNT")) : (avg_b_row > 16.0 ? 25 : -1);
+#define SPB_LAUNCH_COUNT(NL) do { if (bal) CKR(allow_ballast(k_merge_count<NL>)); \
+        if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
+        k_merge_count<NL><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, stats); } while (0)
+        if (nl_count <= 2 && nl_fit <= 2) SPB_LAUNCH_COUNT(2);
+        else if (nl_count <= 4 && nl_fit <= 4) SPB_LAUNCH_COUNT(4);
+        else if (nl_count <= 6 && nl_fit <= 6) SPB_LAUNCH_COUNT(6);
+        else SPB_LAUNCH_COUNT(8);
+#undef SPB_LAUNCH_COUNT
+    }
     CK(cudaGetLastError());
     ull h_stats[8];
     u32 *hash_rows = nullptr;
@@ -904,9 +960,21 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         ++ctx->launches;
         const u32 g = (u32)div_up(nrows, MR_THREADS);
         const int stage = getenv("SPB_MERGE_STAGE") ? atoi(getenv("SPB_MERGE_STAGE")) : 16;
-        if (stage == 16) k_merge_numeric<16><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
-        else if (stage == 4) k_merge_numeric<4><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
-        else k_merge_numeric<8><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val);
+        const size_t bal = ballast_for_blocks(blk_num, (size_t)MR_THREADS * 17 * 12);
+        // numeric: the staging buffers (26 KB per block) compete with L1.  Rows with many products (long sequential
+        // walks through B) ran best with 4 blocks and half of the array as L1, short rows with 7 blocks.
+        const double avg_row_products = h_stats[1] ? (double)h_stats[0] / (double)h_stats[1] : 0.0;
+        const int carve_n = getenv("SPB_MERGE_CARVEOUT_NUMERIC") ? atoi(getenv("SPB_MERGE_CARVEOUT_NUMERIC")) : (avg_row_products > 64.0 ? 50 : 75);
+#define SPB_LAUNCH_NUM(NL, ST) do { if (bal) CKR(allow_ballast(k_merge_numeric<NL, ST>)); \
+        if (carve_n >= 0) CK(cudaFuncSetAttribute(k_merge_numeric<NL, ST>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_n)); \
+        k_merge_numeric<NL, ST><<<g, MR_THREADS, bal, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val); } while (0)
+        if (stage == 4) SPB_LAUNCH_NUM(8, 4);
+        else if (stage == 8) SPB_LAUNCH_NUM(8, 8);
+        else if (nl_num <= 2 && nl_fit <= 2) SPB_LAUNCH_NUM(2, 16);
+        else if (nl_num <= 4 && nl_fit <= 4) SPB_LAUNCH_NUM(4, 16);
+        else if (nl_num <= 6 && nl_fit <= 6) SPB_LAUNCH_NUM(6, 16);
+        else SPB_LAUNCH_NUM(8, 16);
+#undef SPB_LAUNCH_NUM
     }
     for (auto &ch : chunks)
         if (ch.n) ++ctx->launches, k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);

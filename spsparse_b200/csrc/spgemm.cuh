@@ -50,6 +50,15 @@ struct MMOperands {
     int debug;  // experiments only (SPB_MERGE_DEBUG): 1 = skip the global stores, 2 = plain (non-streaming) stores
 };
 
+// ---- longest compressed row (picks the register-merge kernels' NLMAX) ----------------------------------
+__global__ void k_row_maxlen(const u32 *__restrict__ row_start, u32 nrows, u32 *out) {
+    u32 best = 0;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += (u64)gridDim.x * blockDim.x)
+        best = max(best, row_start[r + 1] - row_start[r]);
+    best = __reduce_max_sync(SPB_FULL_MASK, best);
+    if (lane_id() == 0 && best) atomicMax(out, best);
+}
+
 // ---- per A entry: number of products it forms (0 if its row or its j is excluded) -------------
 __global__ void k_entry_products(MMOperands m, const i32 *__restrict__ a_row, u32 *ent_f) {
     for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < m.nnz_a; e += (u64)gridDim.x * blockDim.x) {
@@ -194,8 +203,16 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
     return ROW_MERGE;
 }
 
+// Registers: a merge of NL lists keeps 7 registers per list live (cursor, end, head column, head value, scaled A
+// value).  Compiled for eight lists the kernels need 78-86 registers and run 20 warps per SM, which is what bounds
+// them -- every step waits an L2 round trip for the heads it advanced.  NLMAX = the longest row of op(A) that can
+// take the merge, rounded up to 2/4/6/8 (the host knows it): configs 3 and 5 (4 and 5 entries per row) get kernels
+// with half the registers and twice the warps.
+template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 4 ? 8 : NLMAX <= 6 ? 6 : 5; };
+
 // stats: [0] F of merged rows, [1] rows merged, [2] rows ESC
-__global__ void __launch_bounds__(128, MR_MIN_BLOCKS) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
+template <int NLMAX>
+__global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = ROW_SKIP;
@@ -207,9 +224,9 @@ __global__ void __launch_bounds__(128, MR_MIN_BLOCKS) k_merge_count(MMOperands m
         if (on) {
             if (len > (u32)MERGE_MAX_LISTS) cls = ROW_ESC;   // products counted later, from the per-entry prefix sums
             else if (len <= 2) cls = count_row<2>(m, s, len, max_products, c, f);
-            else if (len <= 4) cls = count_row<4>(m, s, len, max_products, c, f);
-            else if (len <= 6) cls = count_row<6>(m, s, len, max_products, c, f);
-            else cls = count_row<8>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2)>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2)>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2)>(m, s, len, max_products, c, f);
         }
         row_cls[r] = (unsigned char)cls;
         if (cls != ROW_ESC) row_cnt[r] = c;  // ESC rows are filled by the expand-sort-compress stage
@@ -288,8 +305,8 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
     }
 }
 
-template <int STAGE>
-__global__ void __launch_bounds__(MR_THREADS, MR_MIN_BLOCKS) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
+template <int NLMAX, int STAGE>
+__global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? MergeBlocks<NLMAX>::value : 1)) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
                                                               const u64 *__restrict__ c_ptr, i32 *c_i, i32 *c_k,
                                                               double *c_v) {
     __shared__ i32 s_k[MR_THREADS * (STAGE + 1)];
@@ -311,9 +328,9 @@ __global__ void __launch_bounds__(MR_THREADS, MR_MIN_BLOCKS) k_merge_numeric(MMO
     double *sv = s_v + warp * 32 * (STAGE + 1);
     if (maxlen == 0) return;
     if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (maxlen <= 4) merge_rows_warp<4, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (maxlen <= 6) merge_rows_warp<6, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else merge_rows_warp<8, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
 }
 
 // ---- longer rows: shared-memory bitmap (symbolic) + shared-memory hash accumulators (numeric) ----------
