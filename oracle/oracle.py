@@ -127,6 +127,13 @@ class Impl:
                                                C.c_int, C.c_int, _i64p, _f64p]
             f("consolidate_timed").restype = C.c_double
         f("dim_beginnings").restype = C.c_int64
+        u64p = C.POINTER(C.c_uint64)
+        f("transpose").argtypes = [C.c_int, C.c_int64, _i32p, _i32p, C.POINTER(C.c_int), _i32p, _i32p]
+        f("transpose").restype = None
+        f("to_dense").argtypes = [C.c_int, u64p, C.c_int64, _i32p, _i32p, _f64p, C.c_int, _f64p]
+        f("to_dense").restype = C.c_int
+        f("to_sparse").argtypes = [C.c_int, u64p, _f64p, _i32p, _i32p, _f64p]
+        f("to_sparse").restype = C.c_int64
         f("multiply_mm").restype = C.c_int
         f("multiply_mv").argtypes = [C.c_double, C.POINTER(_Vec), C.POINTER(_Mat), C.c_char,
                                      C.POINTER(_Vec), C.POINTER(_Vec), C.c_int, C.c_int,
@@ -167,6 +174,39 @@ class Impl:
             so = (C.c_int * 2)(*a.sort_order)
             m = self._f("dim_beginnings")(a.n, _p32(a.idx[0]), _p32(a.idx[1]), so, out.ctypes.data_as(_i64p))
         return out[:m].copy()
+
+    # ---- algorithm.hpp:46-57 (copy :30-37 is the identity permutation)
+    def transpose(self, a: Coo, perm) -> Coo:
+        n = a.n
+        o0 = np.empty(max(n, 1), dtype=np.int32)
+        o1 = np.empty(max(n, 1), dtype=np.int32)
+        pm = (C.c_int * 2)(*(list(perm) + [0])[:2])
+        i1 = _p32(a.idx[1]) if a.rank > 1 else None
+        self._f("transpose")(a.rank, n, _p32(a.idx[0]), i1, pm, _p32(o0), _p32(o1))
+        idx = [o0[:n].copy()] + ([o1[:n].copy()] if a.rank > 1 else [])
+        return Coo(tuple(a.shape[p] for p in perm), idx, np.array(a.val, dtype=np.float64, copy=True), None)
+
+    # ---- VectorCooArray.hpp:313-321 + accum.hpp:110-140
+    def to_dense(self, a: Coo, policy=ADD) -> np.ndarray:
+        dense = np.empty(tuple(int(x) for x in a.shape), dtype=np.float64)
+        shp = (C.c_uint64 * 2)(*(list(a.shape) + [1])[:2])
+        i1 = _p32(a.idx[1]) if a.rank > 1 else None
+        rc = self._f("to_dense")(a.rank, shp, a.n, _p32(a.idx[0]), i1, _p64f(a.val), int(policy), _p64f(dense))
+        if rc != 0:
+            raise ValueError("to_dense: index out of bounds")
+        return dense
+
+    # ---- algorithm.hpp:433-440
+    def to_sparse(self, dense: np.ndarray) -> Coo:
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        cells = max(dense.size, 1)
+        o0 = np.empty(cells, dtype=np.int32)
+        o1 = np.empty(cells, dtype=np.int32)
+        ov = np.empty(cells, dtype=np.float64)
+        shp = (C.c_uint64 * 2)(*(list(dense.shape) + [1])[:2])
+        m = self._f("to_sparse")(dense.ndim, shp, _p64f(dense), _p32(o0), _p32(o1), _p64f(ov))
+        idx = [o0[:m].copy()] + ([o1[:m].copy()] if dense.ndim > 1 else [])
+        return Coo(tuple(dense.shape), idx, ov[:m].copy(), None)
 
     # ---- xiter.hpp Join2Xiter / Join3Xiter
     def join(self, a, b, c=None):

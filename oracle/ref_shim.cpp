@@ -10,6 +10,9 @@
 //   spsparse::dim_beginnings      slib/spsparse/algorithm.hpp:74-118
 //   spsparse::Join2Xiter/Join3Xiter slib/spsparse/xiter.hpp:149-278
 //   spsparse::multiply (MM, MV)   slib/spsparse/multiply_sparse.hpp:152-248, 281-365
+//   spsparse::transpose           slib/spsparse/algorithm.hpp:46-57
+//   spsparse::copy into DenseAccum (= to_dense with a policy)  algorithm.hpp:30-37, accum.hpp:110-140
+//   spsparse::to_sparse           slib/spsparse/algorithm.hpp:433-440
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -93,6 +96,65 @@ int64_t ref_consolidate(int rank, int64_t n, const int32_t *idx0, const int32_t 
         for (size_t i = 0; i < R.size(); ++i) { out0[i] = R.index(0, i); outv[i] = R.val(i); }
         return (int64_t)R.size();
     }
+}
+
+void ref_transpose(int rank, int64_t n, const int32_t *idx0, const int32_t *idx1, const int *perm,
+                   int32_t *out0, int32_t *out1) {
+    if (rank == 2) {
+        Mat A({(size_t)1 << 31, (size_t)1 << 31});
+        for (int64_t i = 0; i < n; ++i) A.add({idx0[i], idx1[i]}, 1.0);
+        Mat R(A.shape);
+        transpose(R, A, {perm[0], perm[1]});
+        for (size_t i = 0; i < R.size(); ++i) { out0[i] = R.index(0, i); out1[i] = R.index(1, i); }
+    } else {
+        Vec A({(size_t)1 << 31});
+        for (int64_t i = 0; i < n; ++i) A.add({idx0[i]}, 1.0);
+        Vec R(A.shape);
+        transpose(R, A, {perm[0]});
+        for (size_t i = 0; i < R.size(); ++i) out0[i] = R.index(0, i);
+    }
+}
+
+int ref_to_dense(int rank, const uint64_t *shape, int64_t n, const int32_t *idx0, const int32_t *idx1,
+                 const double *val, int policy, double *dense) {
+    if (rank == 2) {
+        Mat A({(size_t)shape[0], (size_t)shape[1]});
+        for (int64_t i = 0; i < n; ++i) A.add({idx0[i], idx1[i]}, val[i]);
+        blitz::Array<double, 2> ret(ibmisc::to_tiny<int, size_t, 2>(A.shape));
+        ret = 0;
+        DenseAccum<Mat> accum(ret, pol(policy));
+        copy(accum, A);
+        for (size_t i = 0; i < shape[0]; ++i)
+            for (size_t j = 0; j < shape[1]; ++j) dense[i * shape[1] + j] = ret((int)i, (int)j);
+    } else {
+        Vec A({(size_t)shape[0]});
+        for (int64_t i = 0; i < n; ++i) A.add({idx0[i]}, val[i]);
+        blitz::Array<double, 1> ret(ibmisc::to_tiny<int, size_t, 1>(A.shape));
+        ret = 0;
+        DenseAccum<Vec> accum(ret, pol(policy));
+        copy(accum, A);
+        for (size_t i = 0; i < shape[0]; ++i) dense[i] = ret((int)i);
+    }
+    return 0;
+}
+
+int64_t ref_to_sparse(int rank, const uint64_t *shape, const double *dense, int32_t *out0, int32_t *out1,
+                      double *outv) {
+    if (rank == 2) {
+        blitz::Array<double, 2> arr((int)shape[0], (int)shape[1]);
+        for (size_t i = 0; i < shape[0]; ++i)
+            for (size_t j = 0; j < shape[1]; ++j) arr((int)i, (int)j) = dense[i * shape[1] + j];
+        Mat R({(size_t)shape[0], (size_t)shape[1]});
+        to_sparse(R, arr);
+        for (size_t i = 0; i < R.size(); ++i) { out0[i] = R.index(0, i); out1[i] = R.index(1, i); outv[i] = R.val(i); }
+        return (int64_t)R.size();
+    }
+    blitz::Array<double, 1> arr((int)shape[0]);
+    for (size_t i = 0; i < shape[0]; ++i) arr((int)i) = dense[i];
+    Vec R({(size_t)shape[0]});
+    to_sparse(R, arr);
+    for (size_t i = 0; i < R.size(); ++i) { out0[i] = R.index(0, i); outv[i] = R.val(i); }
+    return (int64_t)R.size();
 }
 
 // Times only the reference's consolidate() call (container fill excluded); returns seconds.

@@ -13,6 +13,9 @@
  *   - multiply (matrix*matrix)                slib/spsparse/multiply_sparse.hpp:152-248
  *   - multiply (matrix*vector)                slib/spsparse/multiply_sparse.hpp:281-365
  *   - isnone                                  slib/spsparse/spsparse.hpp:95-103
+ *   - transpose / copy                        slib/spsparse/algorithm.hpp:30-57
+ *   - to_dense (DenseAccum) / to_sparse       slib/spsparse/VectorCooArray.hpp:313-321, accum.hpp:110-140,
+ *                                             algorithm.hpp:433-440
  *
  * Parity pinning: tests/test_oracle_*.py check every function here against (a) the golden
  * vectors of the reference's own tests (tests/test_array.cpp:67-79,135-168,
@@ -150,6 +153,64 @@ int64_t orc_consolidate(int rank, int64_t n, const int32_t *idx0, const int32_t 
     }
 finished:
     free(perm);
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * transpose   algorithm.hpp:46-57: every entry, in order, with its indices permuted
+ * (new dimension k takes old dimension perm[k]); copy (:30-37) is the identity permutation.
+ * ---------------------------------------------------------------------------------------- */
+void orc_transpose(int rank, int64_t n, const int32_t *idx0, const int32_t *idx1, const int *perm,
+                   int32_t *out0, int32_t *out1) {
+    const int32_t *idx[2] = {idx0, idx1};
+    int32_t *out[2] = {out0, out1};
+    for (int64_t i = 0; i < n; ++i)
+        for (int new_k = 0; new_k < rank; ++new_k) out[new_k][i] = idx[perm[new_k]][i]; /* :51-54 */
+}
+
+/* ------------------------------------------------------------------------------------------
+ * to_dense   VectorCooArray.hpp:313-321: a zeroed row-major array, then copy() (algorithm.hpp:30-37)
+ * into a DenseAccum (accum.hpp:110-140), entry after entry in stored order.  The method itself uses ADD;
+ * the accumulator's other two policies are restated as written (LEAVE_ALONE overwrites unless the cell
+ * holds a NaN, :128-130).  Returns -1 if an index is outside the shape (blitz would not check).
+ * ---------------------------------------------------------------------------------------- */
+int orc_to_dense(int rank, const uint64_t *shape, int64_t n, const int32_t *idx0, const int32_t *idx1,
+                 const double *val, int policy, double *dense) {
+    uint64_t cells = 1;
+    for (int k = 0; k < rank; ++k) cells *= shape[k];
+    for (uint64_t c = 0; c < cells; ++c) dense[c] = 0.0; /* :316 ret = 0 */
+    for (int64_t i = 0; i < n; ++i) {
+        if (idx0[i] < 0 || (uint64_t)idx0[i] >= shape[0]) return -1;
+        uint64_t c = (uint64_t)idx0[i];
+        if (rank == 2) {
+            if (idx1[i] < 0 || (uint64_t)idx1[i] >= shape[1]) return -1;
+            c = c * shape[1] + (uint64_t)idx1[i];
+        }
+        double *oval = &dense[c];
+        if (policy == ORC_LEAVE_ALONE) { if (!isnan(*oval)) *oval = val[i]; } /* accum.hpp:128-130 */
+        else if (policy == ORC_ADD) *oval += val[i];                           /* :131-133 */
+        else *oval = val[i];                                                   /* :134-136 */
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * to_sparse   algorithm.hpp:433-440: every element != 0 (NaN included) of a row-major dense array,
+ * in storage order.  Outputs need room for every cell.  Returns the number of entries.
+ * ---------------------------------------------------------------------------------------- */
+int64_t orc_to_sparse(int rank, const uint64_t *shape, const double *dense, int32_t *out0, int32_t *out1,
+                      double *outv) {
+    uint64_t cells = 1;
+    for (int k = 0; k < rank; ++k) cells *= shape[k];
+    int64_t m = 0;
+    for (uint64_t c = 0; c < cells; ++c) {
+        if (dense[c] != 0) { /* :438 */
+            if (rank == 2) { out0[m] = (int32_t)(c / shape[1]); out1[m] = (int32_t)(c % shape[1]); }
+            else out0[m] = (int32_t)c;
+            outv[m] = dense[c];
+            ++m;
+        }
+    }
     return m;
 }
 

@@ -41,6 +41,19 @@ def consolidate_case(seed):
                 policy=POLICIES[seed % 3], zero_nan=int((seed // 3) % 2))
 
 
+def dense_case(seed):
+    """Input for transpose / to_dense / to_sparse: small shapes (the dense form is materialised), many
+    duplicate tuples, all value flavours."""
+    rng = np.random.default_rng(5000 + seed)
+    rank = 1 if seed % 5 == 4 else 2
+    n = int([0, 1, 7, 60, 400, 3000][seed % 6])
+    shape = [(3, 4), (40, 50), (64, 33), (1, 200), (257, 2)][seed % 5] if rank == 2 else [(6,), (500,)][seed % 2]
+    idx = [rng.integers(0, s, n).astype(np.int32) for s in shape]
+    val = _values(rng, n, ["pos", "int", "mixed"][seed % 3])
+    perm = (0,) if rank == 1 else ((1, 0) if seed % 2 == 0 else (0, 1))
+    return dict(shape=np.array(shape, np.int64), idx=idx, val=val, perm=np.array(perm, np.int32), policy=POLICIES[seed % 3])
+
+
 def _sparse_vec(rng, dim, flavour, extra_shape=0):
     """Scale vector as the reference wants it: ascending, unique; explicit zeros allowed."""
     k = int(rng.integers(1, dim + 1))

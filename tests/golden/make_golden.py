@@ -53,6 +53,23 @@ def reference_test_inputs(seed, mv):
     return A, B
 
 
+def dense_ops():
+    """4b. transpose / to_dense (DenseAccum, all policies) / to_sparse  """
+    d = Packer()
+    nd = 60
+    for s in range(nd):
+        c = _cases.dense_case(s)
+        a = O.Coo(tuple(c["shape"]), c["idx"], c["val"])
+        put(d, f"d{s}_in", a)
+        d[f"d{s}_args"] = np.array(list(c["perm"]) + [c["policy"]], np.int32)
+        put(d, f"d{s}_T", ref.transpose(a, tuple(c["perm"])))
+        dense = ref.to_dense(a, c["policy"])
+        d[f"d{s}_dense"] = dense
+        put(d, f"d{s}_sparse", ref.to_sparse(dense))
+    d["count"] = np.array(nd)
+    d.save(os.path.join(HERE, "dense_ops_cases.npz"))
+
+
 def main():
     # 1. the reference's own randomized tests, seeds 1..999 (BASELINE config 1)
     d = Packer()
@@ -121,6 +138,8 @@ def main():
     d["count"] = np.array(nmv)
     d.save(os.path.join(HERE, "multiply_mv_cases.npz"))
 
+    dense_ops()
+
     # 5. known answer of BASELINE config 2's generator at reduced size (SURVEY App. C #2 family)
     orc = O.port()
     a = orc.gen_dup_coo(0x5EED0002, 0, 300000, 210000, 12, 1024)
@@ -133,4 +152,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["dense"]:  # only the newest pack
+        dense_ops()
+    else:
+        main()

@@ -138,3 +138,17 @@ def test_config2_family_known_answer(orc):
     w = np.arange(1, r.n + 1, dtype=np.uint64)
     assert [int((w * x.astype(np.uint64)).sum()) for x in r.idx] == [int(c) for c in z["chk"]]
     assert np.array_equal(r.idx[0][::64], z["idx0"]) and np.array_equal(r.val[::64], z["val"])
+
+
+# ---- transpose / to_dense / to_sparse (algorithm.hpp:46-57, accum.hpp:110-140, algorithm.hpp:433-440)
+def test_dense_ops_fixtures(orc):
+    p = _golden.pack("dense_ops_cases")
+    for s in range(int(p["count"])):
+        a = _golden.get_coo(p, f"d{s}_in")
+        args = [int(x) for x in p[f"d{s}_args"]]
+        perm, policy = tuple(args[:-1]), args[-1]
+        assert _cases.same_coo(orc.transpose(a, perm), _golden.get_coo(p, f"d{s}_T")), s
+        dense = orc.to_dense(a, policy)
+        want = p[f"d{s}_dense"]
+        assert dense.shape == want.shape and np.array_equal(dense.view(np.uint64), want.view(np.uint64)), s  # bit for bit, NaN and -0 included
+        assert _cases.same_coo(orc.to_sparse(dense), _golden.get_coo(p, f"d{s}_sparse")), s

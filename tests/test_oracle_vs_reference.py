@@ -46,3 +46,14 @@ def test_join_live(orc, ref):
         lists = [np.unique(rng.integers(0, 30, int(rng.integers(0, 20)))).astype(np.int32) for _ in range(3)]
         assert np.array_equal(orc.join(lists[0], lists[1]), ref.join(lists[0], lists[1]))
         assert np.array_equal(orc.join(*lists), ref.join(*lists))
+
+
+def test_dense_ops_live(orc, ref):
+    for s in range(100, 220):
+        c = _cases.dense_case(s)
+        a = O.Coo(tuple(c["shape"]), c["idx"], c["val"])
+        assert _cases.same_coo(orc.transpose(a, tuple(c["perm"])), ref.transpose(a, tuple(c["perm"]))), s
+        for policy in _cases.POLICIES:
+            g, w = orc.to_dense(a, policy), ref.to_dense(a, policy)
+            assert np.array_equal(g.view(np.uint64), w.view(np.uint64)), (s, policy)
+        assert _cases.same_coo(orc.to_sparse(g), ref.to_sparse(w)), s
