@@ -110,6 +110,20 @@ int spb_sorted_permutation(spb_ctx *ctx, const spb_coo *in, const int *sort_orde
  * sentinel n.  Writes min(count, cap) offsets to host memory, returns the full count. */
 int spb_dim_beginnings(spb_ctx *ctx, const spb_coo *sorted, uint64_t *out, uint64_t cap, uint64_t *count);
 
+/* ---- copy / transpose / to_dense / to_sparse: the steps either side of the path -----------
+ * spb_coo_copy       spsparse::copy into a fresh array            algorithm.hpp:30-37
+ * spb_coo_transpose  spsparse::transpose(ret, A, perm)            algorithm.hpp:46-57: new dimension k takes old
+ *                    dimension perm[k] (indices AND shape); entries keep their order; result not flagged sorted
+ * spb_coo_to_dense   VectorCooArray::to_dense                     VectorCooArray.hpp:313-321, with the duplicate policies
+ *                    of DenseAccum (accum.hpp:110-140; the method itself uses ADD).  `dense` is a HOST array of
+ *                    prod(shape) doubles, row-major, overwritten.  Out-of-bounds indices are an error.
+ * spb_dense_to_coo   spsparse::to_sparse                          algorithm.hpp:433-440: every element != 0 (NaN
+ *                    included) of a HOST row-major array, in storage order; result not flagged sorted */
+int spb_coo_copy(spb_ctx *ctx, const spb_coo *in, spb_coo **out);
+int spb_coo_transpose(spb_ctx *ctx, const spb_coo *in, const int *perm /*[rank]*/, spb_coo **out);
+int spb_coo_to_dense(spb_ctx *ctx, const spb_coo *in, int policy, double *dense);
+int spb_dense_to_coo(spb_ctx *ctx, int rank, const uint64_t *shape, const double *dense, spb_coo **out);
+
 /* ---- multiply, matrix*matrix  (spsparse::multiply, multiply_sparse.hpp:152-248) ---------
  * out = C * diag(si) * op(A) * diag(sj) * op(B) * diag(sk); scale vectors may be NULL; they are
  * used as stored (ascending, non-repeating).  A and B are consolidated internally unless already

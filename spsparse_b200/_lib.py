@@ -50,6 +50,10 @@ SIGNATURES = {
     "spb_coo_device_ptrs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "spb_coo_dense_ptr": (C.c_int, [vp, vp, C.POINTER(vp), u64p]),
     "spb_coo_dense_ptr_range": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.POINTER(vp)]),
+    "spb_coo_copy": (C.c_int, [vp, vp, C.POINTER(vp)]),
+    "spb_coo_transpose": (C.c_int, [vp, vp, C.POINTER(C.c_int), C.POINTER(vp)]),
+    "spb_coo_to_dense": (C.c_int, [vp, vp, C.c_int, C.POINTER(C.c_double)]),
+    "spb_dense_to_coo": (C.c_int, [vp, C.c_int, u64p, C.POINTER(C.c_double), C.POINTER(vp)]),
     "spb_coo_wrap_csr": (C.c_int, [vp, u64p, C.c_int, vp, vp, vp, C.c_uint64, C.POINTER(vp)]),
     "spb_coo_set_sorted": (C.c_int, [vp, intp]),
     "spb_coo_download": (C.c_int, [vp, vp, C.POINTER(i32p), f64p]),

@@ -180,6 +180,37 @@ def consolidate(ctx: Context, A: CooArray, sort_order, duplicate_policy=ADD, zer
     return (out, st) if stats else out
 
 
+def copy(ctx: Context, A: CooArray):
+    """spsparse::copy (algorithm.hpp:30-37) into a fresh array."""
+    h = vp()
+    check(ctx.lib.spb_coo_copy(ctx.h, A.h, C.byref(h)))
+    return CooArray(ctx, h)
+
+
+def transpose(ctx: Context, A: CooArray, perm):
+    """spsparse::transpose (algorithm.hpp:46-57): new dimension k takes old dimension perm[k]."""
+    h = vp()
+    check(ctx.lib.spb_coo_transpose(ctx.h, A.h, (C.c_int * 2)(*(list(perm) + [0])[:2]), C.byref(h)))
+    return CooArray(ctx, h)
+
+
+def to_dense(ctx: Context, A: CooArray, duplicate_policy=ADD):
+    """VectorCooArray::to_dense (VectorCooArray.hpp:313-321; DenseAccum policies accum.hpp:110-140) -> numpy array."""
+    dense = np.empty(tuple(A.shape), dtype=np.float64)
+    if dense.size:
+        check(ctx.lib.spb_coo_to_dense(ctx.h, A.h, int(duplicate_policy), dense.ctypes.data_as(_lib.f64p)))
+    return dense
+
+
+def to_sparse(ctx: Context, dense):
+    """spsparse::to_sparse (algorithm.hpp:433-440): the elements != 0 of a dense array, in storage order."""
+    dense = np.ascontiguousarray(dense, dtype=np.float64)
+    h = vp()
+    check(ctx.lib.spb_dense_to_coo(ctx.h, dense.ndim, (C.c_uint64 * dense.ndim)(*dense.shape),
+                                   dense.ctypes.data_as(_lib.f64p), C.byref(h)))
+    return CooArray(ctx, h)
+
+
 def _h(x):
     return x.h if x is not None else None
 

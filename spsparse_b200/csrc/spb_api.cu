@@ -21,6 +21,7 @@
 #include "reduce_by_key.cuh"
 #include "scan.cuh"
 #include "spgemm.cuh"
+#include "dense_ops.cuh"
 
 thread_local std::string g_last_error;
 
@@ -1156,6 +1157,99 @@ int spb_sorted_permutation(spb_ctx *ctx, const spb_coo *in, const int *sort_orde
     }
     spb_coo_free(ctx, sorted);
     return rc;
+}
+
+// ---- the steps either side of the path: copy / transpose / to_dense / to_sparse -------------------------------
+int spb_coo_transpose(spb_ctx *ctx, const spb_coo *in, const int *perm, spb_coo **out) {
+    if (!ctx || !in || !perm || !out) return spb_fail(SPB_ERR_ARG, "spb_coo_transpose: null argument");
+    bool seen[2] = {false, false};
+    for (int k = 0; k < in->rank; ++k) {
+        if (perm[k] < 0 || perm[k] >= in->rank || seen[perm[k]]) return spb_fail(SPB_ERR_ARG, "spb_coo_transpose: not a permutation");
+        seen[perm[k]] = true;
+    }
+    for (int k = 0; k < in->rank; ++k)
+        if (in->n && !in->idx[k]) return spb_fail(SPB_ERR_ARG, "spb_coo_transpose: compressed-form array");
+    CK(cudaSetDevice(ctx->device));
+    uint64_t shape[2] = {1, 1};
+    for (int k = 0; k < in->rank; ++k) shape[k] = in->shape[perm[k]];
+    CKR(coo_new(ctx, in->rank, shape, in->n, true, out));
+    spb_coo *r = *out;
+    if (in->n) {
+        for (int k = 0; k < in->rank; ++k)  // new dimension k takes old dimension perm[k]  (algorithm.hpp:51-54)
+            CK(cudaMemcpyAsync(r->idx[k], in->idx[perm[k]], in->n * sizeof(i32), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(r->val, in->val, in->n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;  // like a fresh VectorCooArray that was add()ed to: edit mode, not flagged sorted
+}
+
+int spb_coo_copy(spb_ctx *ctx, const spb_coo *in, spb_coo **out) {
+    const int ident[2] = {0, 1};
+    return spb_coo_transpose(ctx, in, ident, out);
+}
+
+int spb_coo_to_dense(spb_ctx *ctx, const spb_coo *in, int policy, double *dense) {
+    if (!ctx || !in || !dense) return spb_fail(SPB_ERR_ARG, "spb_coo_to_dense: null argument");
+    if (policy < 0 || policy > 2) return spb_fail(SPB_ERR_ARG, "unknown duplicate policy %d", policy);
+    CK(cudaSetDevice(ctx->device));
+    const u64 ncols = in->rank == 2 ? in->shape[1] : 1;
+    const u64 cells = in->shape[0] * ncols;
+    if (cells == 0) return SPB_OK;
+    if (cells > (1ull << 33)) return spb_fail(SPB_ERR_TOO_LARGE, "spb_coo_to_dense: %llu cells", (ull)cells);
+    Scratch ws(ctx);
+    double *d;
+    CKR(ws.get(&d, cells));
+    CK(cudaMemsetAsync(d, 0, cells * sizeof(double), ctx->stream));  // ret = 0  (VectorCooArray.hpp:316)
+    if (in->n) {
+        // stable sort by cell, every entry kept (zeros too: REPLACE / LEAVE_ALONE see them), bounds checked
+        const int so[2] = {0, 1};
+        spb_coo *sorted = nullptr;
+        CKR(consolidate_core(ctx, in, so, so, POLICY_KEEP_ALL, false, 0, &sorted, nullptr));
+        ++ctx->launches, k_dense_fold<<<grid_for(sorted->n, 256, (u32)ctx->sm_count * 32), 256, 0, ctx->stream>>>(
+            sorted->idx[0], in->rank == 2 ? sorted->idx[1] : nullptr, sorted->val, sorted->n, ncols, policy, d);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        spb_coo_free(ctx, sorted);
+        if (e != cudaSuccess) return spb_fail(SPB_ERR_CUDA, "spb_coo_to_dense: %s", cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(dense, d, cells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SPB_OK;
+}
+
+int spb_dense_to_coo(spb_ctx *ctx, int rank, const uint64_t *shape, const double *dense, spb_coo **out) {
+    if (!ctx || !shape || !out || (rank != 1 && rank != 2)) return spb_fail(SPB_ERR_ARG, "spb_dense_to_coo: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    const u64 ncols = rank == 2 ? shape[1] : 1;
+    const u64 cells = shape[0] * ncols;
+    if (cells && !dense) return spb_fail(SPB_ERR_ARG, "spb_dense_to_coo: null data pointer");
+    if (cells > (1ull << 33)) return spb_fail(SPB_ERR_TOO_LARGE, "spb_dense_to_coo: %llu cells", (ull)cells);
+    u64 n = 0;
+    Scratch ws(ctx);
+    double *d = nullptr;
+    unsigned char *keep = nullptr;
+    u64 *slot = nullptr;
+    const u32 cap = (u32)ctx->sm_count * 32;
+    if (cells) {
+        CKR(ws.get(&d, cells));
+        CKR(ws.get(&keep, cells));
+        CKR(ws.get(&slot, cells + 1));
+        CK(cudaMemcpyAsync(d, dense, cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ++ctx->launches, k_dense_flags<<<grid_for(cells, 256, cap), 256, 0, ctx->stream>>>(d, cells, keep);
+        CKR((exclusive_scan<unsigned char, u64>(ctx, ws, keep, slot, cells)));
+        CK(cudaMemcpyAsync(&n, slot + cells, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n >= (1ull << 31)) return spb_fail(SPB_ERR_TOO_LARGE, "spb_dense_to_coo: %llu entries; a VectorCooArray holds < 2^31", (ull)n);
+    CKR(coo_new(ctx, rank, shape, n, true, out));
+    spb_coo *r = *out;
+    if (n) {
+        ++ctx->launches, k_dense_compact<<<grid_for(cells, 256, cap), 256, 0, ctx->stream>>>(d, cells, ncols, keep, slot, r->idx[0],
+                                                                                     rank == 2 ? r->idx[1] : nullptr, r->val);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return SPB_OK;  // edit mode, not flagged sorted (to_sparse only add()s)
 }
 
 int spb_dim_beginnings(spb_ctx *ctx, const spb_coo *a, uint64_t *out, uint64_t cap, uint64_t *count) {
