@@ -166,14 +166,17 @@ def run_ours(args):
     timeline = []  # per step: stream-event times (ms) between the phases of the hot path
     pulled = [None]  # rows of B this rank fetched in the last step (None: everything)
 
-    def hot_path(A_raw, B_raw, w):
-        """consolidate(B shard) -> [replicate B, overlapped with] consolidate(A block) -> SpGEMM."""
+    def hot_path(A_raw, B_raw, w, before_a=None):
+        """consolidate(B shard) -> [replicate B, overlapped with] consolidate(A block) -> SpGEMM.
+        before_a: called before the first use of A (the end-to-end run makes the stream wait for A's upload there)."""
         from spsparse_b200 import dist as spd
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record(stream)
         Bc, sb = sp.consolidate(ctx, B_raw, sp.ROW_MAJOR, stats=True)
         ev[1].record(stream)
         pending = None
+        if before_a is not None:
+            before_a()
         if world > 1:
             # interval hull of the inner indices this rank's block of A references: only those rows of B are fetched.
             # (Starting the replication from a helper thread, so that its host round trips overlap consolidate(A), was
@@ -296,7 +299,8 @@ def run_ours(args):
                        torch.empty(m, dtype=torch.int32, device="cuda"), torch.empty(m, dtype=torch.float64, device="cuda")]
                       for _ in range(2)]
             host_in = [hA[0][:nA], hA[1][:nA], hA[2][:nA], hB[0][:nB], hB[1][:nB], hB[2][:nB], hW[0][:m], hW[1][:m]]
-            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            ready = [torch.cuda.Event(), torch.cuda.Event()]      # B and w of the slot are on the device
+            ready_a = [torch.cuda.Event(), torch.cuda.Event()]    # ... and A (uploaded last: consolidate(B) starts under it)
             freed = [torch.cuda.Event(), torch.cuda.Event()]
             state = {"prev_c": None, "prev_done": None}
 
@@ -304,9 +308,12 @@ def run_ours(args):
                 s_ = k % 2
                 up.wait_event(freed[s_])
                 with torch.cuda.stream(up):
-                    for d, h in zip(dev_in[s_], host_in):
-                        d.copy_(h, non_blocking=True)
+                    for j in (3, 4, 5, 6, 7):
+                        dev_in[s_][j].copy_(host_in[j], non_blocking=True)
                     ready[s_].record(up)
+                    for j in (0, 1, 2):
+                        dev_in[s_][j].copy_(host_in[j], non_blocking=True)
+                    ready_a[s_].record(up)
 
             def run_steps(count):
                 nc_last = 0
@@ -322,7 +329,7 @@ def run_ours(args):
                     a = sp.CooArray.wrap_device(ctx, (m, m), [d[0].data_ptr(), d[1].data_ptr()], d[2].data_ptr(), nA)
                     b = sp.CooArray.wrap_device(ctx, (m, m), [d[3].data_ptr(), d[4].data_ptr()], d[5].data_ptr(), nB)
                     ww = sp.CooArray.wrap_device(ctx, (m,), [d[6].data_ptr()], d[7].data_ptr(), m, (0,))
-                    Cm, _ = hot_path(a, b, ww)
+                    Cm, _ = hot_path(a, b, ww, before_a=lambda: stream.wait_event(ready_a[s_]))
                     freed[s_].record(stream)
                     for x in (a, b, ww):
                         x.free()
