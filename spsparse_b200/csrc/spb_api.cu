@@ -840,7 +840,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, A->idx[a_row_dim], ent_f);
         CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
         // second-level bin: long rows with enough products use the bitmap + hash accumulators (needs the columns to fit the bitmap)
-        const bool hash_ok = n_cols <= HASH_MAX_COLS && ctx->hash_min_products != ~0ull;
+        const bool hash_ok = ctx->hash_min_products != ~0ull;
         if (hash_ok) CKR(ws.get(&hash_rows, h_stats[2]));
         ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, ctx->hash_min_products, hash_rows, stats);
         CK(cudaGetLastError());
@@ -862,10 +862,19 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     if (h_stats[5]) {
         ha.rows = hash_rows;
         ha.nrows = (u32)h_stats[5];
-        ha.wpw = (u32)(div_up(div_up(n_cols, 32), HS_WARPS) + 31) & ~31u;
+        // the bitmap covers win_cols columns; wider matrices are handled in column windows (SPB_HASH_WIN_COLS: tests)
+        u64 win_cols = HASH_MAX_COLS;
+        if (const char *e = getenv("SPB_HASH_WIN_COLS")) {
+            const u64 v = strtoull(e, nullptr, 10) & ~31ull;
+            if (v >= 32 && v < win_cols) win_cols = v;
+        }
+        ha.n_win = (u32)div_up(n_cols ? n_cols : 1, win_cols);
+        ha.win_cols = (u32)win_cols;
+        if (ha.n_win > 1) CKR(ws.zeroed(&ha.win_cnt, (u64)ha.nrows * ha.n_win));
+        ha.wpw = (u32)(div_up(div_up(ha.n_win > 1 ? win_cols : n_cols, 32), HS_WARPS) + 31) & ~31u;
         ha.cap = hash_cap;
         ha.row_cnt = row_cnt;
-        hs_grid = ha.nrows < (u32)ctx->sm_count ? ha.nrows : (u32)ctx->sm_count;
+        hs_grid = (u64)ha.nrows * ha.n_win < (u64)ctx->sm_count ? ha.nrows * ha.n_win : (u32)ctx->sm_count;
         hs_smem = (size_t)HS_WARPS * ha.wpw * sizeof(u32);
         CKR(ws.zeroed(&ha.next, 4));
         ha.shrunk = ha.next + 1;

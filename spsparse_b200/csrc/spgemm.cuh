@@ -13,7 +13,7 @@
 //     row runs a k-way merge of the (already column-sorted) B rows entirely in registers -- the
 //     heads of the lists are compared, equal columns are summed in list (= ascending j) order.
 //     A symbolic pass counts, a scan places the rows, the numeric pass repeats the merge and writes.
-//   longer rows (>= hash_min_products products; output columns must fit the shared-memory bitmap):
+//   longer rows (>= hash_min_products products; wide matrices in column windows of the bitmap's size):
 //     symbolic = bitmap of the products' columns, whose set bits in order are the sorted outputs;
 //     numeric = shared-memory hash table column -> output rank with accumulators in rank order,
 //     products added entry after entry (ascending j).
@@ -359,7 +359,10 @@ struct HashArgs {
     u32 *next;           // work counter (zeroed before every launch)
     u32 wpw;             // bitmap words per warp of the symbolic kernel (multiple of 32; HS_WARPS * wpw * 32 >= columns)
     u32 cap;             // outputs per numeric work item (HASH_CAP of the numeric kernel that will run)
-    u32 *row_cnt;        // count pass: number of distinct, unmasked output columns of the row
+    u32 n_win;           // column windows per row: the bitmap covers win_cols columns at a time (1 when they all fit)
+    u32 win_cols;        // multiple of 32
+    u32 *win_cnt;        // [nrows * n_win] count pass: outputs of (row, window); only used when n_win > 1
+    u32 *row_cnt;        // count pass: number of distinct, unmasked output columns of the row (zeroed; windows add up)
     const u64 *c_ptr;    // emit + numeric
     i32 *c_i, *c_k;
     double *c_v;
@@ -418,11 +421,15 @@ __device__ __forceinline__ void stage_entries(u32 bs, u32 len, u32 *st_bs, u32 *
     __syncthreads();
 }
 
+__device__ __forceinline__ u32 hn_lower_bound(const i32 *__restrict__ b_k, u32 lo, u32 hi, i32 key);
+
 // ---- symbolic: bitmap --------------------------------------------------------------------------------------------
+// Matrices with more columns than the bitmap holds are handled in column windows of win_cols columns: a work unit is
+// (row, window); every B row is narrowed to the window by two searches when it is staged.
 template <bool EMIT>
 __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, HashArgs a) {
     extern __shared__ u32 s_bitmap[];  // HS_WARPS * a.wpw words
-    __shared__ u32 s_row, s_item0, s_grab;
+    __shared__ u32 s_row, s_item0, s_grab, s_winbase;
     __shared__ u32 s_wsum[2][HS_WARPS];
     __shared__ u32 s_bs[HS_THREADS], s_pre[HS_THREADS + 1];
     __shared__ u32 s_gcnt[HASH_MAX_COLS / 1024];  // set bits per group of 32 bitmap words, then their exclusive prefix
@@ -433,8 +440,10 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
         __syncthreads();
         if (tid == 0) s_row = atomicAdd(a.next, 1u);
         __syncthreads();
-        if (s_row >= a.nrows) return;
-        const u32 r = a.rows[s_row];
+        if (s_row >= a.nrows * a.n_win) return;
+        const u32 hrow = s_row / a.n_win, win = s_row % a.n_win;  // index into rows[], column window
+        const u32 col0 = win * a.win_cols;                        // first column of the window
+        const u32 r = a.rows[hrow];
         const u32 s = m.arow_start[r], e = m.arow_start[r + 1];
         // ---- products: bits of their columns.  Consecutive lanes hold consecutive products, i.e. (within one B row)
         //      ascending columns, so lanes that hit the same bitmap word form a contiguous run: one ATOMS per run
@@ -444,7 +453,15 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             u32 bs = 0, len = 0;
             if (ent < e) {
                 const i32 j = m.a_j[ent];
-                if (!m.sj_mask || m.sj_mask[j]) { bs = m.bptr[j]; len = m.bptr[j + 1] - bs; }
+                if (!m.sj_mask || m.sj_mask[j]) {
+                    bs = m.bptr[j];
+                    u32 be = m.bptr[j + 1];
+                    if (a.n_win > 1 && bs < be) {
+                        bs = hn_lower_bound(m.b_k, bs, be, (i32)col0);
+                        if ((u64)col0 + a.win_cols <= (u64)INT32_MAX) be = hn_lower_bound(m.b_k, bs, be, (i32)(col0 + a.win_cols));
+                    }
+                    len = be - bs;
+                }
             }
             u32 nE, T;
             if (c0 != s) __syncthreads();  // previous chunk's staging no longer read
@@ -467,14 +484,14 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     if (b0 + u * HS_THREADS >= T) break;  // block-uniform
-                    const u32 word = k[u] >> 5;             // 0x7ffffff for the lanes past the end
+                    const u32 word = k[u] == 0xffffffffu ? 0x7ffffffu : (k[u] - col0) >> 5;  // lanes past the end: no word
                     const u32 prev = __shfl_up_sync(SPB_FULL_MASK, word, 1);
                     const u32 heads = __ballot_sync(SPB_FULL_MASK, lane == 0 || prev != word);
                     const u32 le = 0xffffffffu >> (31 - lane);               // lanes at or below mine
                     const u32 first = 31 - __clz(heads & le);
                     const u32 above = heads & ~le;
                     const u32 last = above ? (u32)__ffs(above) - 2 : 31u;    // last lane of my run
-                    u32 bits = k[u] != 0xffffffffu ? 1u << (k[u] & 31) : 0u;
+                    u32 bits = k[u] != 0xffffffffu ? 1u << (k[u] & 31) : 0u;  // col0 is a multiple of 32
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {  // OR of the run, gathered at its first lane
                         const u32 t = __shfl_down_sync(SPB_FULL_MASK, bits, o);
@@ -498,7 +515,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
                 u32 live = bits;
                 for (u32 t = bits; t; t &= t - 1) {
                     const u32 b = __ffs(t) - 1;
-                    if (m.sk[w * 32 + b] == 0.0) live &= ~(1u << b);
+                    if (m.sk[col0 + w * 32 + b] == 0.0) live &= ~(1u << b);
                 }
                 if (EMIT && live != bits) s_bitmap[w] = live;
                 bits = live;
@@ -519,7 +536,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             if (tid == 0) {
                 u32 total = 0;
                 for (int w = 0; w < HS_WARPS; ++w) total += s_wsum[0][w];
-                a.row_cnt[r] = total;
+                if (a.n_win > 1) { a.win_cnt[(u64)hrow * a.n_win + win] = total; atomicAdd(&a.row_cnt[r], total); }
+                else a.row_cnt[r] = total;
             }
             continue;
         }
@@ -547,10 +565,17 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             if (l0) s_glist[lbefore] = (unsigned short)g0;
             if (l1) s_glist[lbefore + l0] = (unsigned short)g1;
         }
-        const u32 n_items = (total + a.cap - 1) / a.cap;
+        // work items of the numeric pass are cut from the whole row: the row's first window creates them
+        const u32 row_total = a.n_win > 1 ? (u32)(a.c_ptr[r + 1] - a.c_ptr[r]) : total;
+        const u32 n_items = win == 0 ? (row_total + a.cap - 1) / a.cap : 0;
         if (tid == 0) {
-            s_item0 = atomicAdd(a.n_items, n_items);
-            if (n_items > 1) a.row_split[s_row] = atomicAdd(a.split_total, (ull)(n_items - 1) * (e - s));
+            if (win == 0) {
+                s_item0 = atomicAdd(a.n_items, n_items);
+                if (n_items > 1) a.row_split[hrow] = atomicAdd(a.split_total, (ull)(n_items - 1) * (e - s));
+            }
+            u32 before_win = 0;  // outputs of this row in earlier windows
+            for (u32 w2 = 0; w2 < win; ++w2) before_win += a.win_cnt[(u64)hrow * a.n_win + w2];
+            s_winbase = before_win;
             s_grab = 0;
         }
         __syncthreads();
@@ -558,7 +583,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
         //      groups of a power-law row differ in weight by orders of magnitude): the lanes hold 32 consecutive
         //      words, so their outputs are consecutive in C ------------------------------------------------------------
         const i32 irow = m.arow_id[r];
-        const u64 base = a.c_ptr[r];
+        const u64 base = a.c_ptr[r] + s_winbase;
         for (;;) {
             u32 i = 0;
             if (lane == 0) i = atomicAdd(&s_grab, 1u);
@@ -573,10 +598,10 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             u64 pos = base + s_gcnt[g] + incl - c;
             for (; bits; bits &= bits - 1, ++pos) {
                 a.c_i[pos] = irow;
-                a.c_k[pos] = (i32)(w * 32 + __ffs(bits) - 1);
+                a.c_k[pos] = (i32)(col0 + w * 32 + __ffs(bits) - 1);
             }
         }
-        for (u32 p = tid; p < n_items; p += HS_THREADS) a.items[s_item0 + p] = ((u64)s_row << 32) | p;
+        for (u32 p = tid; p < n_items; p += HS_THREADS) a.items[s_item0 + p] = ((u64)hrow << 32) | p;
     }
 }
 

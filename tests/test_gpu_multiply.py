@@ -72,16 +72,20 @@ def test_mm_fixtures_from_the_reference(ctx):
         assert _cases.same_coo(got, want), f"mm case {s}"
 
 
-@pytest.mark.parametrize("variant,item_cap", [(0, 0), (1, 0), (2, 0), (0, 7), (1, 64), (2, 3)])
-def test_mm_fixtures_through_the_hash_accumulator_bin(monkeypatch, variant, item_cap):
+@pytest.mark.parametrize("variant,item_cap,win_cols", [(0, 0, 0), (1, 0, 0), (2, 0, 0), (0, 7, 0), (1, 64, 0), (2, 3, 0),
+                                                       (2, 0, 32), (1, 5, 96), (0, 0, 1024)])
+def test_mm_fixtures_through_the_hash_accumulator_bin(monkeypatch, variant, item_cap, win_cols):
     """Same fixtures with every row forced through the bitmap + shared-memory hash-accumulator kernels (both block
     shapes; with rows cut into many small work items so that the column windows are exercised): the sums are
-    formed in ascending j, so every value is still bit-identical to the reference."""
+    formed in ascending j, so every value is still bit-identical to the reference.  win_cols: bitmap of that many
+    columns only (as for a matrix wider than the 1.5 M columns the real bitmap holds)."""
     import spsparse_b200 as sp
     _esc_env(monkeypatch, 0, 1 << 27, hash_min=0)
     monkeypatch.setenv("SPB_HASH_VARIANT", str(variant))
     if item_cap:
         monkeypatch.setenv("SPB_HASH_ITEM_CAP", str(item_cap))
+    if win_cols:  # bitmap narrower than the matrix: rows are handled in several column windows
+        monkeypatch.setenv("SPB_HASH_WIN_COLS", str(win_cols))
     p = _golden.pack("multiply_mm_cases")
     with sp.Context(0) as c2:
         for s in range(variant, int(p["count"]), 3 if item_cap == 0 else 5):
@@ -284,8 +288,8 @@ def test_medium_scale_against_oracle(ctx, orc):
     dA.free(); R.free()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-def test_hash_accumulator_bin(orc, monkeypatch, variant):
+@pytest.mark.parametrize("variant,win_cols", [(0, 0), (1, 0), (2, 0), (2, 4096)])
+def test_hash_accumulator_bin(orc, monkeypatch, variant, win_cols):
     """Long rows through the bitmap + hash-accumulator kernels: all three bins side by side, scale vectors, a row
     wider than one work item, and rows whose sums cancel exactly (they emit fewer entries than the symbolic
     bound -> gap compaction).  Bit-identical values throughout."""
@@ -322,6 +326,8 @@ def test_hash_accumulator_bin(orc, monkeypatch, variant):
         want, st = orc.multiply_mm(1.5, scales[0], A, ".", None, B, ".", scales[1], want_stats=True)
         _esc_env(monkeypatch, 256, 4000, hash_min=512)
         monkeypatch.setenv("SPB_HASH_VARIANT", str(variant))
+        if win_cols:
+            monkeypatch.setenv("SPB_HASH_WIN_COLS", str(win_cols))
         with sp.Context(0) as c2:
             hs = [up(c2, x) for x in (scales[0], A, B, scales[1])]
             R, gst = sp.multiply(c2, 1.5, hs[0], hs[1], ".", None, hs[2], ".", hs[3], stats=True)
@@ -331,3 +337,30 @@ def test_hash_accumulator_bin(orc, monkeypatch, variant):
             for h in hs + [R]:
                 if h is not None:
                     h.free()
+
+
+def test_hash_bin_wider_than_the_bitmap(ctx, orc):
+    """4 M output columns (the shared-memory bitmap holds 1.5 M): long rows go through the hash bin in three column
+    windows, their outputs cut into many work items; short rows through the merge.  Bit-identical to the oracle."""
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    rng = np.random.default_rng(77)
+    m, nj, nk = 260, 1500, 4_000_000
+    na = 12000
+    ai, aj = rng.integers(0, 200, na), rng.integers(0, nj, na)          # rows 0..199: ~60 entries each
+    ai = np.concatenate([ai, np.arange(200, 260)]); aj = np.concatenate([aj, rng.integers(0, nj, 60)])  # rows 200..259: one entry
+    av = rng.standard_normal(len(ai))
+    nb = 1_500_000
+    bj, bk = rng.integers(0, nj, nb), rng.integers(0, nk, nb)
+    bv = rng.standard_normal(nb)
+    A, B = O.Coo((m, nj), [ai, aj], av), O.Coo((nj, nk), [bj, bk], bv)
+    sk = O.Coo((nk,), [np.arange(0, nk, 3)], 1.0 + (np.arange(0, nk, 3) % 5), (0,))   # two thirds of the columns excluded
+    for scalek in (None, sk):
+        want, st = orc.multiply_mm(0.5, None, A, ".", None, B, ".", scalek, want_stats=True)
+        hs = [up(ctx, x) for x in (A, B, scalek)]
+        R, gst = sp.multiply(ctx, 0.5, None, hs[0], ".", None, hs[1], ".", hs[2], stats=True)
+        assert gst.products == st["F"] and gst.rows_hash >= 190 and gst.rows_merge > 0, gst.asdict()
+        assert _cases.same_coo(down(R), want), scalek is not None
+        for h in hs + [R]:
+            if h is not None:
+                h.free()
