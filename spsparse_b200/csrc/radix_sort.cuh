@@ -101,17 +101,30 @@ __global__ void __launch_bounds__(512) k_sort_hist(SortInput in, int passes, u32
     __syncthreads();
     u32 kept = 0, oob = 0;
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += stride) {
-        i32 hi = ld_stream_i32(in.hi + i);
-        i32 lo = in.lo ? ld_stream_i32(in.lo + i) : 0;
-        double v = ld_stream_f64(in.val + i);
-        if ((u32)hi >= in.extent_hi || (u32)lo >= in.extent_lo) { oob = 1; continue; }
-        if (!input_kept(in, (u32)i, v)) continue;
-        ++kept;
-        u64 key = pack_key(hi, lo, in.bits_lo);
-        for (int p = 0; p < passes; ++p) {
-            atomicAdd(&s_h[p * RS_RADIX + (u32)(key & (RS_RADIX - 1))], 1u);
-            key >>= RS_RADIX_BITS;
+    constexpr int HU = 4;  // entries per thread per trip: all of their loads are issued before the first counter is touched
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < in.n; i0 += HU * stride) {
+        i32 hi[HU], lo[HU];
+        double v[HU];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+            const u64 i = i0 + u * stride;
+            const u64 ic = i < in.n ? i : i0;
+            hi[u] = ld_stream_i32(in.hi + ic);
+            lo[u] = in.lo ? ld_stream_i32(in.lo + ic) : 0;
+            v[u] = ld_stream_f64(in.val + ic);
+        }
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+            const u64 i = i0 + u * stride;
+            if (i >= in.n) break;
+            if ((u32)hi[u] >= in.extent_hi || (u32)lo[u] >= in.extent_lo) { oob = 1; continue; }
+            if (!input_kept(in, (u32)i, v[u])) continue;
+            ++kept;
+            u64 key = pack_key(hi[u], lo[u], in.bits_lo);
+            for (int p = 0; p < passes; ++p) {
+                atomicAdd(&s_h[p * RS_RADIX + (u32)(key & (RS_RADIX - 1))], 1u);
+                key >>= RS_RADIX_BITS;
+            }
         }
     }
     __syncthreads();
