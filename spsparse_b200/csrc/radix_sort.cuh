@@ -95,7 +95,7 @@ __global__ void k_first_kept_pos(SortInput in, u64 *first_kept) {
 
 // ---- histogram of every digit of every pass (one read of the index vectors + values) -----------
 // counters[0] = kept entries, counters[1] = 1 if an index was out of bounds.
-__global__ void __launch_bounds__(512) k_sort_hist(SortInput in, int passes, u32 *hist, u32 *counters) {
+__global__ void __launch_bounds__(512) k_sort_hist(SortInput in, int passes, int shift0, u32 *hist, u32 *counters) {
     __shared__ u32 s_h[RS_MAX_PASSES * RS_RADIX];
     for (int t = threadIdx.x; t < passes * RS_RADIX; t += blockDim.x) s_h[t] = 0;
     __syncthreads();
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(512) k_sort_hist(SortInput in, int passes, u32
             if ((u32)hi[u] >= in.extent_hi || (u32)lo[u] >= in.extent_lo) { oob = 1; continue; }
             if (!input_kept(in, (u32)i, v[u])) continue;
             ++kept;
-            u64 key = pack_key(hi[u], lo[u], in.bits_lo);
+            u64 key = pack_key(hi[u], lo[u], in.bits_lo) >> shift0;  // passes cover the key bits from shift0 upwards
             for (int p = 0; p < passes; ++p) {
                 atomicAdd(&s_h[p * RS_RADIX + (u32)(key & (RS_RADIX - 1))], 1u);
                 key >>= RS_RADIX_BITS;
@@ -366,4 +366,81 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
             a.vals_out[dst] = s_vals[p];
         }
     }
+}
+
+// ---- column order inside the rows -----------------------------------------------------------------------------
+// When the column part of the key is two or more digits wide, the radix passes sort by the ROW part only (stable:
+// the entries of a row stay in insertion order) and this kernel then orders every row's entries by column: entry e
+// looks at the other entries of its row, counts those that must precede it (smaller column, or equal column and
+// earlier = stable) and moves to row start + that count.  Rows are short in the matrices this library is for (a
+// handful of entries; the walk is bounded by SEG_MAX either way), so this is one read and one write of the array in
+// place of (column bits / 8) full passes.  Entries of rows longer than SEG_MAX keep their place and are counted
+// (and flagged when `flags` is given): the host sorts exactly those entries by their full key afterwards.
+constexpr int SG_THREADS = 256;
+constexpr int SG_IPT = 8;
+constexpr int SG_TILE = SG_THREADS * SG_IPT;
+constexpr int SEG_MAX = 64;
+
+__global__ void __launch_bounds__(SG_THREADS) k_segment_sort(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
+                                                             const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
+                                                             unsigned char *flags, u32 *long_count) {
+    __shared__ u64 s_key[SG_TILE + 2 * SEG_MAX];
+    const u32 n = *n_ptr;
+    const u64 base = (u64)blockIdx.x * SG_TILE;
+    if (base >= n) return;
+    const u32 tid = threadIdx.x;
+    for (u32 q = tid; q < SG_TILE + 2 * SEG_MAX; q += SG_THREADS) {
+        const i64 g = (i64)base + (i64)q - SEG_MAX;
+        s_key[q] = (g >= 0 && g < (i64)n) ? ld_stream_u64(keys_in + g) : ~0ull;  // ~0: belongs to no row
+    }
+    double v[SG_IPT];
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u64 g = base + (u64)k * SG_THREADS + tid;
+        v[k] = g < n ? ld_stream_f64(vals_in + g) : 0.0;
+    }
+    __syncthreads();
+    const u64 lo_mask = (1ull << bits_lo) - 1;
+    u32 n_long = 0;
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u32 q = SEG_MAX + (u32)k * SG_THREADS + tid;
+        const u64 g = base + (u64)k * SG_THREADS + tid;
+        if (g >= n) continue;
+        const u64 key = s_key[q];
+        const u64 row = key >> bits_lo, col = key & lo_mask;
+        u32 b = 0, f = 0, before = 0;
+        // inside a row of more than 2 * SEG_MAX entries: no need to walk to find that out
+        if ((s_key[q - SEG_MAX] >> bits_lo) == row || (s_key[q + SEG_MAX] >> bits_lo) == row) b = f = (u32)SEG_MAX;
+        for (; b < (u32)SEG_MAX; ++b) {   // earlier entries of my row
+            const u64 kk = s_key[q - 1 - b];
+            if ((kk >> bits_lo) != row) break;
+            before += (kk & lo_mask) <= col;
+        }
+        for (; f < (u32)SEG_MAX; ++f) {   // later entries of my row
+            const u64 kk = s_key[q + 1 + f];
+            if ((kk >> bits_lo) != row) break;
+            before += (kk & lo_mask) < col;
+        }
+        const bool is_long = b == (u32)SEG_MAX || f == (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
+        const u64 dst = is_long ? g : g - b + before;
+        keys_out[dst] = key;
+        vals_out[dst] = v[k];
+        if (flags) flags[g] = is_long;
+        n_long += is_long;
+    }
+    n_long = __reduce_add_sync(SPB_FULL_MASK, n_long);
+    if (n_long && lane_id() == 0) atomicAdd(long_count, n_long);
+}
+
+// entries of the long rows: out of the array (in order) and back
+__global__ void k_gather_flagged(const u64 *__restrict__ keys, const double *__restrict__ vals, const unsigned char *__restrict__ flags,
+                                 const u64 *__restrict__ slot, u32 n, u64 *k_out, double *v_out) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x)
+        if (flags[e]) { k_out[slot[e]] = keys[e]; v_out[slot[e]] = vals[e]; }
+}
+__global__ void k_scatter_flagged(const u64 *__restrict__ k_sorted, const double *__restrict__ v_sorted,
+                                  const unsigned char *__restrict__ flags, const u64 *__restrict__ slot, u32 n, u64 *keys, double *vals) {
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (u64)gridDim.x * blockDim.x)
+        if (flags[e]) { keys[e] = k_sorted[slot[e]]; vals[e] = v_sorted[slot[e]]; }
 }

@@ -418,9 +418,12 @@ struct SortJob {
 
 // Runs the radix passes over packed keys already in (keysA, valsA) [n_ptr entries, upper bound n_cap];
 // the sorted data ends up in *keys_sorted / *vals_sorted (one of the two buffer pairs).
+template <typename InT, typename OutT>
+static int exclusive_scan(spb_ctx *ctx, Scratch &ws, const InT *in, OutT *out, u64 n);
+
 static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passes, u32 n_cap, const u32 *n_ptr,
                             u32 *hist, u64 *kA, double *vA, u64 *kB, double *vB, const SortInput *in0,
-                            u64 **keys_sorted, double **vals_sorted, Timer *tm, int *mark_after_first) {
+                            u64 **keys_sorted, double **vals_sorted, Timer *tm, int *mark_after_first, int shift0 = 0) {
     const u32 tiles = (u32)div_up(n_cap ? n_cap : 1, RS_TILE);
     u32 *lookback, *tickets;
     CKR(ws.zeroed(&lookback, (u64)passes * tiles * RS_RADIX));
@@ -433,7 +436,7 @@ static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passe
         a.bucket_start = hist + (u64)p * RS_RADIX;
         a.lookback = lookback + (u64)p * tiles * RS_RADIX;
         a.ticket = tickets + p;
-        a.shift = p * RS_RADIX_BITS;
+        a.shift = shift0 + p * RS_RADIX_BITS;
         a.rank_mode = getenv("SPB_RANK_MODE") ? atoi(getenv("SPB_RANK_MODE")) : 0;
         if (p == 0 && first_pass == 0) {
             // pass 0 reads the caller's arrays and writes buffer A
@@ -464,9 +467,21 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     const SortInput &in = job.in;
     const u32 n = in.n;
     const int key_bits = job.bits_hi + in.bits_lo;
-    int passes = (key_bits + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
-    if (passes < 1) passes = 1;
-    if (passes > RS_MAX_PASSES) return spb_fail(SPB_ERR_ARG, "key of %d bits is too wide", key_bits);
+    int passes_full = (key_bits + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
+    if (passes_full < 1) passes_full = 1;
+    if (passes_full > RS_MAX_PASSES) return spb_fail(SPB_ERR_ARG, "key of %d bits is too wide", key_bits);
+    // Radix passes over the row part only + one in-row column sort (k_segment_sort) when that saves at least one pass
+    int passes_row = (job.bits_hi + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
+    if (passes_row < 1) passes_row = 1;
+    // ... and the rows are short: the in-row sort walks each entry's row, so it pays for a handful of entries per row
+    // (config 5: 5 per row, 36.3 -> 28.2 ms) and only breaks even at config 2's 12 per row.  The average over the
+    // POSSIBLE rows is what is known up front; rows longer than SEG_MAX take the fallback inside the branch below.
+    const char *seg_env = getenv("SPB_SEGMENT_SORT");  // "0" never, "1" whenever it saves a pass, unset: heuristic
+    const bool seg_short = (double)n <= 8.0 * (double)in.extent_hi;
+    const bool seg = in.bits_lo > 0 && passes_full - passes_row >= 2 &&
+                     (seg_env ? atoi(seg_env) != 0 : seg_short);
+    const int passes = seg ? passes_row : passes_full;
+    const int shift0 = seg ? in.bits_lo : 0;
     if (n > (1u << 30)) return spb_fail(SPB_ERR_TOO_LARGE, "%u entries exceed the 2^30 per-sort limit", n);
     Scratch ws(ctx);
     Timer tm(ctx->stream);
@@ -485,7 +500,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         ++ctx->launches, k_first_kept_key<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
         ++ctx->launches, k_first_kept_pos<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
     }
-    ++ctx->launches, k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, hist, counters);
+    ++ctx->launches, k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
     ++ctx->launches, k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
     CK(cudaGetLastError());
 
@@ -493,9 +508,47 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     double *vA, *vB = nullptr, *vs;
     CKR(ws.get(&kA, n));
     CKR(ws.get(&vA, n));
-    if (passes > 1) { CKR(ws.get(&kB, n)); CKR(ws.get(&vB, n)); }
+    if (passes > 1 || seg) { CKR(ws.get(&kB, n)); CKR(ws.get(&vB, n)); }
     int t_p0 = t0;
-    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs, &tm, &t_p0));
+    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs, &tm, &t_p0, shift0));
+    const int t_passes = tm.mark();
+    if (seg) {
+        // rows are grouped (insertion order inside): order every row by column
+        u64 *ko = (ks == kA) ? kB : kA;
+        double *vo = (vs == vA) ? vB : vA;
+        const u32 stiles = (u32)div_up(n, SG_TILE);
+        ++ctx->launches, k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+        CK(cudaGetLastError());
+        u32 hc[6];
+        CK(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const u32 n_kept = hc[0], h_long = hc[5];
+        if (h_long && !hc[1]) {
+            // rows longer than SEG_MAX exist: their entries (left in place above) are pulled out in order, sorted by the
+            // full key with the radix passes, and put back -- the pulled-out sequence is ascending in the row, so sorted
+            // position i goes back where gathered position i came from
+            unsigned char *flags;
+            u64 *slot, *lk, *lk2, *lks;
+            double *lv, *lv2, *lvs;
+            u32 *lhist, *lcount;
+            CKR(ws.get(&flags, n_kept));
+            CKR(ws.get(&slot, (u64)n_kept + 1));
+            CK(cudaMemsetAsync(counters + 5, 0, sizeof(u32), ctx->stream));
+            ++ctx->launches, k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+            CKR((exclusive_scan<unsigned char, u64>(ctx, ws, flags, slot, n_kept)));
+            CKR(ws.get(&lk, h_long)); CKR(ws.get(&lv, h_long)); CKR(ws.get(&lk2, h_long)); CKR(ws.get(&lv2, h_long));
+            CKR(ws.zeroed(&lhist, (u64)passes_full * RS_RADIX));
+            CKR(ws.zeroed(&lcount, 8));
+            CK(cudaMemcpyAsync(lcount, &h_long, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+            ++ctx->launches, k_gather_flagged<<<grid_for(n_kept, 256, sgrid * 4), 256, 0, ctx->stream>>>(ks, vs, flags, slot, n_kept, lk, lv);
+            ++ctx->launches, k_keys_hist<<<grid_for(h_long, 512, sgrid), 512, 0, ctx->stream>>>(lk, h_long, passes_full, lhist);
+            ++ctx->launches, k_bucket_starts<<<passes_full, RS_RADIX, 0, ctx->stream>>>(lhist);
+            CKR(run_radix_passes(ctx, ws, 1, passes_full, h_long, lcount, lhist, lk, lv, lk2, lv2, nullptr, &lks, &lvs, nullptr, nullptr));
+            ++ctx->launches, k_scatter_flagged<<<grid_for(n_kept, 256, sgrid * 4), 256, 0, ctx->stream>>>(lks, lvs, flags, slot, n_kept, ko, vo);
+            CK(cudaGetLastError());
+        }
+        ks = ko; vs = vo;
+    }
     const int t1 = tm.mark();
 
     const u32 rtiles = (u32)div_up(n, RK_TILE);
@@ -526,7 +579,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         st->n_in = n; st->n_kept = h[0]; st->n_out = h[2];
         st->key_bits = key_bits; st->passes = passes;
         st->ms_sort = tm.ms(t0, t1); st->ms_reduce = tm.ms(t1, t2); st->ms_total = tm.ms(t0, t2);
-        st->ms_pass = passes > 1 ? tm.ms(t_p0, t1) / (float)(passes - 1) : 0.f;
+        st->ms_pass = passes > 1 ? tm.ms(t_p0, t_passes) / (float)(passes - 1) : 0.f;
     }
     return 0;
 }

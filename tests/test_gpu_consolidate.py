@@ -184,3 +184,42 @@ def test_medium_scale_against_oracle(ctx, orc):
     perm = A.sorted_permutation((0, 1))
     assert np.array_equal(perm, orc.sorted_permutation(a, (0, 1)))
     A.free()
+
+
+@pytest.mark.parametrize("mode", ["1", "0"])
+def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode):
+    """The sort's second organisation -- radix passes over the row part of the key only, then every row ordered by
+    column (k_segment_sort), rows longer than 64 entries re-sorted by their full key -- forced on (and off) for shapes
+    with a wide column part: short rows, rows around the 64-entry limit, hub rows of thousands of entries next to
+    short ones, all policies, zero_nan, both sort orders.  Same answers as the oracle, bit for bit."""
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    monkeypatch.setenv("SPB_SEGMENT_SORT", mode)
+    rng = np.random.default_rng(11)
+    cases = []
+    for s, (shape, n, hubs) in enumerate([((300, 1 << 20), 5000, 0), ((3, 1 << 20), 4000, 0), ((2000, 1 << 18), 60000, 3),
+                                          ((1 << 16, 1 << 16), 200000, 2), ((70, 1 << 17), 70 * 64, 0), ((1 << 20, 300), 30000, 1),
+                                          ((5, 100000), 4099, 0), ((40000, 1 << 16), 1, 0)]):
+        i = rng.integers(0, shape[0], n)
+        k = rng.integers(0, min(shape[1], 5000 if s % 2 else shape[1]), n)     # odd cases: many duplicate tuples
+        for h in range(hubs):                                                   # hub rows: thousands of entries
+            m = rng.integers(1000, 9000)
+            i[h * 9000:h * 9000 + m] = 17 + 5 * h
+        if s == 4:
+            i = np.repeat(np.arange(70), 64)[:n] + 0                            # every row exactly 64 entries ...
+            i[:130] = 3                                                          # ... one with 65+ (just over the limit)
+        v = _cases._values(rng, n, ["pos", "int", "mixed"][s % 3])
+        cases.append(O.Coo(shape, [i, k], v))
+    with sp.Context(0) as c2:
+        for s, a in enumerate(cases):
+            for so in ((0, 1), (1, 0)):
+                for pol in _cases.POLICIES:
+                    zn = (s + pol) % 2
+                    A = up(c2, a)
+                    R, st = sp.consolidate(c2, A, so, pol, zn, stats=True)
+                    got = down(R)
+                    db = R.dim_beginnings()
+                    A.free(); R.free()
+                    want = orc.consolidate(a, so, pol, zn)
+                    assert _cases.same_coo(got, want), (s, so, pol)
+                    assert np.array_equal(db, orc.dim_beginnings(want)), (s, so, pol)
