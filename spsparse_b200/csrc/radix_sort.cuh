@@ -381,7 +381,136 @@ constexpr int SG_IPT = 8;
 constexpr int SG_TILE = SG_THREADS * SG_IPT;
 constexpr int SEG_MAX = 64;
 
-__global__ void __launch_bounds__(SG_THREADS) k_segment_sort(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
+__global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
+                                                                const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
+                                                                unsigned char *flags, u32 *long_count) {
+    // window = the tile plus SEG_MAX entries either side: a row of at most SEG_MAX entries that owns an entry of the
+    // tile lies inside it completely
+    constexpr int W = SG_TILE + 2 * SEG_MAX;
+    constexpr int ITS = (W + SG_THREADS - 1) / SG_THREADS;
+    constexpr int NG = ITS * SG_THREADS / 32;  // groups of 32 window entries (the last ones are padding)
+    __shared__ u64 s_key[W];
+    __shared__ u32 s_col[W];          // column part of every key
+    __shared__ u32 s_hb[NG];          // per group: bit l set = entry l starts a row
+    __shared__ u32 s_last[NG];        // position of the last row start at or before the end of the group (0: none but entry 0)
+    __shared__ u32 s_first[NG];       // position of the first row start inside the group (or beyond the window)
+    const u32 n = *n_ptr;
+    const u64 base = (u64)blockIdx.x * SG_TILE;
+    if (base >= n) return;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 q = tid; q < (u32)W; q += SG_THREADS) {
+        const i64 g = (i64)base + (i64)q - SEG_MAX;
+        s_key[q] = (g >= 0 && g < (i64)n) ? ld_stream_u64(keys_in + g) : ~0ull;  // ~0: belongs to no row
+    }
+    // the values are only moved: pull their lines into L2 now, load them when the destinations are known
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u64 g = base + (u64)k * SG_THREADS + tid;
+        if (g < n && (lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals_in + g));
+    }
+    __syncthreads();
+    const u64 lo_mask = (1ull << bits_lo) - 1;
+    // ---- where the rows start: one ballot per group of 32 window entries ------------------------------------------------
+#pragma unroll
+    for (int it = 0; it < ITS; ++it) {
+        const u32 q = (u32)it * SG_THREADS + tid;
+        bool head = true;  // padding beyond the window: a row start, so that the last real row ends at the window's edge
+        if (q < (u32)W) {
+            const u64 kk = s_key[q];
+            s_col[q] = (u32)(kk & lo_mask);
+            head = q == 0 || (s_key[q - 1] >> bits_lo) != (kk >> bits_lo);
+        }
+        const u32 hb = __ballot_sync(SPB_FULL_MASK, head);
+        if (lane == 0) {
+            const u32 g = q >> 5;
+            s_hb[g] = hb;
+            s_last[g] = hb ? (g << 5) + 31 - __clz(hb) : 0;
+            s_first[g] = hb ? (g << 5) + __ffs(hb) - 1 : 0xffffffffu;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // s_last[g] := last row start BEFORE group g; s_first[g] := first row start AFTER group g
+        u32 carry = 0;
+        for (int r = 0; r < (NG + 31) / 32; ++r) {
+            const int g = r * 32 + (int)lane;
+            const u32 mine = g < NG ? s_last[g] : 0;
+            u32 inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(SPB_FULL_MASK, inc, o);
+                if (lane >= (u32)o) inc = max(inc, t);
+            }
+            u32 exc = __shfl_up_sync(SPB_FULL_MASK, inc, 1);
+            if (lane == 0) exc = 0;
+            if (g < NG) s_last[g] = max(exc, carry);
+            carry = max(carry, __shfl_sync(SPB_FULL_MASK, inc, 31));
+        }
+        carry = 0xffffffffu;
+        for (int r = (NG + 31) / 32 - 1; r >= 0; --r) {
+            const int g = r * 32 + (int)lane;
+            const u32 mine = g < NG ? s_first[g] : 0xffffffffu;
+            u32 inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_down_sync(SPB_FULL_MASK, inc, o);
+                if (lane + o < 32) inc = min(inc, t);
+            }
+            u32 exc = __shfl_down_sync(SPB_FULL_MASK, inc, 1);
+            if (lane == 31) exc = 0xffffffffu;
+            if (g < NG) s_first[g] = min(exc, carry);
+            carry = min(carry, __shfl_sync(SPB_FULL_MASK, inc, 0));
+        }
+    }
+    __syncthreads();
+    // ---- my entries: position inside the row = entries that must precede it --------------------------------------------
+    u32 n_long = 0;
+    i32 shift_by[SG_IPT];  // destination - source position (inside a row: small); INT32_MIN: entry of a long row
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u32 q = SEG_MAX + (u32)k * SG_THREADS + tid;
+        const u64 g = base + (u64)k * SG_THREADS + tid;
+        shift_by[k] = 0;
+        if (g >= n) continue;
+        const u32 grp = q >> 5, l = q & 31, hb = s_hb[grp];
+        const u32 below = hb & (0xffffffffu >> (31 - l));
+        const u32 st = below ? (grp << 5) + 31 - __clz(below) : s_last[grp];
+        const u32 above = l < 31 ? hb & (0xffffffffu << (l + 1)) : 0u;
+        const u32 nx = above ? (grp << 5) + __ffs(above) - 1 : s_first[grp];   // start of the next row
+        const bool is_long = nx - st > (u32)SEG_MAX;  // (a row cut by the window's edge shows more than SEG_MAX entries too)
+        if (!is_long) {
+            const u32 col = s_col[q];
+            u32 before = 0;
+            for (u32 j = st; j < q; ++j) before += s_col[j] <= col;      // earlier entries: stable
+            for (u32 j = q + 1; j < nx; ++j) before += s_col[j] < col;   // later entries
+            shift_by[k] = (i32)(st + before) - (i32)q;
+        }
+        if (flags) flags[g] = is_long;
+        n_long += is_long;
+    }
+    double v[SG_IPT];
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u64 g = base + (u64)k * SG_THREADS + tid;
+        v[k] = g < n ? ld_stream_f64(vals_in + g) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u64 g = base + (u64)k * SG_THREADS + tid;
+        if (g < n) {
+            const u64 dst = (u64)((i64)g + shift_by[k]);
+            keys_out[dst] = s_key[SEG_MAX + k * SG_THREADS + tid];
+            vals_out[dst] = v[k];
+        }
+    }
+    n_long = __reduce_add_sync(SPB_FULL_MASK, n_long);
+    if (n_long && lane == 0) atomicAdd(long_count, n_long);
+}
+
+// The same for rows of a handful of entries (banded, regridding matrices): every entry simply walks its neighbours in
+// the window -- no row table, one barrier.  Measured on the 5-entries-per-row config 5 block: 3.3 ms against 5.0 ms for the
+// kernel above; at config 2's 12 entries per row the walk costs 4.5 ms against 2.5 ms.
+__global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
                                                              const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
                                                              unsigned char *flags, u32 *long_count) {
     __shared__ u64 s_key[SG_TILE + 2 * SEG_MAX];

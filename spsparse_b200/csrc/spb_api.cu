@@ -473,11 +473,13 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     // Radix passes over the row part only + one in-row column sort (k_segment_sort) when that saves at least one pass
     int passes_row = (job.bits_hi + RS_RADIX_BITS - 1) / RS_RADIX_BITS;
     if (passes_row < 1) passes_row = 1;
-    // ... and the rows are short: the in-row sort walks each entry's row, so it pays for a handful of entries per row
-    // (config 5: 5 per row, 36.3 -> 28.2 ms) and only breaks even at config 2's 12 per row.  The average over the
-    // POSSIBLE rows is what is known up front; rows longer than SEG_MAX take the fallback inside the branch below.
+    // ... and the rows are short: the in-row sort compares every entry with the rest of its row (config 5, 5 per row:
+    // 36.3 -> 28.4 ms; config 2, 12 per row: 12.8 -> 10.8 ms).  The average over the POSSIBLE rows is what is known up
+    // front; rows longer than SEG_MAX take the fallback inside the branch below.
     const char *seg_env = getenv("SPB_SEGMENT_SORT");  // "0" never, "1" whenever it saves a pass, unset: heuristic
-    const bool seg_short = (double)n <= 8.0 * (double)in.extent_hi;
+    const bool seg_short = (double)n <= 16.0 * (double)in.extent_hi;
+    const char *walk_env = getenv("SPB_SEGMENT_WALK");
+    const bool seg_walk = walk_env ? atoi(walk_env) != 0 : (double)n <= 6.0 * (double)in.extent_hi;  // very short rows: neighbour walk
     const bool seg = in.bits_lo > 0 && passes_full - passes_row >= 2 &&
                      (seg_env ? atoi(seg_env) != 0 : seg_short);
     const int passes = seg ? passes_row : passes_full;
@@ -517,7 +519,9 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         u64 *ko = (ks == kA) ? kB : kA;
         double *vo = (vs == vA) ? vB : vA;
         const u32 stiles = (u32)div_up(n, SG_TILE);
-        ++ctx->launches, k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+        ++ctx->launches;
+        if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+        else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
         CK(cudaGetLastError());
         u32 hc[6];
         CK(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
@@ -534,7 +538,9 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
             CKR(ws.get(&flags, n_kept));
             CKR(ws.get(&slot, (u64)n_kept + 1));
             CK(cudaMemsetAsync(counters + 5, 0, sizeof(u32), ctx->stream));
-            ++ctx->launches, k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+            ++ctx->launches;
+            if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+            else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
             CKR((exclusive_scan<unsigned char, u64>(ctx, ws, flags, slot, n_kept)));
             CKR(ws.get(&lk, h_long)); CKR(ws.get(&lv, h_long)); CKR(ws.get(&lk2, h_long)); CKR(ws.get(&lv2, h_long));
             CKR(ws.zeroed(&lhist, (u64)passes_full * RS_RADIX));

@@ -186,8 +186,8 @@ def test_medium_scale_against_oracle(ctx, orc):
     A.free()
 
 
-@pytest.mark.parametrize("mode", ["1", "0"])
-def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode):
+@pytest.mark.parametrize("mode,walk", [("1", "1"), ("1", "0"), ("0", "0")])
+def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk):
     """The sort's second organisation -- radix passes over the row part of the key only, then every row ordered by
     column (k_segment_sort), rows longer than 64 entries re-sorted by their full key -- forced on (and off) for shapes
     with a wide column part: short rows, rows around the 64-entry limit, hub rows of thousands of entries next to
@@ -195,6 +195,7 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode):
     import spsparse_b200 as sp
     from _gpu import up, down
     monkeypatch.setenv("SPB_SEGMENT_SORT", mode)
+    monkeypatch.setenv("SPB_SEGMENT_WALK", walk)   # which of the two in-row kernels (neighbour walk / row table)
     rng = np.random.default_rng(11)
     cases = []
     for s, (shape, n, hubs) in enumerate([((300, 1 << 20), 5000, 0), ((3, 1 << 20), 4000, 0), ((2000, 1 << 18), 60000, 3),
