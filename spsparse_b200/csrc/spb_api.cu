@@ -477,7 +477,9 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     // 36.3 -> 28.4 ms; config 2, 12 per row: 12.8 -> 10.8 ms).  The average over the POSSIBLE rows is what is known up
     // front; rows longer than SEG_MAX take the fallback inside the branch below.
     const char *seg_env = getenv("SPB_SEGMENT_SORT");  // "0" never, "1" whenever it saves a pass, unset: heuristic
-    const bool seg_short = (double)n <= 16.0 * (double)in.extent_hi;
+    // (small arrays keep the plain passes: a saved pass is microseconds there, the extra read-back of the long-row count
+    // and a possible fallback are not -- R-MAT scale 20's 4 M-entry operand went 0.85 -> 2.3 ms with it)
+    const bool seg_short = (double)n <= 16.0 * (double)in.extent_hi && n >= (1u << 23);
     const char *walk_env = getenv("SPB_SEGMENT_WALK");
     const bool seg_walk = walk_env ? atoi(walk_env) != 0 : (double)n <= 6.0 * (double)in.extent_hi;  // very short rows: neighbour walk
     const bool seg = in.bits_lo > 0 && passes_full - passes_row >= 2 &&
