@@ -85,3 +85,43 @@ def test_row_partition_matches_single_process(tmp_path):
     assert np.array_equal(got_i, want.idx[0]) and np.array_equal(got_k, want.idx[1])
     assert np.array_equal(got_v, want.val)
     assert int(parts[0]["sizes"].sum()) == 5 * m - 6  # B shards together hold the consolidated B
+
+
+def test_pruned_plan_and_assembly_random():
+    """plan_pulls + assemble_pruned_ptr on random shard sizes and need ranges (pure functions, no process group): every
+    needed row comes back with exactly its entries, every other row is empty, and the pointer is monotone."""
+    sys.path.insert(0, ROOT)
+    from spsparse_b200.dist import assemble_pruned_ptr, plan_pulls
+    rng = np.random.default_rng(123)
+    for trial in range(200):
+        world = int(rng.integers(1, 7))
+        rows = [int(rng.integers(0, 40)) for _ in range(world)]          # some shards may be empty
+        roffs = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        m = int(roffs[-1])
+        if m == 0:
+            continue
+        row_len = rng.integers(0, 6, m)                                  # entries per global row
+        # per-shard local pointers (with the sentinel) and entry payloads = (global row, running number)
+        lptr, payload = [], []
+        for g in range(world):
+            ln = row_len[roffs[g]:roffs[g + 1]]
+            lptr.append(np.concatenate([[0], np.cumsum(ln)]).astype(np.int32))
+            payload.append(np.repeat(np.arange(roffs[g], roffs[g + 1]), ln))
+        lo = int(rng.integers(0, m)); hi = int(rng.integers(lo, m))
+        if trial % 10 == 0:
+            lo, hi = 0, m - 1
+        pulls = plan_pulls(roffs, lo, hi)
+        assert sum(b - a for _, a, b in pulls) == hi - lo + 1
+        chunks = [torch.from_numpy(lptr[g][a:b].copy()) for g, a, b in pulls]
+        e_los = [int(lptr[g][a]) for g, a, b in pulls]
+        counts = [int(lptr[g][b] - lptr[g][a]) for g, a, b in pulls]
+        ptr, total = assemble_pruned_ptr(m, roffs, pulls, chunks, e_los, counts, "cpu")
+        ptr = ptr.numpy().astype(np.int64)
+        data = np.concatenate([payload[g][lptr[g][a]:lptr[g][b]] for g, a, b in pulls]) if pulls else np.empty(0, np.int64)
+        assert total == len(data) == ptr[-1] and np.all(np.diff(ptr) >= 0) and ptr[0] == 0
+        for r in range(m):
+            got = data[ptr[r]:ptr[r + 1]]
+            if lo <= r <= hi:
+                assert len(got) == row_len[r] and np.all(got == r)
+            else:
+                assert len(got) == 0
