@@ -46,12 +46,52 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md's clocks line).
+
+    NVML is polled from a thread every 2 ms (a timed region can be as short as 50 ms at 8 GPUs, where a
+    100 ms `nvidia-smi -lms` loop returns nothing); `nvidia-smi` stays as the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, uuid=None):
+        import threading
+        self.p = self.f = self.thread = None
+        self.sm, self.reasons, self.smax = [], set(), None
+        self.halt = threading.Event()
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID(uuid) if uuid else nv.nvmlDeviceGetHandleByIndex(gpu)
+            except (nv.NVMLError, TypeError):
+                h = nv.nvmlDeviceGetHandleByIndex(gpu)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                    nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                    nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                    nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+
+            def poll():
+                while not self.halt.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for b, nm in bits.items():
+                            if r & b:
+                                self.reasons.add(nm)
+                    except nv.NVMLError:
+                        pass
+                    self.halt.wait(0.002)
+
+            self.source = "nvml, 2 ms period"
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001 -- no NVML: fall back to the nvidia-smi loop
+            self.thread = None
+        self.source = "nvidia-smi -lms 100"
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -60,8 +100,17 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        if self.thread is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.smax, reasons=sorted(self.reasons),
+                           samples=len(self.sm))
+            return out
         if self.p is None:
+            if self.f is not None:
+                os.unlink(self.f.name)
             return out
         self.p.terminate()
         try:
@@ -71,7 +120,6 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
@@ -80,13 +128,21 @@ class ClockSampler:
                 sm.append(float(c[1])); smax.append(float(c[2]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[5:9]):
+            for nm, v in zip(self.NAMES, c[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         os.unlink(self.f.name)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
         return out
+
+
+def gpu_uuid(torch, local):
+    """NVML name of the CUDA device `local` (CUDA_VISIBLE_DEVICES may renumber the devices; NVML never does)."""
+    try:
+        return "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 class DevView:
@@ -217,7 +273,7 @@ def run_ours(args):
             Cm.free()
         barrier()
         l0 = launches()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local, gpu_uuid(torch, local)) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = []
         e0.record(stream)

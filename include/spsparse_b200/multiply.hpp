@@ -11,6 +11,58 @@
 
 namespace spsparse {
 
+// ---- row walkers of one multiply operand, with or without a diagonal scale vector ------------------------
+// Interface mirrored: MultXiter multiply_sparse.hpp:39-46, SimpleMultXiter :52-66, ScaledMultXiter :71-90,
+// new_mult_xiter :98-111.  A walker visits the non-empty rows (leading sorted dimension) of a consolidated
+// matrix; with a scale vector it visits only the rows the vector has an entry for and reports that entry.
+// multiply() below does not need them -- the kernels read dense-ified scale vectors -- they are here for host
+// code that walks operands the way the reference's multiply does.  The matrix must be consolidated
+// (dim_beginnings_xiter needs the sort flag); the scale vector ascending and duplicate-free.
+template <class MatT>
+struct MultXiter {
+    typedef typename DimBeginningsXiter<MatT>::sub_xiter_type sub_xiter_type;
+    virtual ~MultXiter() {}
+    virtual typename MatT::index_type index() = 0;       // the row's index
+    virtual bool eof() = 0;
+    virtual void operator++() = 0;
+    virtual typename MatT::val_type scale_val() = 0;     // scale[index()], 1 without a scale vector
+    virtual sub_xiter_type sub_xiter() = 0;              // the row's entries
+};
+
+template <class MatT>
+class SimpleMultXiter : public MultXiter<MatT> {
+    DimBeginningsXiter<MatT> rows;
+
+public:
+    explicit SimpleMultXiter(MatT const &A) : rows(A.dim_beginnings_xiter()) {}
+    typename MatT::index_type index() { return *rows; }
+    bool eof() { return rows.eof(); }
+    void operator++() { ++rows; }
+    typename MatT::val_type scale_val() { return 1; }
+    typename MultXiter<MatT>::sub_xiter_type sub_xiter() { return rows.sub_xiter(); }
+};
+
+template <class MatT, class ScaleT>
+class ScaledMultXiter : public MultXiter<MatT> {
+    typedef ValSTLXiter<typename ScaleT::const_dim_iterator> scale_xiter_type;
+    Join2Xiter<DimBeginningsXiter<MatT>, scale_xiter_type> both;  // rows present in A AND in the scale vector
+
+public:
+    ScaledMultXiter(MatT const &A, ScaleT const &scale)
+        : both(A.dim_beginnings_xiter(), scale_xiter_type(scale.dim_begin(0), scale.dim_end(0))) {}
+    typename MatT::index_type index() { return *both.i1; }
+    bool eof() { return both.eof(); }
+    void operator++() { ++both; }
+    typename MatT::val_type scale_val() { return both.i2.val(); }
+    typename MultXiter<MatT>::sub_xiter_type sub_xiter() { return both.i1.sub_xiter(); }
+};
+
+template <class MatT, class ScaleT>
+std::unique_ptr<MultXiter<MatT>> new_mult_xiter(MatT const &A, ScaleT const *scale) {
+    typedef std::unique_ptr<MultXiter<MatT>> ptr;
+    return scale ? ptr(new ScaledMultXiter<MatT, ScaleT>(A, *scale)) : ptr(new SimpleMultXiter<MatT>(A));
+}
+
 // ret = C * diag(scalei) * op(A) * diag(scalej) * op(B) * diag(scalek)
 template <class ScaleIT, class MatAT, class ScaleJT, class MatBT, class ScaleKT, class AccumulatorT>
 void multiply(AccumulatorT &ret, double C, ScaleIT const *scalei, MatAT const &A, char transpose_A,

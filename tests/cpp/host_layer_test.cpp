@@ -150,7 +150,45 @@ static void test_multiply() {
     CHECK(total.val == 9.);
 }
 
+static void test_mult_xiters() {
+    // multiply_sparse.hpp:39-111: rows of a consolidated matrix, alone and joined with a scale vector
+    Mat b({20, 10});
+    b.add({6, 4}, 10.); b.add({1, 3}, 17.); b.add({2, 4}, 17.); b.add({1, 0}, 15.); b.add({9, 9}, 1.);
+    b.consolidate({0, 1});
+    std::vector<int> rows, cols;
+    std::vector<double> sv, vals;
+    auto plain(new_mult_xiter(b, (Vec *)0));
+    for (; !plain->eof(); ++*plain) {
+        rows.push_back(plain->index());
+        sv.push_back(plain->scale_val());
+        for (auto jj(plain->sub_xiter()); !jj.eof(); ++jj) { cols.push_back(*jj); vals.push_back(jj.val()); }
+    }
+    CHECK(same(rows, {1, 2, 6, 9}) && same(sv, {1., 1., 1., 1.}));
+    CHECK(same(cols, {0, 3, 4, 4, 9}) && same(vals, {15., 17., 17., 10., 1.}));
+    Vec s({20});
+    s.add({0}, 7.); s.add({2}, 3.); s.add({5}, 4.); s.add({9}, .5); s.add({19}, 2.);
+    rows.clear(); sv.clear(); cols.clear();
+    auto scaled(new_mult_xiter(b, &s));
+    for (; !scaled->eof(); ++*scaled) {
+        rows.push_back(scaled->index());
+        sv.push_back(scaled->scale_val());
+        auto jj(scaled->sub_xiter());
+        cols.push_back(*jj);
+    }
+    CHECK(same(rows, {2, 9}) && same(sv, {3., .5}) && same(cols, {4, 9}));
+    // column-major operand: the walker follows the leading sorted dimension (columns), entries report rows
+    b.consolidate({1, 0});
+    rows.clear(); cols.clear();
+    SimpleMultXiter<Mat> bycol(b);
+    for (; !bycol.eof(); ++bycol) {
+        cols.push_back(bycol.index());
+        for (auto jj(bycol.sub_xiter()); !jj.eof(); ++jj) rows.push_back(*jj);
+    }
+    CHECK(same(cols, {0, 3, 4, 9}) && same(rows, {1, 1, 2, 6, 9}));
+}
+
 int main() {
+    test_mult_xiters();
     test_consolidate();
     test_permutation_and_rows();
     test_errors();
