@@ -48,8 +48,9 @@ def peaks():
 class ClockSampler:
     """SM clock and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md's clocks line).
 
-    NVML is polled from a thread every 2 ms (a timed region can be as short as 50 ms at 8 GPUs, where a
-    100 ms `nvidia-smi -lms` loop returns nothing); `nvidia-smi` stays as the fallback when NVML cannot be opened."""
+    Two sources run side by side: NVML polled from a thread every 2 ms (a timed region can be as short as 50 ms at
+    8 GPUs, where a 100 ms `nvidia-smi -lms` loop returns nothing) and the recipe's `nvidia-smi` loop.  The NVML
+    samples are reported when there are any, the nvidia-smi ones otherwise."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -60,6 +61,12 @@ class ClockSampler:
         self.p = self.f = self.thread = None
         self.sm, self.reasons, self.smax = [], set(), None
         self.halt = threading.Event()
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(uuid or gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -81,59 +88,53 @@ class ClockSampler:
                         for b, nm in bits.items():
                             if r & b:
                                 self.reasons.add(nm)
-                    except nv.NVMLError:
+                    except Exception:  # noqa: BLE001 -- a failed query is a missing sample
                         pass
                     self.halt.wait(0.002)
 
-            self.source = "nvml, 2 ms period"
             self.thread = threading.Thread(target=poll, daemon=True)
             self.thread.start()
-            return
-        except Exception:  # noqa: BLE001 -- no NVML: fall back to the nvidia-smi loop
+        except Exception:  # noqa: BLE001 -- no NVML: the nvidia-smi loop is the only source
             self.thread = None
-        self.source = "nvidia-smi -lms 100"
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+
+    def _smi_samples(self):
+        sm, smax, reasons = [], [], set()
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        if self.f is not None:
+            self.f.flush()
+            self.f.seek(0)
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); smax.append(float(c[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(self.NAMES, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            self.f.close()
+            os.unlink(self.f.name)
+        return sm, (max(smax) if smax else None), reasons
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
         if self.thread is not None:
             self.halt.set()
             self.thread.join(timeout=2)
-            if self.sm:
-                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.smax, reasons=sorted(self.reasons),
-                           samples=len(self.sm))
-            return out
-        if self.p is None:
-            if self.f is not None:
-                os.unlink(self.f.name)
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); smax.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(self.NAMES, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        sm, smax, reasons = self._smi_samples()
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.smax, reasons=sorted(self.reasons | reasons),
+                       samples=len(self.sm), source="nvml, 2 ms period")
+        elif sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(smax), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi -lms 100")
         return out
 
 

@@ -235,6 +235,62 @@ static void test_accumulators_and_host_loops() {
     CHECK(sorted.size() == 2 && !sorted.edit_mode);
 }
 
+// A consolidated matrix whose row-start list is supplied by the test instead of by the device (the list is a lazily
+// filled cache, VectorCooArray.hpp:323-335): lets the row walkers run without a GPU.
+struct PresetMat : Mat {
+    PresetMat(std::array<size_t, 2> const &shape) : Mat(shape) {}
+    void preset(std::array<int, 2> const &order, std::vector<size_t> const &starts) {
+        set_sorted(order);
+        _dim_beginnings = starts;
+        dim_beginnings_set = true;
+    }
+};
+
+static void test_mult_xiters() {
+    // multiply_sparse.hpp:39-111
+    PresetMat b({20, 10});
+    b.add({1, 0}, 15.); b.add({1, 3}, 17.); b.add({2, 4}, 17.); b.add({6, 4}, 10.); b.add({9, 9}, 1.);
+    b.preset({0, 1}, {0, 2, 3, 4, 5});
+    Mat const &bm(b);
+    std::vector<int> rows, cols;
+    std::vector<double> sv, vals;
+    auto plain(new_mult_xiter(bm, (Vec *)0));
+    for (; !plain->eof(); ++*plain) {
+        rows.push_back(plain->index());
+        sv.push_back(plain->scale_val());
+        for (auto jj(plain->sub_xiter()); !jj.eof(); ++jj) { cols.push_back(*jj); vals.push_back(jj.val()); }
+    }
+    CHECK(same(rows, {1, 2, 6, 9}) && same(sv, {1., 1., 1., 1.}));
+    CHECK(same(cols, {0, 3, 4, 4, 9}) && same(vals, {15., 17., 17., 10., 1.}));
+    // with a scale vector: only rows the vector has an entry for, each with its scale value
+    Vec s({20});
+    s.add({0}, 7.); s.add({2}, 3.); s.add({5}, 4.); s.add({9}, .5); s.add({19}, 2.);
+    rows.clear(); sv.clear(); cols.clear();
+    auto scaled(new_mult_xiter(bm, &s));
+    for (; !scaled->eof(); ++*scaled) {
+        rows.push_back(scaled->index());
+        sv.push_back(scaled->scale_val());
+        auto jj(scaled->sub_xiter());
+        cols.push_back(*jj);
+    }
+    CHECK(same(rows, {2, 9}) && same(sv, {3., .5}) && same(cols, {4, 9}));
+    Vec miss({20});
+    miss.add({0}, 1.); miss.add({3}, 1.); miss.add({19}, 1.);
+    ScaledMultXiter<Mat, Vec> none(bm, miss);
+    CHECK(none.eof());
+    // a column-major operand is walked by column; the entries of a column report their rows
+    PresetMat c({20, 10});
+    c.add({1, 0}, 15.); c.add({1, 3}, 17.); c.add({2, 4}, 17.); c.add({6, 4}, 10.); c.add({9, 9}, 1.);
+    c.preset({1, 0}, {0, 1, 2, 4, 5});
+    rows.clear(); cols.clear();
+    SimpleMultXiter<Mat> bycol(c);
+    for (; !bycol.eof(); ++bycol) {
+        cols.push_back(bycol.index());
+        for (auto jj(bycol.sub_xiter()); !jj.eof(); ++jj) rows.push_back(*jj);
+    }
+    CHECK(same(cols, {0, 3, 4, 9}) && same(rows, {1, 1, 2, 6, 9}));
+}
+
 static int hook_calls = 0;
 static char hook_text[256];
 static void counting_hook(int, const char *fmt, ...) {
@@ -292,6 +348,7 @@ int main() {
     test_joins();
     test_predicates_and_constants();
     test_accumulators_and_host_loops();
+    test_mult_xiters();
     test_error_convention();
     std::printf("host_only_test: %d failure(s)\n", failures);
     return failures ? 1 : 0;
