@@ -19,6 +19,7 @@
 #include "gen.cuh"
 #include "radix_sort.cuh"
 #include "reduce_by_key.cuh"
+#include "reduce_segsort.cuh"
 #include "scan.cuh"
 #include "spgemm.cuh"
 #include "dense_ops.cuh"
@@ -223,6 +224,7 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaFuncSetAttribute(k_radix_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_reduce_segsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
     const char *s = getenv("SPB_MERGE_MAX_PRODUCTS");
     c->merge_max_products = s ? (u32)strtoul(s, nullptr, 10) : 1024u;
     s = getenv("SPB_ESC_CHUNK");
@@ -516,69 +518,91 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     int t_p0 = t0;
     CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs, &tm, &t_p0, shift0));
     const int t_passes = tm.mark();
-    if (seg) {
-        // rows are grouped (insertion order inside): order every row by column
-        u64 *ko = (ks == kA) ? kB : kA;
-        double *vo = (vs == vA) ? vB : vA;
-        const u32 stiles = (u32)div_up(n, SG_TILE);
-        ++ctx->launches;
-        if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
-        else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
-        CK(cudaGetLastError());
-        u32 hc[6];
-        CK(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        const u32 n_kept = hc[0], h_long = hc[5];
-        if (h_long && !hc[1]) {
-            // rows longer than SEG_MAX exist: their entries (left in place above) are pulled out in order, sorted by the
-            // full key with the radix passes, and put back -- the pulled-out sequence is ascending in the row, so sorted
-            // position i goes back where gathered position i came from
-            unsigned char *flags;
-            u64 *slot, *lk, *lk2, *lks;
-            double *lv, *lv2, *lvs;
-            u32 *lhist, *lcount;
-            CKR(ws.get(&flags, n_kept));
-            CKR(ws.get(&slot, (u64)n_kept + 1));
-            CK(cudaMemsetAsync(counters + 5, 0, sizeof(u32), ctx->stream));
+    // SPB_FUSED_REDUCE=1: the in-row column sort runs inside the reduce pass (k_reduce_segsort) instead of as a pass of
+    // its own.  It has no path for rows longer than SEG_MAX: it counts their entries, and if there are any its output
+    // is discarded and the separate kernels run after all (second trip of the loop below).
+    const char *fused_env = getenv("SPB_FUSED_REDUCE");
+    bool fused = seg && seg_walk && fused_env && atoi(fused_env) != 0;
+    u32 h[6];
+    int t1 = t_passes, t2 = t_passes;
+    u64 *const ks_rows = ks;      // grouped by row, insertion order inside: what both variants start from
+    double *const vs_rows = vs;
+    for (int attempt = 0;; ++attempt) {
+        ks = ks_rows; vs = vs_rows;
+        if (seg && !fused) {
+            // rows are grouped (insertion order inside): order every row by column
+            u64 *ko = (ks == kA) ? kB : kA;
+            double *vo = (vs == vA) ? vB : vA;
+            const u32 stiles = (u32)div_up(n, SG_TILE);
             ++ctx->launches;
-            if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
-            else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
-            CKR((exclusive_scan<unsigned char, u64>(ctx, ws, flags, slot, n_kept)));
-            CKR(ws.get(&lk, h_long)); CKR(ws.get(&lv, h_long)); CKR(ws.get(&lk2, h_long)); CKR(ws.get(&lv2, h_long));
-            CKR(ws.zeroed(&lhist, (u64)passes_full * RS_RADIX));
-            CKR(ws.zeroed(&lcount, 8));
-            CK(cudaMemcpyAsync(lcount, &h_long, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-            ++ctx->launches, k_gather_flagged<<<grid_for(n_kept, 256, sgrid * 4), 256, 0, ctx->stream>>>(ks, vs, flags, slot, n_kept, lk, lv);
-            ++ctx->launches, k_keys_hist<<<grid_for(h_long, 512, sgrid), 512, 0, ctx->stream>>>(lk, h_long, passes_full, lhist);
-            ++ctx->launches, k_bucket_starts<<<passes_full, RS_RADIX, 0, ctx->stream>>>(lhist);
-            CKR(run_radix_passes(ctx, ws, 1, passes_full, h_long, lcount, lhist, lk, lv, lk2, lv2, nullptr, &lks, &lvs, nullptr, nullptr));
-            ++ctx->launches, k_scatter_flagged<<<grid_for(n_kept, 256, sgrid * 4), 256, 0, ctx->stream>>>(lks, lvs, flags, slot, n_kept, ko, vo);
+            if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+            else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
             CK(cudaGetLastError());
+            u32 hc[6];
+            CK(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const u32 n_kept = hc[0], h_long = hc[5];
+            if (h_long && !hc[1]) {
+                // rows longer than SEG_MAX exist: their entries (left in place above) are pulled out in order, sorted by the
+                // full key with the radix passes, and put back -- the pulled-out sequence is ascending in the row, so sorted
+                // position i goes back where gathered position i came from
+                unsigned char *flags;
+                u64 *slot, *lk, *lk2, *lks;
+                double *lv, *lv2, *lvs;
+                u32 *lhist, *lcount;
+                CKR(ws.get(&flags, n_kept));
+                CKR(ws.get(&slot, (u64)n_kept + 1));
+                CK(cudaMemsetAsync(counters + 5, 0, sizeof(u32), ctx->stream));
+                ++ctx->launches;
+                if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+                else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+                CKR((exclusive_scan<unsigned char, u64>(ctx, ws, flags, slot, n_kept)));
+                CKR(ws.get(&lk, h_long)); CKR(ws.get(&lv, h_long)); CKR(ws.get(&lk2, h_long)); CKR(ws.get(&lv2, h_long));
+                CKR(ws.zeroed(&lhist, (u64)passes_full * RS_RADIX));
+                CKR(ws.zeroed(&lcount, 8));
+                CK(cudaMemcpyAsync(lcount, &h_long, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+                ++ctx->launches, k_gather_flagged<<<grid_for(n_kept, 256, sgrid * 4), 256, 0, ctx->stream>>>(ks, vs, flags, slot, n_kept, lk, lv);
+                ++ctx->launches, k_keys_hist<<<grid_for(h_long, 512, sgrid), 512, 0, ctx->stream>>>(lk, h_long, passes_full, lhist);
+                ++ctx->launches, k_bucket_starts<<<passes_full, RS_RADIX, 0, ctx->stream>>>(lhist);
+                CKR(run_radix_passes(ctx, ws, 1, passes_full, h_long, lcount, lhist, lk, lv, lk2, lv2, nullptr, &lks, &lvs, nullptr, nullptr));
+                ++ctx->launches, k_scatter_flagged<<<grid_for(n_kept, 256, sgrid * 4), 256, 0, ctx->stream>>>(lks, lvs, flags, slot, n_kept, ko, vo);
+                CK(cudaGetLastError());
+            }
+            ks = ko; vs = vo;
         }
-        ks = ko; vs = vo;
+        t1 = tm.mark();
+
+        const u32 rtiles = (u32)div_up(n, RK_TILE);
+        ReduceArgs ra;
+        memset(&ra, 0, sizeof ra);
+        ra.keys = ks; ra.vals = vs; ra.n_ptr = counters; ra.bits_lo = in.bits_lo; ra.policy = job.policy;
+        ra.out_hi = out_hi; ra.out_lo = out_lo; ra.out_val = out_val; ra.out_count = counters + 2;
+        CKR(ws.zeroed(&ra.state, rtiles));
+        CKR(ws.zeroed(&ra.ticket, 1));
+        ra.long_cap = n / RK_LONG_RUN + 1;
+        CKR(ws.get(&ra.long_list, 2ull * ra.long_cap));
+        ra.long_count = counters + 3;
+        ra.row_start = row_start; ra.row_id = row_id; ra.row_count = counters + 4;
+        if (fused) {
+            ++ctx->launches, k_reduce_segsort<<<rtiles, RK_THREADS, sizeof(RfSmem), ctx->stream>>>(ra, counters + 5);
+        } else {
+            ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
+            if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
+                ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
+        }
+        CK(cudaGetLastError());
+        t2 = tm.mark();
+
+        CK(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (fused && h[5] && !h[1] && attempt == 0) {
+            // rows longer than SEG_MAX: start over from the row-grouped array with the separate kernels
+            fused = false;
+            CK(cudaMemsetAsync(counters + 2, 0, 4 * sizeof(u32), ctx->stream));  // out count, long runs, rows, long-row entries
+            continue;
+        }
+        break;
     }
-    const int t1 = tm.mark();
-
-    const u32 rtiles = (u32)div_up(n, RK_TILE);
-    ReduceArgs ra;
-    memset(&ra, 0, sizeof ra);
-    ra.keys = ks; ra.vals = vs; ra.n_ptr = counters; ra.bits_lo = in.bits_lo; ra.policy = job.policy;
-    ra.out_hi = out_hi; ra.out_lo = out_lo; ra.out_val = out_val; ra.out_count = counters + 2;
-    CKR(ws.zeroed(&ra.state, rtiles));
-    CKR(ws.zeroed(&ra.ticket, 1));
-    ra.long_cap = n / RK_LONG_RUN + 1;
-    CKR(ws.get(&ra.long_list, 2ull * ra.long_cap));
-    ra.long_count = counters + 3;
-    ra.row_start = row_start; ra.row_id = row_id; ra.row_count = counters + 4;
-    ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
-    if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
-        ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
-    CK(cudaGetLastError());
-    const int t2 = tm.mark();
-
-    u32 h[5];
-    CK(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     if (h[1]) return spb_fail(SPB_ERR_ARG, "Sparse index out of bounds (an index is negative or >= its extent)");
     *h_kept = h[0];
     *h_out = h[2];

@@ -2,6 +2,8 @@
 the reference-generated fixtures, the CPU oracle on fresh seeded inputs, and size-independent
 properties at larger sizes.  Index structure must be bit-exact; values are bit-exact too because
 the duplicate fold keeps the reference's left-to-right order (tolerance stated where it is not)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -186,8 +188,8 @@ def test_medium_scale_against_oracle(ctx, orc):
     A.free()
 
 
-@pytest.mark.parametrize("mode,walk", [("1", "1"), ("1", "0"), ("0", "0")])
-def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk):
+@pytest.mark.parametrize("mode,walk,fused", [("1", "1", "0"), ("1", "0", "0"), ("0", "0", "0"), ("1", "1", "1")])
+def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused):
     """The sort's second organisation -- radix passes over the row part of the key only, then every row ordered by
     column (k_segment_sort), rows longer than 64 entries re-sorted by their full key -- forced on (and off) for shapes
     with a wide column part: short rows, rows around the 64-entry limit, hub rows of thousands of entries next to
@@ -196,13 +198,26 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk):
     from _gpu import up, down
     monkeypatch.setenv("SPB_SEGMENT_SORT", mode)
     monkeypatch.setenv("SPB_SEGMENT_WALK", walk)   # which of the two in-row kernels (neighbour walk / row table)
+    # fused = "1": the in-row sort runs inside the reduce pass (k_reduce_segsort); the cases with hub rows make it
+    # give up and fall back to the separate kernels
+    monkeypatch.setenv("SPB_FUSED_REDUCE", fused)
+    if fused == "1" and not os.environ.get("SPB_TEST_EXPERIMENTAL"):
+        pytest.skip("k_reduce_segsort is experimental (not yet run on a GPU): set SPB_TEST_EXPERIMENTAL=1")
     rng = np.random.default_rng(11)
     cases = []
     for s, (shape, n, hubs) in enumerate([((300, 1 << 20), 5000, 0), ((3, 1 << 20), 4000, 0), ((2000, 1 << 18), 60000, 3),
                                           ((1 << 16, 1 << 16), 200000, 2), ((70, 1 << 17), 70 * 64, 0), ((1 << 20, 300), 30000, 1),
-                                          ((5, 100000), 4099, 0), ((40000, 1 << 16), 1, 0)]):
+                                          ((5, 100000), 4099, 0), ((40000, 1 << 16), 1, 0),
+                                          # no row over the limit (the fused kernel keeps its result): heavy duplicates,
+                                          # very short rows, every row exactly at the 64-entry limit
+                                          ((4000, 1 << 20), 50000, 0), ((1 << 17, 1 << 17), 300000, 0), ((1001, 1 << 16), 64007, 0)]):
         i = rng.integers(0, shape[0], n)
         k = rng.integers(0, min(shape[1], 5000 if s % 2 else shape[1]), n)     # odd cases: many duplicate tuples
+        if s == 8:
+            k = rng.integers(0, 6, n)                                           # runs of duplicates across tile ends
+        if s == 10:
+            i = np.concatenate([np.zeros(7, dtype=np.int64), np.repeat(np.arange(1, 1001), 64)])
+            k = rng.integers(0, 40, n)
         for h in range(hubs):                                                   # hub rows: thousands of entries
             m = rng.integers(1000, 9000)
             i[h * 9000:h * 9000 + m] = 17 + 5 * h
