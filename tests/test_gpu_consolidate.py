@@ -2,8 +2,6 @@
 the reference-generated fixtures, the CPU oracle on fresh seeded inputs, and size-independent
 properties at larger sizes.  Index structure must be bit-exact; values are bit-exact too because
 the duplicate fold keeps the reference's left-to-right order (tolerance stated where it is not)."""
-import os
-
 import numpy as np
 import pytest
 
@@ -201,8 +199,6 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused)
     # fused = "1": the in-row sort runs inside the reduce pass (k_reduce_segsort); the cases with hub rows make it
     # give up and fall back to the separate kernels
     monkeypatch.setenv("SPB_FUSED_REDUCE", fused)
-    if fused == "1" and not os.environ.get("SPB_TEST_EXPERIMENTAL"):
-        pytest.skip("k_reduce_segsort is experimental (not yet run on a GPU): set SPB_TEST_EXPERIMENTAL=1")
     rng = np.random.default_rng(11)
     cases = []
     for s, (shape, n, hubs) in enumerate([((300, 1 << 20), 5000, 0), ((3, 1 << 20), 4000, 0), ((2000, 1 << 18), 60000, 3),
