@@ -18,6 +18,7 @@
 #include "csr.cuh"
 #include "gen.cuh"
 #include "radix_sort.cuh"
+#include "radix_sort9.cuh"
 #include "reduce_by_key.cuh"
 #include "reduce_segsort.cuh"
 #include "scan.cuh"
@@ -225,6 +226,8 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     CK(cudaFuncSetAttribute(k_radix_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_reduce_segsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
+    CK(cudaFuncSetAttribute(k_radix_pass9<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_pass9<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
     const char *s = getenv("SPB_MERGE_MAX_PRODUCTS");
     c->merge_max_products = s ? (u32)strtoul(s, nullptr, 10) : 1024u;
     s = getenv("SPB_ESC_CHUNK");
@@ -425,32 +428,39 @@ static int exclusive_scan(spb_ctx *ctx, Scratch &ws, const InT *in, OutT *out, u
 
 static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passes, u32 n_cap, const u32 *n_ptr,
                             u32 *hist, u64 *kA, double *vA, u64 *kB, double *vB, const SortInput *in0,
-                            u64 **keys_sorted, double **vals_sorted, Timer *tm, int *mark_after_first, int shift0 = 0) {
+                            u64 **keys_sorted, double **vals_sorted, Timer *tm, int *mark_after_first, int shift0 = 0,
+                            int digit_bits = RS_RADIX_BITS) {
     const u32 tiles = (u32)div_up(n_cap ? n_cap : 1, RS_TILE);
+    const bool nine = digit_bits == R9_BITS;   // k_radix_pass9: 512 buckets per pass (hist and look-back rows are 512 wide)
+    const u64 radix = nine ? R9_RADIX : RS_RADIX;
     u32 *lookback, *tickets;
-    CKR(ws.zeroed(&lookback, (u64)passes * tiles * RS_RADIX));
+    CKR(ws.zeroed(&lookback, (u64)passes * tiles * radix));
     CKR(ws.zeroed(&tickets, (u64)passes));
     u64 *kin = kA, *kout = kB;
     double *vin = vA, *vout = vB;
     for (int p = 0; p < passes; ++p) {
         PassArgs a;
         a.n_ptr = n_ptr;
-        a.bucket_start = hist + (u64)p * RS_RADIX;
-        a.lookback = lookback + (u64)p * tiles * RS_RADIX;
+        a.bucket_start = hist + (u64)p * radix;
+        a.lookback = lookback + (u64)p * tiles * radix;
         a.ticket = tickets + p;
-        a.shift = shift0 + p * RS_RADIX_BITS;
+        a.shift = shift0 + p * digit_bits;
         a.rank_mode = getenv("SPB_RANK_MODE") ? atoi(getenv("SPB_RANK_MODE")) : 0;
         if (p == 0 && first_pass == 0) {
             // pass 0 reads the caller's arrays and writes buffer A
             a.keys_in = nullptr; a.vals_in = nullptr; a.keys_out = kA; a.vals_out = vA;
-            ++ctx->launches, k_radix_pass<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            ++ctx->launches;
+            if (nine) k_radix_pass9<true><<<tiles, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            else k_radix_pass<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
             kin = kA; vin = vA; kout = kB; vout = vB;
             if (tm) *mark_after_first = tm->mark();
         } else {
             a.keys_in = kin; a.vals_in = vin; a.keys_out = kout; a.vals_out = vout;
             SortInput dummy;
             memset(&dummy, 0, sizeof dummy);
-            ++ctx->launches, k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            ++ctx->launches;
+            if (nine) k_radix_pass9<false><<<tiles, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            else k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
             u64 *tk = kin; kin = kout; kout = tk;
             double *tv = vin; vin = vout; vout = tv;
         }
@@ -486,7 +496,15 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     const bool seg_walk = walk_env ? atoi(walk_env) != 0 : (double)n <= 6.0 * (double)in.extent_hi;  // very short rows: neighbour walk
     const bool seg = in.bits_lo > 0 && passes_full - passes_row >= 2 &&
                      (seg_env ? atoi(seg_env) != 0 : seg_short);
-    const int passes = seg ? passes_row : passes_full;
+    // SPB_RADIX9=1 (experimental): 9-bit digits (k_radix_pass9) when that covers the same bits in fewer passes --
+    // a 27-bit row part takes three passes instead of four
+    const int cover_bits = seg ? job.bits_hi : key_bits;
+    const char *r9_env = getenv("SPB_RADIX9");
+    const int passes8 = seg ? passes_row : passes_full;
+    const int passes9 = cover_bits > 0 ? (cover_bits + R9_BITS - 1) / R9_BITS : 1;
+    const bool nine = r9_env && atoi(r9_env) != 0 && passes9 < passes8;
+    const int digit_bits = nine ? R9_BITS : RS_RADIX_BITS;
+    const int passes = nine ? passes9 : passes8;
     const int shift0 = seg ? in.bits_lo : 0;
     if (n > (1u << 30)) return spb_fail(SPB_ERR_TOO_LARGE, "%u entries exceed the 2^30 per-sort limit", n);
     Scratch ws(ctx);
@@ -495,7 +513,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
 
     u32 *hist, *counters;  // counters: [0] kept, [1] out-of-bounds flag, [2] out count, [3] long runs
     u64 *first_kept;
-    CKR(ws.zeroed(&hist, (u64)passes * RS_RADIX));
+    CKR(ws.zeroed(&hist, (u64)passes * (nine ? R9_RADIX : RS_RADIX)));
     CKR(ws.zeroed(&counters, 8));
     CKR(ws.get(&first_kept, 2));
     CK(cudaMemsetAsync(first_kept, 0xFF, 2 * sizeof(u64), ctx->stream));
@@ -506,8 +524,13 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         ++ctx->launches, k_first_kept_key<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
         ++ctx->launches, k_first_kept_pos<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
     }
-    ++ctx->launches, k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
-    ++ctx->launches, k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
+    if (nine) {
+        ++ctx->launches, k_sort_hist9<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
+        ++ctx->launches, k_bucket_starts9<<<passes, R9_RADIX / 2, 0, ctx->stream>>>(hist);
+    } else {
+        ++ctx->launches, k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
+        ++ctx->launches, k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
+    }
     CK(cudaGetLastError());
 
     u64 *kA, *kB = nullptr, *ks;
@@ -516,7 +539,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     CKR(ws.get(&vA, n));
     if (passes > 1 || seg) { CKR(ws.get(&kB, n)); CKR(ws.get(&vB, n)); }
     int t_p0 = t0;
-    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs, &tm, &t_p0, shift0));
+    CKR(run_radix_passes(ctx, ws, 0, passes, n, counters, hist, kA, vA, kB, vB, &in0, &ks, &vs, &tm, &t_p0, shift0, digit_bits));
     const int t_passes = tm.mark();
     // SPB_FUSED_REDUCE=1: the in-row column sort runs inside the reduce pass (k_reduce_segsort) instead of as a pass of
     // its own.  It has no path for rows longer than SEG_MAX: it counts their entries, and if there are any its output

@@ -235,3 +235,38 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused)
                     want = orc.consolidate(a, so, pol, zn)
                     assert _cases.same_coo(got, want), (s, so, pol)
                     assert np.array_equal(db, orc.dim_beginnings(want)), (s, so, pol)
+
+
+@pytest.mark.parametrize("seg", ["1", "0"])
+def test_nine_bit_digit_passes(orc, monkeypatch, seg):
+    """SPB_RADIX9=1: 9-bit digits (k_radix_pass9) wherever they cover the key -- or, with the in-row column sort, its row
+    part -- in fewer passes than 8-bit ones: 17-bit and 27-bit row parts, 34- and 54-bit keys; all policies, zero_nan, both
+    sort orders, duplicates.  Same answers as the oracle, bit for bit."""
+    import os
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    if not os.environ.get("SPB_TEST_EXPERIMENTAL"):
+        pytest.skip("k_radix_pass9 is experimental (not yet run on a GPU): set SPB_TEST_EXPERIMENTAL=1")
+    monkeypatch.setenv("SPB_RADIX9", "1")
+    monkeypatch.setenv("SPB_SEGMENT_SORT", seg)
+    rng = np.random.default_rng(99)
+    cases = []
+    for s, (shape, n, kmax) in enumerate([((1 << 17, 1 << 17), 150000, None), ((100_000_000, 100_000_000), 120000, None),
+                                          ((100_000_000, 100_000_000), 50000, 40), ((300, 1 << 20), 9000, None),
+                                          ((1 << 26, 1 << 26), 4097, None), ((1 << 17, 1 << 17), 1, None)]):
+        i = rng.integers(0, shape[0] if s != 2 else 3000, n)
+        k = rng.integers(0, kmax or shape[1], n)
+        cases.append(O.Coo(shape, [i, k], _cases._values(rng, n, ["pos", "int", "mixed"][s % 3])))
+    with sp.Context(0) as c2:
+        for s, a in enumerate(cases):
+            for so in ((0, 1), (1, 0)):
+                for pol in _cases.POLICIES:
+                    zn = (s + pol) % 2
+                    A = up(c2, a)
+                    R, st = sp.consolidate(c2, A, so, pol, zn, stats=True)
+                    got = down(R)
+                    db = R.dim_beginnings()
+                    A.free(); R.free()
+                    want = orc.consolidate(a, so, pol, zn)
+                    assert _cases.same_coo(got, want), (s, so, pol, st.passes)
+                    assert np.array_equal(db, orc.dim_beginnings(want)), (s, so, pol)
