@@ -468,7 +468,8 @@ def run_ours(args):
                              "timeline_ms": dict(zip(["consolidate_b", "replicate_b_launch", "consolidate_a", "replicate_b_wait",
                                                       "spgemm_incl_prepare"],
                                                      [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)]))},
-            "roofline": {"bound": "hbm", "kernel": "k_radix_pass<false> (one 8-bit LSD scatter pass, key+value)",
+            "roofline": {"bound": "hbm", "kernel": ("k_radix_pass9<false> (one 9-bit LSD scatter pass, key+value)" if sa.digit_bits == 9 else
+                                                    "k_radix_pass<false> (one 8-bit LSD scatter pass, key+value)"),
                          "achieved": pass_gbs, "peak": hbm, "unit": "GB/s", "frac": pass_gbs / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
                          "peak_source": peak_src},

@@ -93,9 +93,10 @@ int spb_coo_free(spb_ctx *ctx, spb_coo *a);
  * array's own dimension order.  `out` is a new array flagged sorted by sort_order. */
 typedef struct {
     uint64_t n_in, n_kept, n_out; /* entries in, after the input-zero drop, after merging */
-    int key_bits, passes;         /* significant key bits, 8-bit radix passes run */
+    int key_bits, passes;         /* significant key bits, radix passes run */
     float ms_total, ms_sort, ms_reduce;
     float ms_pass; /* mean duration of one radix scatter pass (passes after the first), 0 if only one */
+    int digit_bits; /* width of a radix digit: 8, or 9 where that saves a pass */
 } spb_consolidate_stats;
 int spb_consolidate(spb_ctx *ctx, const spb_coo *in, const int *sort_order, int policy, int zero_nan,
                     spb_coo **out, spb_consolidate_stats *stats /* may be NULL */);

@@ -19,7 +19,7 @@ class ConsolidateStats(C.Structure):
     _fields_ = [("n_in", C.c_uint64), ("n_kept", C.c_uint64), ("n_out", C.c_uint64),
                 ("key_bits", C.c_int), ("passes", C.c_int),
                 ("ms_total", C.c_float), ("ms_sort", C.c_float), ("ms_reduce", C.c_float),
-                ("ms_pass", C.c_float)]
+                ("ms_pass", C.c_float), ("digit_bits", C.c_int)]
 
 
 class MMStats(C.Structure):

@@ -496,13 +496,16 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     const bool seg_walk = walk_env ? atoi(walk_env) != 0 : (double)n <= 6.0 * (double)in.extent_hi;  // very short rows: neighbour walk
     const bool seg = in.bits_lo > 0 && passes_full - passes_row >= 2 &&
                      (seg_env ? atoi(seg_env) != 0 : seg_short);
-    // SPB_RADIX9=1 (experimental): 9-bit digits (k_radix_pass9) when that covers the same bits in fewer passes --
-    // a 27-bit row part takes three passes instead of four
+    // 9-bit digits (k_radix_pass9) when they cover the same bits in fewer passes -- a 27-bit row part takes three
+    // passes instead of four (SPB_RADIX9)
     const int cover_bits = seg ? job.bits_hi : key_bits;
     const char *r9_env = getenv("SPB_RADIX9");
     const int passes8 = seg ? passes_row : passes_full;
     const int passes9 = cover_bits > 0 ? (cover_bits + R9_BITS - 1) / R9_BITS : 1;
-    const bool nine = r9_env && atoi(r9_env) != 0 && passes9 < passes8;
+    // default: on where it was measured -- the row passes of a large array (the heuristic's own choice of the row-pass
+    // organisation, which needs 2^23 entries); "1" = wherever it saves a pass, "0" = never
+    const bool nine_wanted = r9_env ? atoi(r9_env) != 0 : (seg && !seg_env);
+    const bool nine = nine_wanted && passes9 < passes8;
     const int digit_bits = nine ? R9_BITS : RS_RADIX_BITS;
     const int passes = nine ? passes9 : passes8;
     const int shift0 = seg ? in.bits_lo : 0;
@@ -632,7 +635,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     if (h_rows) *h_rows = h[4];
     if (st) {
         st->n_in = n; st->n_kept = h[0]; st->n_out = h[2];
-        st->key_bits = key_bits; st->passes = passes;
+        st->key_bits = key_bits; st->passes = passes; st->digit_bits = digit_bits;
         st->ms_sort = tm.ms(t0, t1); st->ms_reduce = tm.ms(t1, t2); st->ms_total = tm.ms(t0, t2);
         st->ms_pass = passes > 1 ? tm.ms(t_p0, t_passes) / (float)(passes - 1) : 0.f;
     }

@@ -246,7 +246,8 @@ def test_nine_bit_digit_passes(orc, monkeypatch, seg):
     import spsparse_b200 as sp
     from _gpu import up, down
     if not os.environ.get("SPB_TEST_EXPERIMENTAL"):
-        pytest.skip("k_radix_pass9 is experimental (not yet run on a GPU): set SPB_TEST_EXPERIMENTAL=1")
+        pytest.skip("SPB_RADIX9=1 on small arrays has not been run on a GPU yet (the default only uses 9-bit digits for the "
+                    "row passes of arrays of 2^23 entries or more, covered by test_config5_full_size): set SPB_TEST_EXPERIMENTAL=1")
     monkeypatch.setenv("SPB_RADIX9", "1")
     monkeypatch.setenv("SPB_SEGMENT_SORT", seg)
     rng = np.random.default_rng(99)
