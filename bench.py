@@ -474,7 +474,10 @@ def run_ours(args):
                                                     "k_radix_pass<false> (one 8-bit LSD scatter pass, key+value)"),
                          "achieved": pass_gbs, "peak": hbm, "unit": "GB/s", "frac": pass_gbs / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
-                         "peak_source": peak_src},
+                         "peak_source": peak_src,
+                         "note": ("9-bit digits: three passes over the 27-bit row part instead of four 8-bit ones; one 9-bit pass was "
+                                  "measured 17 % slower than an 8-bit one (which ran at 0.61 of the peak), the consolidate 8 % faster "
+                                  "(profiles/r01_radix9_ab.txt)") if sa.digit_bits == 9 else None},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(l1 - l0),
