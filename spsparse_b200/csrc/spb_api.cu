@@ -217,8 +217,17 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
                         cudaGetErrorString(e));
     if (device < 0 || device >= count) return spb_fail(SPB_ERR_ARG, "device %d out of range (%d devices)", device, count);
     CK(cudaSetDevice(device));
-    spb_ctx *c = new spb_ctx();
+    struct Undo {  // a failing set-up step below must not leak the context or its stream
+        spb_ctx *c;
+        ~Undo() {
+            if (!c) return;
+            if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+            delete c;
+        }
+    } undo{new spb_ctx()};
+    spb_ctx *c = undo.c;
     c->device = device;
+    c->stream = nullptr;
     c->own_stream = (cuda_stream == nullptr);
     if (c->own_stream) CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     else c->stream = (cudaStream_t)cuda_stream;
@@ -243,6 +252,7 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     CK(cudaFuncSetAttribute(k_hash_numeric<512, 5120, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<512, 5120, 8192>)));
     CK(cudaFuncSetAttribute(k_hash_numeric<256, 2560, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<256, 2560, 4096>)));
     if (c->esc_chunk < 1) c->esc_chunk = 1;
+    undo.c = nullptr;
     *out = c;
     return SPB_OK;
 }
@@ -303,10 +313,16 @@ static int coo_new(spb_ctx *ctx, int rank, const u64 *shape, u64 n, bool allocat
     a->range_lo = a->range_hi = 0;
     a->max_row_len = 0;
     if (allocate) {
-        CK(cudaSetDevice(ctx->device));
         size_t cnt = n ? n : 1;
-        for (int k = 0; k < rank; ++k) CK(ctx->pool.alloc((void **)&a->idx[k], cnt * sizeof(i32)));
-        CK(ctx->pool.alloc((void **)&a->val, cnt * sizeof(double)));
+        cudaError_t e = cudaSetDevice(ctx->device);
+        for (int k = 0; k < rank && e == cudaSuccess; ++k) e = ctx->pool.alloc((void **)&a->idx[k], cnt * sizeof(i32));
+        if (e == cudaSuccess) e = ctx->pool.alloc((void **)&a->val, cnt * sizeof(double));
+        if (e != cudaSuccess) {  // give back what was obtained
+            for (int k = 0; k < 2; ++k) ctx->pool.release(a->idx[k]);
+            ctx->pool.release(a->val);
+            delete a;
+            return spb_fail(SPB_ERR_CUDA, "device allocation for %llu entries failed: %s", (ull)n, cudaGetErrorString(e));
+        }
     }
     *out = a;
     return SPB_OK;
@@ -342,12 +358,18 @@ int spb_coo_upload(spb_ctx *ctx, int rank, const uint64_t *shape, const int32_t 
     CKR(coo_new(ctx, rank, shape, n, true, out));
     spb_coo *a = *out;
     set_order(a, sort_order);
-    if (n) {
-        for (int k = 0; k < rank; ++k)
-            CK(cudaMemcpyAsync(a->idx[k], idx[k], n * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(a->val, val, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < rank && n && e == cudaSuccess; ++k) {
+        if (!idx[k]) { spb_coo_free(ctx, a); *out = nullptr; return spb_fail(SPB_ERR_ARG, "null index pointer for dimension %d", k); }
+        e = cudaMemcpyAsync(a->idx[k], idx[k], n * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream);
     }
-    CK(cudaStreamSynchronize(ctx->stream));  // host buffers are free to go when we return
+    if (n && e == cudaSuccess) e = cudaMemcpyAsync(a->val, val, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host buffers are free to go when we return
+    if (e != cudaSuccess) {
+        spb_coo_free(ctx, a);
+        *out = nullptr;
+        return spb_fail(SPB_ERR_CUDA, "upload of %llu entries failed: %s", (ull)n, cudaGetErrorString(e));
+    }
     return SPB_OK;
 }
 
