@@ -27,3 +27,75 @@ def test_reference_arm_prints_one_json_line():
 def test_scripts_parse():
     for rel in ["bench.py", "__graft_entry__.py"] + [os.path.join("tools", f) for f in sorted(os.listdir(os.path.join(ROOT, "tools"))) if f.endswith(".py")]:
         ast.parse(open(os.path.join(ROOT, rel)).read(), filename=rel)
+
+
+def _bench():
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench
+
+
+def test_clock_sampler_prefers_nvml_and_survives_failed_queries(monkeypatch):
+    """bench.py's clocks line: NVML polled every 2 ms (fake module here), failed queries are missing samples, throttle
+    reasons are collected; without NVML and without nvidia-smi the line carries nulls instead of failing."""
+    import time
+    import types
+    bench = _bench()
+    nv = types.ModuleType("pynvml")
+
+    class NVMLError(Exception):
+        pass
+    calls = [0]
+
+    def clock(h, t):
+        calls[0] += 1
+        if calls[0] % 4 == 0:
+            raise NVMLError("transient")
+        return 1900 + calls[0] % 2
+    nv.NVMLError = NVMLError
+    nv.nvmlInit = lambda: None
+    nv.nvmlDeviceGetHandleByUUID = lambda u: ("uuid", u)
+    nv.nvmlDeviceGetHandleByIndex = lambda i: ("index", i)
+    nv.NVML_CLOCK_SM = 1
+    nv.nvmlDeviceGetMaxClockInfo = lambda h, t: 1965
+    nv.nvmlDeviceGetClockInfo = clock
+    nv.nvmlDeviceGetCurrentClocksThrottleReasons = lambda h: 4 | 1   # sw_power_cap + gpu_idle (not reported)
+    nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown = 8, 64
+    nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap = 32, 4
+    monkeypatch.setitem(sys.modules, "pynvml", nv)
+    s = bench.ClockSampler(0, "GPU-1234")
+    time.sleep(0.05)
+    out = s.stop()
+    assert out["samples"] >= 5 and out["source"].startswith("nvml") and 1900 <= out["sm_mhz"] <= 1901
+    assert out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    broken = types.ModuleType("pynvml")   # no NVML at all (no attributes): falls back to nvidia-smi, absent here too
+    monkeypatch.setitem(sys.modules, "pynvml", broken)
+    out = bench.ClockSampler(0, None).stop()
+    assert out["samples"] == 0 and out["sm_mhz"] is None and out["reasons"] == []
+
+
+def test_numa_binding_reads_sysfs_and_never_fails(monkeypatch):
+    import builtins
+    import io
+    import types
+    bench = _bench()
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1B, pci_device_id=0)
+    torch = types.SimpleNamespace(cuda=types.SimpleNamespace(get_device_properties=lambda i: props))
+    have = os.sched_getaffinity(0)
+    some = sorted(have)[: max(1, len(have) // 2)]
+    files = {"/sys/bus/pci/devices/0000:1b:00.0/numa_node": "1\n",
+             "/sys/devices/system/node/node1/cpulist": ",".join(str(c) for c in some) + ",100000-100003\n"}
+    real = builtins.open
+    monkeypatch.setattr(builtins, "open", lambda p, *a, **k: io.StringIO(files[p]) if p in files else real(p, *a, **k))
+    try:
+        out = bench.bind_to_gpu_numa_node(torch, 0)
+        assert out["node"] == 1 and out["cpus"] == len(some) and os.sched_getaffinity(0) == set(some)
+        assert out["bound"] == (set(some) != have)
+    finally:
+        os.sched_setaffinity(0, have)
+    files["/sys/bus/pci/devices/0000:1b:00.0/numa_node"] = "-1\n"
+    assert bench.bind_to_gpu_numa_node(torch, 0)["bound"] is False and os.sched_getaffinity(0) == have
+    del files["/sys/bus/pci/devices/0000:1b:00.0/numa_node"]       # no such device in sysfs
+    assert bench.bind_to_gpu_numa_node(torch, 0)["bound"] is False
+    monkeypatch.setenv("SPB_NO_NUMA_BIND", "1")
+    assert bench.bind_to_gpu_numa_node(torch, 0) == {"bound": False, "why": "SPB_NO_NUMA_BIND"}
