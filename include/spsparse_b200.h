@@ -155,6 +155,35 @@ int spb_multiply_mm_prepared(spb_ctx *ctx, double C, const spb_coo *scalei, cons
                              int a_row_dim, const spb_coo *scalej, const spb_coo *B, int b_inner_dim,
                              const spb_coo *scalek, spb_coo **out, spb_mm_stats *stats);
 
+/* ---- multiply in row panels -----------------------------------------------------------------
+ * The A-row loop of spsparse::multiply carries no state from one row to the next
+ * (multiply_sparse.hpp:192-246): the product can be formed one panel -- a contiguous range of the
+ * non-empty rows of op(A) -- at a time, and the panels' results, concatenated in panel order, are
+ * exactly what spb_multiply_mm returns.  This is the way to products that no single array can
+ * hold (>= 2^31 entries, the reference's own cap, algorithm.hpp:419; or more bytes than the GPU
+ * has): R-MAT 2^24 rows A*A has 3*10^10 outputs.
+ *
+ * spb_mm_plan_create   consolidates A and B as spb_multiply_mm does (once), counts the intermediate
+ *                      products of every row and cuts the rows into panels of about
+ *                      max_products_per_panel products each (a single row is never cut).  The scale
+ *                      vectors are used, not copied: they must outlive the plan.  A and B may be freed.
+ * spb_mm_plan_info     which rows of C panel p holds (first/last row index), its product count, and the
+ *                      shape of C (multiply_sparse.hpp:169).  panel >= n_panels: only `shape` is written.
+ * spb_mm_plan_symbolic symbolic phase of one panel only: exact product count and bins, and the panel's
+ *                      output count (exact, except that outputs of the hash-accumulator bin whose terms cancel
+ *                      to exactly 0 are still counted) -- no result array is allocated.
+ * spb_mm_plan_panel    the panel's rows of C, as spb_multiply_mm would have produced them. */
+typedef struct spb_mm_plan spb_mm_plan;
+int spb_mm_plan_create(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,
+                       const spb_coo *scalej, const spb_coo *B, char transpose_B, const spb_coo *scalek,
+                       int policy, int zero_nan, uint64_t max_products_per_panel, spb_mm_plan **out,
+                       uint64_t *n_panels, uint64_t *products);
+int spb_mm_plan_info(const spb_mm_plan *plan, uint64_t panel, int32_t *first_row, int32_t *last_row,
+                     uint64_t *products, uint64_t *shape /*[2]*/);
+int spb_mm_plan_symbolic(spb_mm_plan *plan, uint64_t panel, spb_mm_stats *stats);
+int spb_mm_plan_panel(spb_mm_plan *plan, uint64_t panel, spb_coo **out, spb_mm_stats *stats /* may be NULL */);
+int spb_mm_plan_destroy(spb_mm_plan *plan);
+
 /* ---- multiply, matrix*vector  (spsparse::multiply, multiply_sparse.hpp:281-365) -------- */
 int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,
                     const spb_coo *scalej, const spb_coo *V, int policy, int zero_nan, spb_coo **out);

@@ -65,6 +65,12 @@ SIGNATURES = {
                                   C.POINTER(vp), C.POINTER(MMStats)]),
     "spb_multiply_mm_prepared": (C.c_int, [vp, C.c_double, vp, vp, C.c_int, vp, vp, C.c_int, vp,
                                            C.POINTER(vp), C.POINTER(MMStats)]),
+    "spb_mm_plan_create": (C.c_int, [vp, C.c_double, vp, vp, C.c_char, vp, vp, C.c_char, vp, C.c_int, C.c_int, C.c_uint64,
+                                     C.POINTER(vp), u64p, u64p]),
+    "spb_mm_plan_info": (C.c_int, [vp, C.c_uint64, i32p, i32p, u64p, u64p]),
+    "spb_mm_plan_symbolic": (C.c_int, [vp, C.c_uint64, C.POINTER(MMStats)]),
+    "spb_mm_plan_panel": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(MMStats)]),
+    "spb_mm_plan_destroy": (C.c_int, [vp]),
     "spb_multiply_mv": (C.c_int, [vp, C.c_double, vp, vp, C.c_char, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     "spb_gen_dup_coo": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(vp)]),
     "spb_gen_banded": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]),

@@ -242,6 +242,47 @@ def multiply_prepared(ctx: Context, Cst, scalei, A, a_row_dim, scalej, B, b_inne
     return CooArray(ctx, h), st
 
 
+class MultiplyPlan:
+    """spsparse::multiply formed in row panels (spb_mm_plan_*): the A-row loop of the reference carries no state between
+    rows (multiply_sparse.hpp:192-246), so ``panel(0), panel(1), ...`` concatenated are the result of ``multiply`` -- for
+    products too large for one array (R-MAT 2^24 A*A)."""
+
+    def __init__(self, ctx: Context, Cst, scalei, A, transpose_A, scalej, B, transpose_B, scalek,
+                 duplicate_policy=ADD, zero_nan=False, max_products_per_panel=1 << 30):
+        self.ctx = ctx
+        self._keep = (scalei, scalej, scalek)  # used by the plan, not copied
+        h, n, f = vp(), C.c_uint64(), C.c_uint64()
+        check(ctx.lib.spb_mm_plan_create(ctx.h, float(Cst), _h(scalei), A.h, transpose_A.encode(), _h(scalej), B.h,
+                                         transpose_B.encode(), _h(scalek), int(duplicate_policy), int(bool(zero_nan)),
+                                         int(max_products_per_panel), C.byref(h), C.byref(n), C.byref(f)))
+        self.h, self.n_panels, self.products = h, int(n.value), int(f.value)
+        shp = (C.c_uint64 * 2)()
+        check(ctx.lib.spb_mm_plan_info(self.h, self.n_panels, None, None, None, shp))
+        self.shape = (int(shp[0]), int(shp[1]))
+
+    def info(self, p):
+        """(first row index, last row index, intermediate products) of panel p"""
+        a, b, f = C.c_int32(), C.c_int32(), C.c_uint64()
+        check(self.ctx.lib.spb_mm_plan_info(self.h, int(p), C.byref(a), C.byref(b), C.byref(f), None))
+        return int(a.value), int(b.value), int(f.value)
+
+    def symbolic(self, p) -> MMStats:
+        st = MMStats()
+        check(self.ctx.lib.spb_mm_plan_symbolic(self.h, int(p), C.byref(st)))
+        return st
+
+    def panel(self, p, stats=False):
+        h, st = vp(), MMStats()
+        check(self.ctx.lib.spb_mm_plan_panel(self.h, int(p), C.byref(h), C.byref(st)))
+        out = CooArray(self.ctx, h)
+        return (out, st) if stats else out
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.spb_mm_plan_destroy(self.h)
+            self.h = None
+
+
 # ---- synthetic inputs on the device (SURVEY.md Appendix C) ------------------------------------
 def gen_dup_coo(ctx, seed, i0, n, ubase, bits, zero_every=0):
     h = vp()

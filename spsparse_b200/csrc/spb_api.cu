@@ -887,7 +887,7 @@ template <typename K> static int allow_ballast(K kernel) {
 // A: consolidated, sorted by (a_row_dim, other).  B: consolidated, sorted by (b_inner_dim, other).
 static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, int a_row_dim,
                          const spb_coo *sj, const spb_coo *B, int b_inner_dim, const spb_coo *sk,
-                         spb_coo *out, spb_mm_stats *st, Timer &tm, int t_begin) {
+                         spb_coo *out, spb_mm_stats *st, Timer &tm, int t_begin, bool symbolic_only = false) {
     Scratch ws(ctx);
     const int a_in = 1 - a_row_dim, b_col = 1 - b_inner_dim;
     const u64 m_rows = A->shape[a_row_dim], n_inner = A->shape[a_in], n_cols = B->shape[b_col];
@@ -1088,8 +1088,22 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaStreamSynchronize(ctx->stream));
     const int t_sym = tm.mark();
     if (tracing()) fprintf(stderr, "[spb] mm: symbolic host %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
+    if (symbolic_only) {
+        // counts only (spb_mm_plan_symbolic): F and the bins are exact; nnz_c is exact except that hash-bin outputs whose
+        // terms cancel to exactly 0 are still counted (the numeric pass is what finds them)
+        if (st) {
+            st->products = h_stats[0] + h_stats[3] + h_stats[4]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2] - h_stats[5];
+            st->products_esc = h_stats[3]; st->rows_hash = h_stats[5]; st->products_hash = h_stats[4];
+            st->nnz_a = A->n; st->nnz_b = B->n; st->rows_a = nrows; st->nnz_c = nnz_c;
+            st->ms_prepare = tm.ms(t_begin, t_prep);
+            st->ms_symbolic = tm.ms(t_prep, t_sym);
+            st->ms_total = tm.ms(t_begin, t_sym);
+        }
+        return SPB_OK;
+    }
     if (nnz_c >= (1ull << 31))
-        return spb_fail(SPB_ERR_TOO_LARGE, "product has %llu entries; a VectorCooArray holds < 2^31 (algorithm.hpp:419)", (ull)nnz_c);
+        return spb_fail(SPB_ERR_TOO_LARGE, "product has %llu entries; a VectorCooArray holds < 2^31 (algorithm.hpp:419) -- "
+                        "form it in row panels (spb_mm_plan_create)", (ull)nnz_c);
 
     // ---- numeric ------------------------------------------------------------------------------------
     size_t cnt = nnz_c ? nnz_c : 1;
@@ -1576,6 +1590,238 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
     if (rc) { spb_coo_free(ctx, r); *out = nullptr; }
     return rc;
 }
+
+}  // extern "C"
+
+// ---- multiply in row panels ------------------------------------------------------------------------------------------
+// The A-row loop of spsparse::multiply carries no state from one row to the next (multiply_sparse.hpp:192-246), so the
+// product can be formed panel by panel -- a panel is a contiguous range of the non-empty rows of op(A) -- and the panels'
+// results, concatenated in panel order, are the reference's output.  This is how products with more than 2^31 entries
+// (which no VectorCooArray can hold, algorithm.hpp:419) or more bytes than the GPU has are computed: BASELINE config 4.
+struct spb_mm_plan {
+    spb_ctx *ctx;
+    double C;
+    const spb_coo *si, *sj, *sk;   // the caller's scale vectors (must outlive the plan)
+    spb_coo *Ac, *Bc;              // consolidated operands owned by the plan (nullptr: the caller's array is used as it is)
+    const spb_coo *A, *B;          // what the panels multiply
+    int a_row_dim, b_inner_dim;
+    u64 shape[2];
+    u64 products;                  // F of the whole product
+    std::vector<u32> row_lo;       // [panels + 1] compressed row numbers
+    std::vector<u32> ent_lo;       // [panels + 1] entry offsets into A
+    std::vector<u64> prod_lo;      // [panels + 1] product offsets
+    std::vector<i32> row_first;    // [panels] row index i of each panel's first row
+    std::vector<i32> row_last;     // [panels] ... and of its last row
+};
+
+// rb[c] = first compressed row whose first product has number >= c * chunk (c = nchunks: nrows); eb / pb: its first
+// entry and the number of that entry's first product; rid[c]: the row index of row rb[c] (and of row rb[c+1]-1 in rid2)
+__global__ void k_panel_bounds(const u32 *__restrict__ arow_start, const i32 *__restrict__ arow_id, const u64 *__restrict__ ent_off,
+                               u32 nrows, u64 chunk, u32 nchunks, u32 *rb, u32 *eb, u64 *pb) {
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nchunks) return;
+    u32 lo = 0, hi = nrows;
+    if (c == nchunks) lo = nrows;
+    else {
+        const u64 want = (u64)c * chunk;
+        while (lo < hi) {
+            const u32 mid = lo + (hi - lo) / 2;
+            if (ent_off[arow_start[mid]] < want) lo = mid + 1; else hi = mid;
+        }
+    }
+    rb[c] = lo;
+    eb[c] = arow_start[lo];
+    pb[c] = ent_off[arow_start[lo]];
+}
+__global__ void k_rebase_u32(const u32 *__restrict__ src, u64 n, u32 base, u32 *dst) {
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) dst[t] = src[t] - base;
+}
+
+extern "C" {
+
+int spb_mm_plan_destroy(spb_mm_plan *plan) {
+    if (!plan) return SPB_OK;
+    spb_coo_free(plan->ctx, plan->Ac);
+    spb_coo_free(plan->ctx, plan->Bc);
+    delete plan;
+    return SPB_OK;
+}
+
+int spb_mm_plan_create(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, char tA, const spb_coo *sj,
+                       const spb_coo *B, char tB, const spb_coo *sk, int policy, int zero_nan,
+                       uint64_t max_products_per_panel, spb_mm_plan **out, uint64_t *n_panels, uint64_t *products) {
+    if (!ctx || !A || !B || !out) return spb_fail(SPB_ERR_ARG, "spb_mm_plan_create: null argument");
+    if (A->rank != 2 || B->rank != 2) return spb_fail(SPB_ERR_ARG, "A and B must be rank-2 arrays");
+    if (policy < 0 || policy > 2) return spb_fail(SPB_ERR_ARG, "unknown duplicate policy %d", policy);
+    if (max_products_per_panel == 0) return spb_fail(SPB_ERR_ARG, "max_products_per_panel must be positive");
+    CKR(scale_ok(si, "scalei")); CKR(scale_ok(sj, "scalej")); CKR(scale_ok(sk, "scalek"));
+    CK(cudaSetDevice(ctx->device));
+    const int a_so[2] = {tA == 'T' ? 1 : 0, tA == 'T' ? 0 : 1};   // multiply_sparse.hpp:167-169
+    const int b_so[2] = {tB == 'T' ? 0 : 1, tB == 'T' ? 1 : 0};
+    const int b_mine[2] = {b_so[1], b_so[0]};
+    if (A->shape[a_so[1]] != B->shape[b_so[1]])  // :172-174
+        return spb_fail(SPB_ERR_INNER_DIM, "Inner dimensions for A (%ld) and B (%ld) must match!",
+                        (long)A->shape[a_so[1]], (long)B->shape[b_so[1]]);
+    spb_mm_plan *p = new spb_mm_plan();
+    p->ctx = ctx; p->C = C; p->si = si; p->sj = sj; p->sk = sk; p->Ac = p->Bc = nullptr; p->A = A; p->B = B;
+    p->a_row_dim = a_so[0]; p->b_inner_dim = b_mine[0];
+    p->shape[0] = A->shape[a_so[0]]; p->shape[1] = B->shape[b_so[0]];
+    p->products = 0;
+    *out = p;
+    if (n_panels) *n_panels = 0;
+    if (products) *products = 0;
+    // :178-184: the empty product has no panels
+    if (C == 0.0 || (si && si->n == 0) || A->n == 0 || (sj && sj->n == 0) || B->n == 0 || (sk && sk->n == 0)) return SPB_OK;
+    int rc = 0;
+    if (!(A->sort_order[0] == a_so[0] && A->sort_order[1] == a_so[1])) {
+        rc = consolidate_core(ctx, A, a_so, a_so, policy, true, zero_nan, &p->Ac, nullptr);
+        p->A = p->Ac;
+    }
+    if (!rc) {
+        if (B->sort_order[0] == b_so[0] && B->sort_order[1] == b_so[1])
+            rc = consolidate_core(ctx, B, b_mine, b_so, POLICY_KEEP_ALL, false, 0, &p->Bc, nullptr);
+        else
+            rc = consolidate_core(ctx, B, b_mine, b_so, policy, true, zero_nan, &p->Bc, nullptr);
+        p->B = p->Bc;
+    }
+    if (rc) { spb_mm_plan_destroy(p); *out = nullptr; return rc; }
+    if (p->A->n == 0 || p->B->n == 0) return SPB_OK;
+    // products per entry of A -> where the panels are cut
+    auto body = [&]() -> int {
+        Scratch ws(ctx);
+        MMOperands m;
+        memset(&m, 0, sizeof m);
+        m.a_j = p->A->idx[1 - p->a_row_dim]; m.a_val = p->A->val; m.nnz_a = (u32)p->A->n;
+        RowIndex ri;
+        CKR(build_row_index(ctx, p->A, &ri));
+        m.arow_id = ri.id; m.arow_start = ri.start; m.nrows = ri.nrows;
+        u32 *bptr;
+        CKR(build_dense_ptr(ctx, p->B, p->A->shape[1 - p->a_row_dim], &bptr));
+        m.bptr = bptr;
+        double *d;
+        unsigned char *mask;
+        if (si) { CKR(densify(ctx, ws, si, p->shape[0], &d, nullptr)); m.si = d; }
+        if (sj) { CKR(densify(ctx, ws, sj, p->A->shape[1 - p->a_row_dim], &d, &mask)); m.sj = d; m.sj_mask = mask; }
+        u32 *ent_f;
+        u64 *ent_off;
+        CKR(ws.get(&ent_f, m.nnz_a));
+        CKR(ws.get(&ent_off, (u64)m.nnz_a + 1));
+        const u32 cap = (u32)ctx->sm_count * 32;
+        ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, p->A->idx[p->a_row_dim], ent_f);
+        CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
+        u64 F = 0;
+        CK(cudaMemcpyAsync(&F, ent_off + m.nnz_a, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        spb_coo *Am = const_cast<spb_coo *>(p->A);
+        u32 *mx = nullptr;
+        if (!Am->max_row_len) {
+            CKR(ws.zeroed(&mx, 1));
+            ++ctx->launches, k_row_maxlen<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(ri.start, ri.nrows, mx);
+            CK(cudaMemcpyAsync(&Am->max_row_len, mx, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        p->products = F;
+        u64 nch64 = div_up(F ? F : 1, max_products_per_panel);
+        if (nch64 > ri.nrows) nch64 = ri.nrows;   // a panel holds at least one row
+        const u32 nch = (u32)nch64;
+        const u64 chunk = div_up(F ? F : 1, (u64)nch);  // even panels
+        u32 *rb, *eb;
+        u64 *pb;
+        CKR(ws.get(&rb, (u64)nch + 1)); CKR(ws.get(&eb, (u64)nch + 1)); CKR(ws.get(&pb, (u64)nch + 1));
+        ++ctx->launches, k_panel_bounds<<<(u32)div_up((u64)nch + 1, 128), 128, 0, ctx->stream>>>(ri.start, ri.id, ent_off, ri.nrows, chunk, nch, rb, eb, pb);
+        CK(cudaGetLastError());
+        std::vector<u32> h_rb(nch + 1), h_eb(nch + 1);
+        std::vector<u64> h_pb(nch + 1);
+        CK(cudaMemcpyAsync(h_rb.data(), rb, (nch + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_eb.data(), eb, (nch + 1) * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(h_pb.data(), pb, (nch + 1) * sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        h_rb[0] = 0; h_eb[0] = 0; h_pb[0] = 0;          // rows without products in front of the first cut belong to panel 0
+        h_pb[nch] = F;
+        for (u32 c = 0; c <= nch; ++c) {               // drop empty panels (a hub row can span several chunks)
+            if (c > 0 && c < nch && h_rb[c] == p->row_lo.back()) continue;
+            if (c == nch && !p->row_lo.empty() && h_rb[c] == p->row_lo.back()) { p->prod_lo.back() = F; break; }
+            p->row_lo.push_back(h_rb[c]); p->ent_lo.push_back(h_eb[c]); p->prod_lo.push_back(h_pb[c]);
+        }
+        const size_t np = p->row_lo.size() - 1;
+        // first / last row index of every panel (information for the caller: which rows of C a panel holds)
+        p->row_first.resize(np); p->row_last.resize(np);
+        for (size_t c = 0; c < np; ++c) {
+            CK(cudaMemcpyAsync(&p->row_first[c], ri.id + p->row_lo[c], sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&p->row_last[c], ri.id + p->row_lo[c + 1] - 1, sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    rc = body();
+    if (rc) { spb_mm_plan_destroy(p); *out = nullptr; return rc; }
+    if (n_panels) *n_panels = p->row_lo.empty() ? 0 : p->row_lo.size() - 1;
+    if (products) *products = p->products;
+    return SPB_OK;
+}
+
+int spb_mm_plan_info(const spb_mm_plan *plan, uint64_t panel, int32_t *first_row, int32_t *last_row, uint64_t *products,
+                     uint64_t *shape) {
+    if (!plan) return spb_fail(SPB_ERR_ARG, "spb_mm_plan_info: null plan");
+    if (shape) { shape[0] = plan->shape[0]; shape[1] = plan->shape[1]; }
+    const size_t np = plan->row_lo.empty() ? 0 : plan->row_lo.size() - 1;
+    if (panel >= np) {
+        if (first_row || last_row || products) return spb_fail(SPB_ERR_ARG, "panel %llu of %zu", (ull)panel, np);
+        return SPB_OK;
+    }
+    if (first_row) *first_row = plan->row_first[panel];
+    if (last_row) *last_row = plan->row_last[panel];
+    if (products) *products = plan->prod_lo[panel + 1] - plan->prod_lo[panel];
+    return SPB_OK;
+}
+
+// one panel: symbolic_only = counts, no result array
+static int plan_run(spb_mm_plan *plan, uint64_t panel, bool symbolic_only, spb_coo **out, spb_mm_stats *stats) {
+    if (!plan || (!symbolic_only && !out)) return spb_fail(SPB_ERR_ARG, "spb_mm_plan: null argument");
+    const size_t np = plan->row_lo.empty() ? 0 : plan->row_lo.size() - 1;
+    if (panel >= np) return spb_fail(SPB_ERR_ARG, "panel %llu of %zu", (ull)panel, np);
+    spb_ctx *ctx = plan->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    const u32 r0 = plan->row_lo[panel], r1 = plan->row_lo[panel + 1], e0 = plan->ent_lo[panel], e1 = plan->ent_lo[panel + 1];
+    // the panel as an operand of its own: rows r0..r1 of op(A), row starts re-based to its first entry
+    Scratch ws(ctx);
+    u32 *rs;
+    CKR(ws.get(&rs, (u64)(r1 - r0) + 1));
+    ++ctx->launches, k_rebase_u32<<<grid_for((u64)(r1 - r0) + 1, 256, (u32)ctx->sm_count * 8), 256, 0, ctx->stream>>>(plan->A->row_start + r0, (u64)(r1 - r0) + 1, e0, rs);
+    CK(cudaGetLastError());
+    spb_coo v = *plan->A;
+    v.owned = false;
+    v.idx[0] += e0; v.idx[1] += e0; v.val += e0;
+    v.n = e1 - e0;
+    v.row_start = rs; v.row_id = plan->A->row_id + r0; v.nrows = r1 - r0; v.rows_valid = true;
+    v.dense_ptr = nullptr; v.range_ptr = nullptr;
+    spb_coo *r = nullptr;
+    if (!symbolic_only) {
+        CKR(coo_new(ctx, 2, plan->shape, 0, false, &r));
+        r->owned = true;
+    }
+    spb_coo dummy;
+    memset(&dummy, 0, sizeof dummy);
+    Timer tm(ctx->stream);
+    const int t0 = tm.mark();
+    int rc = multiply_core(ctx, plan->C, plan->si, &v, plan->a_row_dim, plan->sj, plan->B, plan->b_inner_dim, plan->sk,
+                           symbolic_only ? &dummy : r, stats, tm, t0, symbolic_only);
+    if (rc) { spb_coo_free(ctx, r); return rc; }
+    if (out) *out = r;
+    return SPB_OK;
+}
+
+int spb_mm_plan_symbolic(spb_mm_plan *plan, uint64_t panel, spb_mm_stats *stats) {
+    return plan_run(plan, panel, true, nullptr, stats);
+}
+
+int spb_mm_plan_panel(spb_mm_plan *plan, uint64_t panel, spb_coo **out, spb_mm_stats *stats) {
+    return plan_run(plan, panel, false, out, stats);
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- generators ------------------------------------------------------------------------------------
 int spb_gen_dup_coo(spb_ctx *ctx, uint64_t seed, uint64_t i0, uint64_t n, uint64_t ubase, int bits,

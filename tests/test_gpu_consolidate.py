@@ -242,12 +242,8 @@ def test_nine_bit_digit_passes(orc, monkeypatch, seg):
     """SPB_RADIX9=1: 9-bit digits (k_radix_pass9) wherever they cover the key -- or, with the in-row column sort, its row
     part -- in fewer passes than 8-bit ones: 17-bit and 27-bit row parts, 34- and 54-bit keys; all policies, zero_nan, both
     sort orders, duplicates.  Same answers as the oracle, bit for bit."""
-    import os
     import spsparse_b200 as sp
     from _gpu import up, down
-    if not os.environ.get("SPB_TEST_EXPERIMENTAL"):
-        pytest.skip("SPB_RADIX9=1 on small arrays has not been run on a GPU yet (the default only uses 9-bit digits for the "
-                    "row passes of arrays of 2^23 entries or more, covered by test_config5_full_size): set SPB_TEST_EXPERIMENTAL=1")
     monkeypatch.setenv("SPB_RADIX9", "1")
     monkeypatch.setenv("SPB_SEGMENT_SORT", seg)
     rng = np.random.default_rng(99)

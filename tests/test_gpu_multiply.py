@@ -364,3 +364,62 @@ def test_hash_bin_wider_than_the_bitmap(ctx, orc):
         for h in hs + [R]:
             if h is not None:
                 h.free()
+
+
+# ---- multiply in row panels (spb_mm_plan_*): the panels concatenated ARE the product ---------------------------------------
+def gpu_mm_panels(ctx, Cst, si, A, tA, sj, B, tB, sk, pol=O.ADD, zn=False, max_products=1 << 30):
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    hs = [up(ctx, x) for x in (si, A, sj, B, sk)]
+    plan = sp.MultiplyPlan(ctx, Cst, hs[0], hs[1], tA, hs[2], hs[3], tB, hs[4], pol, zn, max_products)
+    hs[1].free(); hs[3].free()                 # the plan holds its own consolidated operands
+    parts, sym = [], []
+    last = -1
+    for p in range(plan.n_panels):
+        first_row, last_row, f = plan.info(p)
+        st0 = plan.symbolic(p)
+        R, st = plan.panel(p, stats=True)
+        c = down(R)
+        R.free()
+        assert st0.products == st.products == f and st0.rows_merge == st.rows_merge and st0.rows_hash == st.rows_hash
+        assert st0.nnz_c >= st.nnz_c == c.n     # the symbolic count is exact unless hash-bin sums cancel to 0
+        assert first_row > last and last_row >= first_row
+        if c.n:
+            assert first_row <= c.idx[0].min() and c.idx[0].max() <= last_row
+        last = last_row
+        parts.append(c)
+        sym.append(st0)
+    shape, total = plan.shape, plan.products
+    plan.free()
+    for h in (hs[0], hs[2], hs[4]):
+        if h is not None:
+            h.free()
+    idx = [np.concatenate([c.idx[d] for c in parts]) if parts else np.empty(0, np.int32) for d in (0, 1)]
+    val = np.concatenate([c.val for c in parts]) if parts else np.empty(0)
+    assert sum(s.products for s in sym) == total
+    return O.Coo(shape, idx, val, None), len(parts)
+
+
+@pytest.mark.parametrize("max_products", [1, 7, 1 << 30])
+def test_mm_fixtures_in_row_panels(ctx, max_products):
+    p = _golden.pack("multiply_mm_cases")
+    for s in range(0, int(p["count"]), 2):
+        si, A, sj, B, sk, want = (_golden.get_coo(p, f"m{s}_{x}") for x in ("si", "A", "sj", "B", "sk", "out"))
+        Cst, tA, tB, pol, zn = p[f"m{s}_args"]
+        got, n_panels = gpu_mm_panels(ctx, float(Cst), si, A, chr(int(tA)), sj, B, chr(int(tB)), sk, int(pol), int(zn), max_products)
+        assert _cases.same_coo(got, want), f"mm case {s} in {n_panels} panels"
+
+
+@pytest.mark.parametrize("hash_min", [512, 0])
+def test_rmat_in_row_panels_against_oracle(orc, monkeypatch, hash_min):
+    """R-MAT scale 13 A*A (hub rows, all three bins) cut into ~40 panels: identical to the oracle's product, and the
+    symbolic-only counts add up to the product's."""
+    import spsparse_b200 as sp
+    from spsparse_b200 import gen
+    monkeypatch.setenv("SPB_HASH_MIN_PRODUCTS", str(hash_min))
+    shp, idx, val = gen.rmat(0x5EED0004, 13, 4 << 13)
+    a = O.Coo(shp, idx, val)
+    want, wst = orc.multiply_mm(1.0, None, a, ".", None, a, ".", None, want_stats=True)
+    with sp.Context(0) as c2:
+        got, n_panels = gpu_mm_panels(c2, 1.0, None, a, ".", None, a, ".", None, max_products=wst["F"] // 40)
+    assert 20 <= n_panels <= 41 and _cases.same_coo(got, want)
