@@ -38,7 +38,7 @@ enum {
     SPB_ERR_ARG = 2,        /* bad argument (null pointer, rank, index out of bounds, ...) */
     SPB_ERR_INNER_DIM = 3,  /* multiply: inner dimensions differ (multiply_sparse.hpp:172-174) */
     SPB_ERR_NOT_SORTED = 4, /* dim_beginnings on an unsorted array (algorithm.hpp:82-84) */
-    SPB_ERR_TOO_LARGE = 5   /* more than 2^30 entries in one sort (reference cap: 2^31, algorithm.hpp:419) */
+    SPB_ERR_TOO_LARGE = 5   /* 2^31 or more entries in one array (the reference's own cap, algorithm.hpp:419) */
 };
 
 /* DuplicatePolicy, same order as spsparse.hpp:25-26 */
@@ -53,6 +53,10 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out);
 int spb_ctx_destroy(spb_ctx *ctx);
 int spb_ctx_sync(spb_ctx *ctx);
 int spb_ctx_device(const spb_ctx *ctx, int *device, void **cuda_stream);
+/* The context keeps freed device blocks for reuse (the hot path asks for the same multi-GB scratch sizes every call).
+ * spb_ctx_trim waits for the stream and hands every cached block back to the driver -- for processes that share the GPU
+ * with another allocator; released_bytes (may be NULL) reports how much. */
+int spb_ctx_trim(spb_ctx *ctx, uint64_t *released_bytes);
 /* kernels launched through this context so far (measurement aid) */
 int spb_ctx_launch_count(const spb_ctx *ctx, uint64_t *launches);
 
@@ -127,7 +131,7 @@ int spb_dense_to_coo(spb_ctx *ctx, int rank, const uint64_t *shape, const double
 
 /* ---- multiply, matrix*matrix  (spsparse::multiply, multiply_sparse.hpp:152-248) ---------
  * out = C * diag(si) * op(A) * diag(sj) * op(B) * diag(sk); scale vectors may be NULL; they are
- * used as stored (ascending, non-repeating).  A and B are consolidated internally unless already
+ * used as stored and must be ascending and non-repeating (xiter.hpp:146, 201), else SPB_ERR_ARG.  A and B are consolidated internally unless already
  * flagged sorted in the order the reference needs (Consolidate<>, algorithm.hpp:354-369).
  * The result is row-major sorted, unique, exact-zero sums dropped, and -- like the reference's --
  * left flagged unsorted / in edit mode. */

@@ -93,11 +93,14 @@ __global__ void k_scatter_row_len_range(const u32 *__restrict__ row_start, const
 }
 
 // Sparse scale vector -> dense values (absent = 0) and presence mask.
-// Entries whose index is beyond `dim` can never join a row/column and are ignored.
+// Entries whose index is beyond `dim` can never join a row/column and are ignored.  The reference's joins walk these
+// vectors as sorted lists without repeats (xiter.hpp:146, 201); one that is not leaves *bad != 0 and the call fails --
+// with a repeated index the scatter below would have no defined winner.
 __global__ void k_densify(const i32 *__restrict__ idx, const double *__restrict__ val, u64 n, u64 dim,
-                          double *dense, unsigned char *mask) {
+                          double *dense, unsigned char *mask, u32 *bad) {
     for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
         u32 j = (u32)idx[t];
+        if (t && idx[t - 1] >= idx[t]) *bad = 1u;
         if (j < dim) {
             dense[j] = val[t];
             if (mask) mask[j] = 1;

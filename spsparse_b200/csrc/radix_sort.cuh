@@ -24,10 +24,14 @@ constexpr int RS_MAX_PASSES = 8;
 constexpr size_t RS_SMEM_BYTES =
     (size_t)RS_TILE * 16 + (size_t)RS_WARPS * RS_NB * sizeof(u32) + 64;
 
-// Look-back word of the sort: [31:30] flag, [29:0] count  => at most 2^30 entries per sort.
-#define RS_FLAG_AGG (1u << 30)
-#define RS_FLAG_INCL (2u << 30)
-#define RS_VALUE(w) ((w) & ((1u << 30) - 1))
+// Look-back word of the sort: 0 = not published yet; bit 31 set = inclusive prefix of the tile in bits 30:0; otherwise the
+// tile's own count + 1 (a tile holds RS_TILE entries, so this never reaches bit 31).  Prefixes up to 2^31 - 1: the
+// reference's own limit on the entries of one array (algorithm.hpp:419-421).
+#define RS_WORD_AGG(c) ((c) + 1u)
+#define RS_WORD_INCL(c) ((c) | 0x80000000u)
+#define RS_READY(w) ((w) != 0u)
+#define RS_IS_INCL(w) (((w) >> 31) != 0u)
+#define RS_VALUE(w) (RS_IS_INCL(w) ? ((w) & 0x7fffffffu) : (w) - 1u)
 
 // Where pass 0 reads from, and which inputs it drops.
 struct SortInput {
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
     for (int w = 0; w < RS_WARPS; ++w) total += s_wcnt[w * RS_NB + tid];
     // publish this tile's count of digit `tid` as early as possible
     u32 *lb = a.lookback + (u64)tile * RS_RADIX + tid;
-    st_relaxed_u32(lb, (tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG) | total);
+    st_relaxed_u32(lb, tile == 0 ? RS_WORD_INCL(total) : RS_WORD_AGG(total));
     u32 incl = warp_incl_scan(total);
     if (lane == 31) s_misc[1 + warp] = incl;
     __syncthreads();
@@ -338,17 +342,17 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
             u32 w[RS_LOOKBACK];
 #pragma unroll
             for (int u = 0; u < RS_LOOKBACK; ++u)
-                w[u] = (p - u >= 0) ? ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid) : RS_FLAG_INCL;
+                w[u] = (p - u >= 0) ? ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid) : RS_WORD_INCL(0u);
 #pragma unroll
             for (int u = 0; u < RS_LOOKBACK; ++u) {
                 if (done) break;
-                while ((w[u] >> 30) == 0) w[u] = ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid);
+                while (!RS_READY(w[u])) w[u] = ld_relaxed_u32(a.lookback + (u64)(p - u) * RS_RADIX + tid);
                 excl += RS_VALUE(w[u]);
-                if ((w[u] >> 30) == 2) done = true;
+                if (RS_IS_INCL(w[u])) done = true;
             }
             p -= RS_LOOKBACK;
         }
-        st_relaxed_u32(lb, RS_FLAG_INCL | (excl + total));
+        st_relaxed_u32(lb, RS_WORD_INCL(excl + total));
     }
     const u32 gbase = a.bucket_start[tid] + excl - lstart;  // global slot = gbase + position in tile
     __syncthreads();  // all staging done, s_wcnt free

@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
     u64 *lb_all = reinterpret_cast<u64 *>(a.lookback);
     u64 *lb = lb_all + (u64)tile * (R9_RADIX / 2) + tid;
     {
-        const u32 flag = tile == 0 ? RS_FLAG_INCL : RS_FLAG_AGG;
-        st_relaxed_u64(lb, (u64)(flag | tot0) | ((u64)(flag | tot1) << 32));
+        const u32 w0 = tile == 0 ? RS_WORD_INCL(tot0) : RS_WORD_AGG(tot0), w1 = tile == 0 ? RS_WORD_INCL(tot1) : RS_WORD_AGG(tot1);
+        st_relaxed_u64(lb, (u64)w0 | ((u64)w1 << 32));
     }
     const u32 pair = tot0 + tot1;
     const u32 incl = warp_incl_scan(pair);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
     // ---- decoupled look-back, one digit pair per thread ---------------------------------------------
     u32 excl0 = 0, excl1 = 0;
     if (tile > 0) {
-        const u64 both_incl = (u64)RS_FLAG_INCL | ((u64)RS_FLAG_INCL << 32);
+        const u64 both_incl = (u64)RS_WORD_INCL(0u) | ((u64)RS_WORD_INCL(0u) << 32);
         i64 p = (i64)tile - 1;
         bool done = false;
         while (!done) {
@@ -241,15 +241,15 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
 #pragma unroll
             for (int u = 0; u < R9_LOOKBACK; ++u) {
                 if (done) break;
-                while (((u32)w[u] >> 30) == 0) w[u] = ld_relaxed_u64(lb_all + (u64)(p - u) * (R9_RADIX / 2) + tid);
+                while (!RS_READY((u32)w[u])) w[u] = ld_relaxed_u64(lb_all + (u64)(p - u) * (R9_RADIX / 2) + tid);
                 const u32 w0 = (u32)w[u], w1 = (u32)(w[u] >> 32);
                 excl0 += RS_VALUE(w0);
                 excl1 += RS_VALUE(w1);
-                if ((w0 >> 30) == 2) done = true;
+                if (RS_IS_INCL(w0)) done = true;
             }
             p -= R9_LOOKBACK;
         }
-        st_relaxed_u64(lb, (u64)(RS_FLAG_INCL | (excl0 + tot0)) | ((u64)(RS_FLAG_INCL | (excl1 + tot1)) << 32));
+        st_relaxed_u64(lb, (u64)RS_WORD_INCL(excl0 + tot0) | ((u64)RS_WORD_INCL(excl1 + tot1) << 32));
     }
     const u32 gbase0 = a.bucket_start[2 * tid] + excl0 - lstart0;  // global slot = gbase + position in tile
     const u32 gbase1 = a.bucket_start[2 * tid + 1] + excl1 - lstart1;

@@ -4,7 +4,7 @@
 // equal keys are adjacent after the stable sort and still in insertion order, so the head of
 // every run folds its followers left to right -- acc = v0; acc += v1; ... -- which is the
 // reference's association order, hence bit-identical sums.  Runs longer than RK_LONG_RUN are
-// finished by k_long_runs with a block-wide tree (same value to ~1 ulp * log n, documented).
+// finished by k_long_runs, one warp per run, in the same left-to-right order (bit-identical too).
 // Output slots come from a single-pass decoupled look-back over the tiles' head counts.
 //
 // The same kernel is the "compress" step of expand-sort-compress in multiply (MODE_ESC): there
@@ -17,7 +17,7 @@ constexpr int RK_THREADS = 256;
 constexpr int RK_IPT = 8;
 constexpr int RK_TILE = RK_THREADS * RK_IPT;
 constexpr int RK_WARPS = RK_THREADS / 32;
-constexpr u32 RK_LONG_RUN = 4096;
+constexpr u32 RK_LONG_RUN = 256;
 
 enum { POLICY_LEAVE_ALONE = 0, POLICY_ADD = 1, POLICY_REPLACE = 2, POLICY_KEEP_ALL = 3 };
 enum { MODE_CONSOLIDATE = 0, MODE_ESC = 1 };
@@ -246,36 +246,55 @@ __global__ void __launch_bounds__(RK_THREADS, RK_MIN_BLOCKS) k_reduce_by_key(Red
     }
 }
 
-// Runs longer than RK_LONG_RUN: one block per run, binary search for its end, tree reduction.
+// Runs longer than RK_LONG_RUN: one WARP per run.  The lanes load 32 consecutive values at a time (the next 32 are already in
+// flight) and the values are added one after the other, handed over by shuffles -- the reference's left-to-right fold
+// (algorithm.hpp:307-310), so these sums are bit-identical to the reference's as well, whatever the run length.
 __global__ void __launch_bounds__(256) k_long_runs(ReduceArgs a) {
-    __shared__ double s_red[256];
     const u32 n = *a.n_ptr;
     u32 cnt = *a.long_count;
     if (cnt > a.long_cap) cnt = a.long_cap;
-    for (u32 t = blockIdx.x; t < cnt; t += gridDim.x) {
+    const u32 lane = lane_id();
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < cnt; t += warps) {
         const u32 slot = a.long_list[2 * t], start = a.long_list[2 * t + 1];
         const u64 key = a.keys[start];
-        u32 lo = start, hi = n;  // first index with keys[] > key
+        // end of the run: gallop (runs are short next to n), then bisect -- first index with keys[] > key
+        u32 lo = start + 1, step = RK_LONG_RUN;
+        u32 hi = n;
+        for (;;) {
+            const u64 probe = (u64)lo + step;
+            if (probe >= n) break;
+            if (a.keys[probe] > key) { hi = (u32)probe; break; }
+            lo = (u32)probe + 1;
+            step *= 2;
+        }
         while (lo < hi) {
-            u32 mid = lo + (hi - lo) / 2;
+            const u32 mid = lo + (hi - lo) / 2;
             if (a.keys[mid] <= key) lo = mid + 1; else hi = mid;
         }
         const u32 end = lo;
         double r;
         if (a.policy == POLICY_ADD) {
-            double s = 0.0;
-            for (u32 i = start + threadIdx.x; i < end; i += blockDim.x) s += a.vals[i];
-            s_red[threadIdx.x] = s;
-            __syncthreads();
-            for (u32 o = 128; o > 0; o >>= 1) {
-                if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
-                __syncthreads();
+            double sum = 0.0;
+            bool first = true;
+            u32 i = start;
+            double v = (i + lane < end) ? a.vals[i + lane] : 0.0;
+            while (i < end) {
+                const u32 m = end - i < 32u ? end - i : 32u;
+                const u32 inext = i + 32;
+                const double vn = (inext < end && inext + lane < end) ? a.vals[inext + lane] : 0.0;
+                for (u32 l = 0; l < m; ++l) {  // warp-uniform trip count
+                    const double x = __shfl_sync(SPB_FULL_MASK, v, (int)l);
+                    if (first) { sum = x; first = false; }   // acc = first value (algorithm.hpp:279)
+                    else sum = __dadd_rn(sum, x);
+                }
+                v = vn;
+                i = inext;
             }
-            r = s_red[0];
+            r = sum;
         } else {
             r = (a.policy == POLICY_REPLACE) ? a.vals[end - 1] : a.vals[start];
         }
-        if (threadIdx.x == 0) a.out_val[slot] = r;
-        __syncthreads();
+        if (lane == 0) a.out_val[slot] = r;
     }
 }

@@ -273,6 +273,15 @@ int spb_ctx_sync(spb_ctx *ctx) {
     return SPB_OK;
 }
 
+int spb_ctx_trim(spb_ctx *ctx, uint64_t *released_bytes) {
+    if (!ctx) return spb_fail(SPB_ERR_ARG, "null context");
+    CK(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->pool.mu_);
+    if (released_bytes) *released_bytes = ctx->pool.cached_bytes;
+    ctx->pool.trim_locked();
+    return SPB_OK;
+}
+
 int spb_ctx_launch_count(const spb_ctx *ctx, uint64_t *launches) {
     if (!ctx || !launches) return spb_fail(SPB_ERR_ARG, "null argument");
     *launches = ctx->launches;
@@ -531,7 +540,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     const int digit_bits = nine ? R9_BITS : RS_RADIX_BITS;
     const int passes = nine ? passes9 : passes8;
     const int shift0 = seg ? in.bits_lo : 0;
-    if (n > (1u << 30)) return spb_fail(SPB_ERR_TOO_LARGE, "%u entries exceed the 2^30 per-sort limit", n);
+    if (n >= (1u << 31)) return spb_fail(SPB_ERR_TOO_LARGE, "%u entries: one sort holds fewer than 2^31 (the reference's own cap, algorithm.hpp:419)", n);
     Scratch ws(ctx);
     Timer tm(ctx->stream);
     const int t0 = tm.mark();
@@ -636,7 +645,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         } else {
             ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
             if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
-                ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count, 256, 0, ctx->stream>>>(ra);
+                ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count * 4, 256, 0, ctx->stream>>>(ra);
         }
         CK(cudaGetLastError());
         t2 = tm.mark();
@@ -668,7 +677,7 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
 // used at this call site (decides which NaNs form the "leading run" when zero_nan).
 static int consolidate_core(spb_ctx *ctx, const spb_coo *in, const int *so, const int *ref_so, int policy,
                             bool drop_zero, int zero_nan, spb_coo **out, spb_consolidate_stats *st) {
-    if (in->n > (1ull << 30)) return spb_fail(SPB_ERR_TOO_LARGE, "%llu entries exceed the 2^30 per-sort limit", (ull)in->n);
+    if (in->n >= (1ull << 31)) return spb_fail(SPB_ERR_TOO_LARGE, "%llu entries: one array holds fewer than 2^31 (the reference's own cap, algorithm.hpp:419)", (ull)in->n);
     spb_coo *r = nullptr;
     CKR(coo_new(ctx, in->rank, in->shape, in->n, true, &r));
     set_order(r, so);
@@ -743,8 +752,14 @@ static int build_row_index(spb_ctx *ctx, const spb_coo *a_const, RowIndex *ri) {
         const u32 n = (u32)a->n;
         const i32 *hi = a->idx[a->sort_order[0]];
         Scratch ws(ctx);
-        CK(ctx->pool.alloc((void **)&a->row_start, ((u64)n + 1) * sizeof(u32)));
-        CK(ctx->pool.alloc((void **)&a->row_id, ((u64)n + 1) * sizeof(i32)));
+        u32 *rs = nullptr;
+        i32 *rid = nullptr;
+        CK(ctx->pool.alloc((void **)&rs, ((u64)n + 1) * sizeof(u32)));
+        if (ctx->pool.alloc((void **)&rid, ((u64)n + 1) * sizeof(i32)) != cudaSuccess) {
+            ctx->pool.release(rs);
+            return spb_fail(SPB_ERR_CUDA, "out of device memory (row list of %u entries)", n);
+        }
+        a->row_start = rs; a->row_id = rid;
         u32 *count, *ticket;
         u64 *state;
         const u32 tiles = (u32)div_up(n ? n : 1, RH_TILE);
@@ -797,12 +812,18 @@ static int build_dense_ptr(spb_ctx *ctx, const spb_coo *a_const, u64 extent, u32
     return 0;
 }
 
-static int densify(spb_ctx *ctx, Scratch &ws, const spb_coo *v, u64 dim, double **dense, unsigned char **mask) {
+// `bad` (device, zeroed by the caller): set when the vector's indices are not strictly ascending; the caller reads it
+// back with its next synchronisation and fails the call (bad_scale_vector)
+static int densify(spb_ctx *ctx, Scratch &ws, const spb_coo *v, u64 dim, double **dense, unsigned char **mask, u32 *bad) {
     CKR(ws.zeroed(dense, dim));
     if (mask) CKR(ws.zeroed(mask, dim));
-    if (v->n) ++ctx->launches, k_densify<<<grid_for(v->n, 256, 1u << 16), 256, 0, ctx->stream>>>(v->idx[0], v->val, v->n, dim, *dense, mask ? *mask : nullptr);
+    if (v->n) ++ctx->launches, k_densify<<<grid_for(v->n, 256, 1u << 16), 256, 0, ctx->stream>>>(v->idx[0], v->val, v->n, dim, *dense, mask ? *mask : nullptr, bad);
     CK(cudaGetLastError());
     return 0;
+}
+static int bad_scale_vector() {
+    return spb_fail(SPB_ERR_ARG, "a scale vector (or a vector operand flagged sorted) is not strictly ascending in its index: the "
+                    "reference joins these as sorted lists without repeats (xiter.hpp:146, 201)");
 }
 
 // ==================================================================================================
@@ -904,9 +925,11 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     m.bptr = bptr; m.b_k = B->idx[b_col]; m.b_val = B->val;
     double *d;
     unsigned char *mask;
-    if (si) { CKR(densify(ctx, ws, si, m_rows, &d, nullptr)); m.si = d; }
-    if (sj) { CKR(densify(ctx, ws, sj, n_inner, &d, &mask)); m.sj = d; m.sj_mask = mask; }
-    if (sk) { CKR(densify(ctx, ws, sk, n_cols, &d, nullptr)); m.sk = d; }
+    u32 *bad_vec;
+    CKR(ws.zeroed(&bad_vec, 1));
+    if (si) { CKR(densify(ctx, ws, si, m_rows, &d, nullptr, bad_vec)); m.si = d; }
+    if (sj) { CKR(densify(ctx, ws, sj, n_inner, &d, &mask, bad_vec)); m.sj = d; m.sj_mask = mask; }
+    if (sk) { CKR(densify(ctx, ws, sk, n_cols, &d, nullptr, bad_vec)); m.sk = d; }
     const int t_prep = tm.mark();
     double h0 = now_ms();
     if (tracing()) fprintf(stderr, "[spb] mm: prepare done (host), alloc so far %.2f ms\n", g_alloc_ms);
@@ -962,8 +985,11 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaGetLastError());
     ull h_stats[8];
     u32 *hash_rows = nullptr;
+    u32 h_bad = 0;
     CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&h_bad, bad_vec, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (h_bad) return bad_scale_vector();
     if (h_stats[2]) {
         // long rows exist: products per A entry, their prefix sums, products per long row
         u32 *ent_f;
@@ -1044,8 +1070,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
             const u32 r_lo = h_rb[c], r_hi = h_rb[c + 1];
             const u64 cnt64 = h_pb[c + 1] - h_pb[c];
             if (cnt64 == 0) continue;
-            if (cnt64 > (1ull << 30))
-                return spb_fail(SPB_ERR_TOO_LARGE, "a single row of the product needs %llu intermediate products (> 2^30)", (ull)cnt64);
+            if (cnt64 >= (1ull << 31))
+                return spb_fail(SPB_ERR_TOO_LARGE, "a single row of the product needs %llu intermediate products (>= 2^31)", (ull)cnt64);
             const u32 cnt = (u32)cnt64;
             const int key_bits = bits_for((u64)(r_hi - r_lo)) + kbits;
             u64 *kA;
@@ -1553,13 +1579,14 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
         rc = build_row_index(ctx, Ause, &ri);
         double *d, *vd, *row_val;
         unsigned char *mask, *vmask, *row_keep;
-        u32 *slot;
+        u32 *slot, *bad_vec = nullptr;
         if (!rc) {
             m.arow_id = ri.id; m.arow_start = ri.start; m.nrows = ri.nrows;
-            if (si) { rc = densify(ctx, ws, si, m_rows, &d, nullptr); m.si = d; }
+            rc = ws.zeroed(&bad_vec, 1);
+            if (!rc && si) { rc = densify(ctx, ws, si, m_rows, &d, nullptr, bad_vec); m.si = d; }
         }
-        if (!rc && sj) { rc = densify(ctx, ws, sj, n_inner, &d, &mask); m.sj = d; m.sj_mask = mask; }
-        if (!rc) rc = densify(ctx, ws, Vuse, n_inner, &vd, &vmask);
+        if (!rc && sj) { rc = densify(ctx, ws, sj, n_inner, &d, &mask, bad_vec); m.sj = d; m.sj_mask = mask; }
+        if (!rc) rc = densify(ctx, ws, Vuse, n_inner, &vd, &vmask, bad_vec);
         if (!rc) rc = ws.get(&row_val, ri.nrows);
         if (!rc) rc = ws.get(&row_keep, ri.nrows);
         if (!rc) rc = ws.get(&slot, (u64)ri.nrows + 1);
@@ -1567,10 +1594,12 @@ int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A,
             const u32 cap = (u32)ctx->sm_count * 32;
             ++ctx->launches, k_mv_rows<<<grid_for(ri.nrows, 256, cap), 256, 0, ctx->stream>>>(m, vd, vmask, row_val, row_keep);
             rc = exclusive_scan<unsigned char, u32>(ctx, ws, row_keep, slot, ri.nrows);
-            u32 nout = 0;
+            u32 nout = 0, h_bad = 0;
             if (!rc) {
                 cudaMemcpyAsync(&nout, slot + ri.nrows, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream);
+                cudaMemcpyAsync(&h_bad, bad_vec, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream);
                 if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = spb_fail(SPB_ERR_CUDA, "multiply_mv: %s", cudaGetErrorString(cudaGetLastError()));
+                else if (h_bad) rc = bad_scale_vector();
             }
             if (!rc) {
                 size_t cnt = nout ? nout : 1;
@@ -1700,8 +1729,10 @@ int spb_mm_plan_create(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo 
         m.bptr = bptr;
         double *d;
         unsigned char *mask;
-        if (si) { CKR(densify(ctx, ws, si, p->shape[0], &d, nullptr)); m.si = d; }
-        if (sj) { CKR(densify(ctx, ws, sj, p->A->shape[1 - p->a_row_dim], &d, &mask)); m.sj = d; m.sj_mask = mask; }
+        u32 *bad_vec;
+        CKR(ws.zeroed(&bad_vec, 1));
+        if (si) { CKR(densify(ctx, ws, si, p->shape[0], &d, nullptr, bad_vec)); m.si = d; }
+        if (sj) { CKR(densify(ctx, ws, sj, p->A->shape[1 - p->a_row_dim], &d, &mask, bad_vec)); m.sj = d; m.sj_mask = mask; }
         u32 *ent_f;
         u64 *ent_off;
         CKR(ws.get(&ent_f, m.nnz_a));
@@ -1710,7 +1741,9 @@ int spb_mm_plan_create(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo 
         ++ctx->launches, k_entry_products<<<grid_for(m.nnz_a, 256, cap), 256, 0, ctx->stream>>>(m, p->A->idx[p->a_row_dim], ent_f);
         CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
         u64 F = 0;
+        u32 h_bad = 0;
         CK(cudaMemcpyAsync(&F, ent_off + m.nnz_a, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&h_bad, bad_vec, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         spb_coo *Am = const_cast<spb_coo *>(p->A);
         u32 *mx = nullptr;
         if (!Am->max_row_len) {
@@ -1719,6 +1752,7 @@ int spb_mm_plan_create(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo 
             CK(cudaMemcpyAsync(&Am->max_row_len, mx, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         }
         CK(cudaStreamSynchronize(ctx->stream));
+        if (h_bad) return bad_scale_vector();
         p->products = F;
         u64 nch64 = div_up(F ? F : 1, max_products_per_panel);
         if (nch64 > ri.nrows) nch64 = ri.nrows;   // a panel holds at least one row
