@@ -584,7 +584,15 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
     }
     for x in (A, s, Ar, Bt):
         x.free()
-    # ---- config 4: R-MAT A*A, full multiply() incl. its consolidations (skewed rows: both bins in use) -----
+    # ---- config 4: R-MAT A*A, full multiply() incl. its consolidations (skewed rows: all three bins in use) -----
+    def mm_model(st):
+        return 16.0 * st.products + 56.0 * st.nnz_a + 16.0 * st.nnz_c + 16.0 * st.rows_a
+
+    def kernel_ms(sts):
+        keys = ("ms_merge_count", "ms_hash_count", "ms_esc", "ms_merge_numeric", "ms_hash_emit", "ms_hash_splits", "ms_hash_numeric")
+        return {k: float(np.mean([getattr(x, k) for x in sts])) for k in keys}
+
+    # (a) the member of the family whose product fits one array (scale 20), in ONE multiply() call -- as in round 1
     sc = args.rmat_scale
     A = sp.gen_rmat(ctx, 0x5EED0004, sc, 4 << sc)
     for _ in range(max(1, args.warmup - 1)):
@@ -594,19 +602,66 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
         Cm, st = sp.multiply(ctx, 1.0, None, A, ".", None, A, ".", None, stats=True)
         sts.append(st); Cm.free()
     ms_k = float(np.mean([x.ms_symbolic + x.ms_numeric for x in sts]))
-    model = 16.0 * st.products + 56.0 * st.nnz_a + 16.0 * st.nnz_c + 16.0 * st.rows_a
-    out["spgemm_config4"] = {
-        "workload": f"BASELINE config 4 family: R-MAT scale {sc} (a,b,c,d = .57,.19,.19,.05; edge factor 4) A*A",
-        "note": "scale 24 as named cannot be held by the reference's own container: its product has far more than 2^31 "
-                "entries (VectorCooArray offsets are int, algorithm.hpp:419; 16 B x nnzC would also exceed 180 GB); the "
-                "library returns SPB_ERR_TOO_LARGE there. Scale 20 is the largest power of two whose product fits.",
+    model = mm_model(st)
+    out[f"spgemm_config4_scale{sc}"] = {
+        "workload": f"BASELINE config 4 family: R-MAT scale {sc} (a,b,c,d = .57,.19,.19,.05; edge factor 4) A*A in one multiply() call",
         "products": st.products, "products_hash": st.products_hash, "products_esc": st.products_esc, "nnz_a": st.nnz_a, "nnz_c": st.nnz_c,
         "rows_merge": st.rows_merge, "rows_hash": st.rows_hash, "rows_esc": st.rows_esc,
         "ms_symbolic": float(np.mean([x.ms_symbolic for x in sts])),
         "ms_numeric": float(np.mean([x.ms_numeric for x in sts])), "ms_prepare_incl_consolidate": float(np.mean([x.ms_prepare for x in sts])),
+        "ms_kernels": kernel_ms(sts),
         "products_per_sec": st.products / (ms_k * 1e-3), "model_bytes": model, "model_frac": model / (ms_k * 1e-3) / 1e9 / hbm,
     }
     A.free()
+    # (b) config 4 AS NAMED: 2^24 rows.  Its product (5.6e10 outputs) fits no single array -- VectorCooArray offsets are int
+    # (algorithm.hpp:419) and 16 B x nnzC is 0.9 TB -- so it is formed in row panels (spb_mm_plan_*: the A-row loop of the
+    # reference carries no state between rows, multiply_sparse.hpp:192-246); every panel's rows of C are produced in full
+    # on the device and released.  Timed: symbolic + numeric of every panel of one sweep (CUDA events inside the library)
+    # and the wall clock of the sweep.
+    scn = args.rmat_scale_named
+    if scn:
+        A = sp.gen_rmat(ctx, 0x5EED0004, scn, 4 << scn)
+        ctx.sync()
+        t0 = time.perf_counter()
+        plan = sp.MultiplyPlan(ctx, 1.0, None, A, ".", None, A, ".", None, max_products_per_panel=args.panel_products)
+        ctx.sync()
+        plan_s = time.perf_counter() - t0
+        A.free()
+        sweeps = []
+        for sweep in range(1 + min(args.steps, 2)):     # one warm-up sweep, at most two timed ones (seconds each)
+            ctx.sync()
+            t0 = time.perf_counter()
+            sts = []
+            for p in range(plan.n_panels):
+                Cp, st = plan.panel(p, stats=True)
+                sts.append(st)
+                Cp.free()
+            ctx.sync()
+            sweeps.append((time.perf_counter() - t0, sts))
+        wall_s, sts = min(sweeps[1:], key=lambda x: x[0])
+
+        class Tot:
+            pass
+        tot = Tot()
+        for k in ("products", "products_hash", "products_esc", "nnz_c", "rows_merge", "rows_hash", "rows_esc", "rows_a"):
+            setattr(tot, k, int(sum(getattr(x, k) for x in sts)))
+        tot.nnz_a = int(sum(x.nnz_a for x in sts))
+        ms_k = float(sum(x.ms_symbolic + x.ms_numeric for x in sts))
+        model = mm_model(tot)
+        kms = {k: float(sum(getattr(x, k) for x in sts)) for k in ("ms_merge_count", "ms_hash_count", "ms_esc", "ms_merge_numeric",
+                                                                    "ms_hash_emit", "ms_hash_splits", "ms_hash_numeric", "ms_prepare")}
+        out["spgemm_config4"] = {
+            "workload": f"BASELINE config 4 as named: R-MAT 2^{scn} rows (a,b,c,d = .57,.19,.19,.05; edge factor 4, {4 << scn} raw edges, duplicates kept) A*A, "
+                        f"formed in {plan.n_panels} row panels of <= {args.panel_products} intermediate products (spb_mm_plan_*)",
+            "products": tot.products, "products_hash": tot.products_hash, "products_esc": tot.products_esc, "nnz_a": tot.nnz_a, "nnz_c": tot.nnz_c,
+            "rows_merge": tot.rows_merge, "rows_hash": tot.rows_hash, "rows_esc": tot.rows_esc, "panels": plan.n_panels,
+            "ms_symbolic_plus_numeric_all_panels": ms_k, "ms_sweep_wall": wall_s * 1e3, "ms_plan_incl_consolidate": plan_s * 1e3,
+            "ms_kernels_all_panels": kms,
+            "products_per_sec": tot.products / (ms_k * 1e-3), "products_per_sec_wall": tot.products / wall_s,
+            "model_bytes": model, "model_frac": model / (ms_k * 1e-3) / 1e9 / hbm,
+            "parity": "tests/test_gpu_full_size.py::test_config4_as_named_scale24_row_panels: an unbiased 1/64 sample of the rows of this product, bit for bit (structure, order, values) against the CPU oracle",
+        }
+        plan.free()
     return out
 
 
@@ -731,7 +786,9 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows of the banded problem (headline: 1e8)")
     ap.add_argument("--cons-entries", type=int, default=200_000_000)
     ap.add_argument("--regrid", type=int, nargs=4, default=[3200, 3125, 1000, 1000])
-    ap.add_argument("--rmat-scale", type=int, default=20)
+    ap.add_argument("--rmat-scale", type=int, default=20, help="member of the config-4 family run in one multiply() call")
+    ap.add_argument("--rmat-scale-named", type=int, default=24, help="config 4 as named (row panels); 0 = skip")
+    ap.add_argument("--panel-products", type=int, default=1 << 30, help="intermediate products per row panel")
     ap.add_argument("--cpu-rows", type=int, default=3000)
     ap.add_argument("--cpu-cons-entries", type=int, default=10_000_000)
     ap.add_argument("--ref-rows", type=int, default=2000)

@@ -147,6 +147,10 @@ typedef struct {
     uint64_t products_hash;
     float ms_prepare;        /* consolidations of A and B, CSR build, scale densify */
     float ms_symbolic, ms_numeric, ms_total;
+    /* inside ms_symbolic: register-merge count kernel; bitmap count pass of the hash bin; expand-sort-compress */
+    float ms_merge_count, ms_hash_count, ms_esc;
+    /* inside ms_numeric: register-merge numeric kernel; hash bin: column emit pass, window searches, accumulators */
+    float ms_merge_numeric, ms_hash_emit, ms_hash_splits, ms_hash_numeric;
 } spb_mm_stats;
 int spb_multiply_mm(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,
                     const spb_coo *scalej, const spb_coo *B, char transpose_B, const spb_coo *scalek,

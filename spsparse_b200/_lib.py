@@ -28,7 +28,10 @@ class MMStats(C.Structure):
                 ("products_esc", C.c_uint64), ("nnz_c", C.c_uint64),
                 ("rows_hash", C.c_uint64), ("products_hash", C.c_uint64),
                 ("ms_prepare", C.c_float), ("ms_symbolic", C.c_float), ("ms_numeric", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float),
+                ("ms_merge_count", C.c_float), ("ms_hash_count", C.c_float), ("ms_esc", C.c_float),
+                ("ms_merge_numeric", C.c_float), ("ms_hash_emit", C.c_float), ("ms_hash_splits", C.c_float),
+                ("ms_hash_numeric", C.c_float)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

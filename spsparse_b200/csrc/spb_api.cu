@@ -983,6 +983,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
 #undef SPB_LAUNCH_COUNT
     }
     CK(cudaGetLastError());
+    const int t_mcount = tm.mark();
     ull h_stats[8];
     u32 *hash_rows = nullptr;
     u32 h_bad = 0;
@@ -1009,6 +1010,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     }
 
     // ---- longer rows: bitmap count pass (the emit pass and the hash-accumulator numeric pass follow the placement) ----
+    const int t_bins = tm.mark();
     HashArgs ha;
     memset(&ha, 0, sizeof ha);
     u32 hs_grid = 0;
@@ -1045,6 +1047,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     }
 
     // ---- long rows: expand-sort-compress into per-chunk temporaries -----------------------------
+    const int t_hcount = tm.mark();
     std::vector<EscChunk> chunks;
     u64 esc_total = 0;
     u32 *esc_first = nullptr;
@@ -1107,6 +1110,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     }
 
     // ---- place the rows ---------------------------------------------------------------------------
+    const int t_esc = tm.mark();
     CKR(ws.get(&c_ptr, (u64)nrows + 1));
     CKR((exclusive_scan<u32, u64>(ctx, ws, row_cnt, c_ptr, nrows)));
     u64 nnz_c = 0;
@@ -1124,6 +1128,9 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
             st->ms_prepare = tm.ms(t_begin, t_prep);
             st->ms_symbolic = tm.ms(t_prep, t_sym);
             st->ms_total = tm.ms(t_begin, t_sym);
+            st->ms_merge_count = tm.ms(t_prep, t_mcount);
+            st->ms_hash_count = tm.ms(t_bins, t_hcount);
+            st->ms_esc = tm.ms(t_hcount, t_esc);
         }
         return SPB_OK;
     }
@@ -1159,9 +1166,11 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         else SPB_LAUNCH_NUM(8, 16);
 #undef SPB_LAUNCH_NUM
     }
+    const int t_mnum = tm.mark();
     for (auto &ch : chunks)
         if (ch.n) ++ctx->launches, k_esc_copy<<<grid_for(ch.n, 256, cap), 256, 0, ctx->stream>>>(ch.row, ch.k, ch.v, ch.n, esc_first, c_ptr, m.arow_id, out->idx[0], out->idx[1], out->val);
     u32 h_shrunk = 0;
+    int t_hemit0 = tm.mark(), t_hemit1 = t_hemit0, t_hsplit = t_hemit0, t_hnum = t_hemit0;
     if (h_stats[5] && nnz_c) {
         // emit pass: the bitmap again, now writing the rows' columns into C and cutting the rows into work items
         u32 h_items = 0;
@@ -1172,6 +1181,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         ++ctx->launches, k_hash_symbolic<true><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());
         ull h_split = 0;
+        t_hemit1 = t_hsplit = t_hnum = tm.mark();
         CK(cudaMemcpyAsync(&h_items, ha.n_items, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(&h_split, ha.split_total, sizeof(ull), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1182,6 +1192,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
             ++ctx->launches, k_hash_splits<<<h_items < cap * 4 ? h_items : cap * 4, 256, 0, ctx->stream>>>(m, ha, h_items, split);
             CK(cudaGetLastError());
             ha.split = split;
+            t_hsplit = t_hnum = tm.mark();
         }
         if (h_items) {
             if (tracing()) CKR(ws.zeroed(&ha.dbg, 16));
@@ -1197,6 +1208,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
                 k_hash_numeric<1024, 10240, 16384><<<g, 1024, sizeof(HashSmem<1024, 10240, 16384>), ctx->stream>>>(m, ha, h_items);
             }
             CK(cudaGetLastError());
+            t_hnum = tm.mark();
             CK(cudaMemcpyAsync(&h_shrunk, ha.shrunk, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
             if (ha.dbg) {
                 ull d[16];
@@ -1243,6 +1255,13 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         st->ms_symbolic = tm.ms(t_prep, t_sym);
         st->ms_numeric = tm.ms(t_sym, t_num);
         st->ms_total = tm.ms(t_begin, t_num);
+        st->ms_merge_count = tm.ms(t_prep, t_mcount);
+        st->ms_hash_count = tm.ms(t_bins, t_hcount);
+        st->ms_esc = tm.ms(t_hcount, t_esc);
+        st->ms_merge_numeric = tm.ms(t_sym, t_mnum);
+        st->ms_hash_emit = tm.ms(t_hemit0, t_hemit1);
+        st->ms_hash_splits = tm.ms(t_hemit1, t_hsplit);
+        st->ms_hash_numeric = tm.ms(t_hsplit, t_hnum);
     }
     return SPB_OK;
 }

@@ -81,12 +81,12 @@ def test_edge_cases(ctx, orc):
     for pol, want in ((O.ADD, n * (n + 1) / 2), (O.LEAVE_ALONE, 1.0), (O.REPLACE, float(n))):
         r, _ = gpu_consolidate(ctx, a, (0, 1), pol)
         assert r.n == 1 and r.val[0] == want
-    # long run of reals: tree order differs from the left fold => 1e-12 relative (north_star tolerance)
+    # long run of reals: the deferred runs are folded left to right as well (one warp per run) => bit-identical
     rng = np.random.default_rng(3)
     a = O.Coo((8, 8), [np.full(n, 3), np.full(n, 5)], 0.5 + rng.random(n))
     r, _ = gpu_consolidate(ctx, a, (0, 1))
     want = orc.consolidate(a, (0, 1))
-    assert abs(r.val[0] - want.val[0]) <= 1e-12 * abs(want.val[0])
+    assert r.val[0] == want.val[0]
     # maximum extents: 2^31 x 2^31 shape, indices at both ends
     big = (1 << 31) - 1
     a = O.Coo((1 << 31, 1 << 31), [[big, 0, big, 0], [big, big, big, 0]], [1., 2., 3., 4.])
@@ -101,6 +101,85 @@ def test_edge_cases(ctx, orc):
         A.dim_beginnings()
     assert e.value.code == 4
     A.free()
+
+
+@pytest.mark.parametrize("so", [(0, 1), (1, 0)])
+def test_duplicate_runs_of_every_length(ctx, orc, so):
+    """Runs of 1 .. 6000 duplicates of real values (and zeros / NaNs to drop), scrambled: runs that end inside a thread's
+    block, cross threads, cross tiles, and exceed the deferral threshold (RK_LONG_RUN = 256, finished by k_long_runs) --
+    every sum bit-identical to the reference's left-to-right fold, for every policy."""
+    rng = np.random.default_rng(41)
+    lens = np.concatenate([rng.integers(1, 12, 3000), rng.integers(200, 330, 300), rng.integers(1000, 6000, 40), [257, 256, 255, 264, 2048, 2304]])
+    keys = rng.permutation(len(lens))
+    i = np.repeat(keys // 700, lens)
+    k = np.repeat(keys % 700 * 1000, lens)
+    o = rng.permutation(len(i))
+    a = O.Coo((200, 1 << 20), [i[o], k[o]], _cases._values(rng, len(i), "mixed"))
+    for pol in _cases.POLICIES:
+        for zn in (0, 1):
+            got, db = gpu_consolidate(ctx, a, so, pol, zn)
+            want = orc.consolidate(a, so, pol, zn)
+            assert _cases.same_coo(got, want), (pol, zn)
+
+
+def test_default_path_large_against_oracle(ctx, orc):
+    """2^23 + 12345 entries in a 10^8 x 10^8 shape: the size from which the DEFAULT path is row-digit passes with 9-bit
+    digits (k_radix_pass9) + in-row column sort + reduce -- compared with the oracle in full, bit for bit: dropped zeros,
+    zero_nan, duplicates, hub rows of thousands of entries (longer than the in-row sort handles: re-sorted by full key)."""
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    rng = np.random.default_rng(2024)
+    n = (1 << 23) + 12345
+    m = 100_000_000
+    i = rng.integers(0, m, n)
+    k = rng.integers(0, m, n)
+    dup = rng.random(n) < 0.3                       # ~30 % duplicates of an earlier tuple
+    src = rng.integers(0, n, n)
+    i[dup], k[dup] = i[src[dup]], k[src[dup]]
+    for h, row in enumerate((5, m - 1, 77_777_777)):  # hub rows
+        sl = slice(100_000 * h, 100_000 * h + 3000 + 2000 * h)
+        i[sl] = row
+        k[sl] = rng.integers(0, 5000, sl.stop - sl.start)
+    a = O.Coo((m, m), [i, k], _cases._values(rng, n, "mixed"))
+    for so, pol, zn in (((0, 1), O.ADD, 1), ((1, 0), O.REPLACE, 0)):
+        A = up(ctx, a)
+        R, st = sp.consolidate(ctx, A, so, pol, zn, stats=True)
+        got, db = down(R), R.dim_beginnings()
+        A.free(); R.free()
+        assert st.digit_bits == 9 and st.passes == 3   # the default took the path this test is about
+        want = orc.consolidate(a, so, pol, zn)
+        assert _cases.same_coo(got, want), (so, pol, zn)
+        assert np.array_equal(db, orc.dim_beginnings(want))
+
+
+def test_more_than_2_30_entries(ctx):
+    """2^30 + 2^20 entries (the reference's cap is 2^31 - 1, algorithm.hpp:419-421; round 1 stopped at 2^30): properties
+    on the device -- count, strict order, value sum, and the first 2^16 outputs against numpy."""
+    import spsparse_b200 as sp
+    import torch
+    from _gpu import DevView
+    n = (1 << 30) + (1 << 20)
+    A = sp.gen_dup_coo(ctx, 0x5EED0002, 0, n, int(0.7 * n), 24, 0)
+    R, st = sp.consolidate(ctx, A, (0, 1), stats=True)
+    (p0, p1), pv = R.device_ptrs()
+    m = R.size()
+    assert st.n_in == n and st.n_kept == n and 0.69 * n < m <= 0.7 * n
+    chunk = 1 << 28
+    prev = -1
+    total = 0.0
+    for c0 in range(0, m, chunk):                   # in pieces: the int64 keys of 7.5e8 entries would not need to fit at once
+        c1 = min(m, c0 + chunk)
+        ti = torch.as_tensor(DevView(p0 + 4 * c0, c1 - c0, "<i4"), device="cuda").long()
+        tk = torch.as_tensor(DevView(p1 + 4 * c0, c1 - c0, "<i4"), device="cuda").long()
+        key = (ti << 24) | tk
+        assert bool((key[1:] > key[:-1]).all().item()) and int(key[0].item()) > prev
+        prev = int(key[-1].item())
+        total += float(torch.as_tensor(DevView(pv + 8 * c0, c1 - c0, "<f8"), device="cuda").sum().item())
+        del ti, tk, key
+    (_, _), av = A.device_ptrs()
+    asum = float(torch.as_tensor(DevView(av, n, "<f8"), device="cuda").sum().item())
+    assert abs(total - asum) <= 1e-9 * asum
+    A.free(); R.free()
 
 
 def test_config2_family_known_answer(ctx):

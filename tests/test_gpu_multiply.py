@@ -423,3 +423,29 @@ def test_rmat_in_row_panels_against_oracle(orc, monkeypatch, hash_min):
     with sp.Context(0) as c2:
         got, n_panels = gpu_mm_panels(c2, 1.0, None, a, ".", None, a, ".", None, max_products=wst["F"] // 40)
     assert 20 <= n_panels <= 41 and _cases.same_coo(got, want)
+
+
+def test_scale_vector_must_be_ascending(ctx):
+    """The reference joins scale vectors as sorted lists without repeats (xiter.hpp:146, 201); one that is not has no
+    defined product there -- here it is an argument error, not a race between the repeated entries."""
+    import spsparse_b200 as sp
+    A = O.Coo((3, 4), [[0, 1, 2], [0, 1, 3]], [1., 2., 3.])
+    B = O.Coo((4, 2), [[0, 1, 3], [0, 1, 1]], [1., 1., 1.])
+    for bad in (O.Coo((4,), [[0, 1, 1, 3]], [1., 2., 5., 1.], (0,)), O.Coo((4,), [[0, 3, 1]], [1., 2., 5.], (0,))):
+        with pytest.raises(sp.SpbError) as e:
+            gpu_mm(ctx, 1.0, None, A, ".", bad, B, ".", None)
+        assert e.value.code == 2
+    V = O.Coo((4,), [[1, 1]], [1., 2.], (0,))      # flagged sorted by the caller, but it is not
+    with pytest.raises(sp.SpbError):
+        gpu_mv(ctx, 1.0, None, A, ".", None, V)
+
+
+def test_pool_trim(ctx):
+    import ctypes
+    import spsparse_b200 as sp
+    A = sp.gen_dup_coo(ctx, 1, 0, 1 << 20, 1 << 19, 12, 0)
+    sp.consolidate(ctx, A, (0, 1)).free()
+    A.free()
+    freed = ctypes.c_uint64()
+    assert ctx.lib.spb_ctx_trim(ctx.h, ctypes.byref(freed)) == 0 and freed.value >= (1 << 20) * 16
+    assert ctx.lib.spb_ctx_trim(ctx.h, ctypes.byref(freed)) == 0 and freed.value == 0
