@@ -250,13 +250,33 @@ def run_ours(args):
             return replicator[0].start(local_ptr, cols, vals, None if os.environ.get("SPB_FULL_REPLICATE") else need)
         return spd.replicate_csr_start(local_ptr, cols, vals, rank, world)
 
+    fetch_ms = []  # per step: (fetch kernel, whole side stream) in ms
     timeline = []  # per step: stream-event times (ms) between the phases of the hot path
     pulled = [None]  # rows of B this rank fetched in the last step (None: everything)
+    # The row-partitioned multiply behind the C ABI (spb_rowpart_*): shards of B published / fetched through peer-mapped
+    # memory by the library's own kernels, no host round trip inside a step.  SPB_LEGACY_DIST=1: the round-1 path
+    # (torch symmetric memory + copy engines driven from Python, spsparse_b200/dist.py), kept for A/B runs.
+    rowpart = [None]
+    mode = {"fetch_all": bool(os.environ.get("SPB_FULL_REPLICATE"))}
+    if not os.environ.get("SPB_LEGACY_DIST"):
+        from spsparse_b200.dist import RowPartition
+        rows_max = max(row_range(m, g, world)[1] - row_range(m, g, world)[0] for g in range(world))
+        rowpart[0] = RowPartition(ctx, rank, world, m, 5 * rows_max + 16)
 
     def hot_path(A_raw, B_raw, w, before_a=None):
         """consolidate(B shard) -> [replicate B, overlapped with] consolidate(A block) -> SpGEMM.
         before_a: called before the first use of A (the end-to-end run makes the stream wait for A's upload there)."""
         from spsparse_b200 import dist as spd
+        if rowpart[0] is not None:
+            if before_a is not None:
+                before_a()
+            Cm, rs = rowpart[0].multiply(1.0, None, A_raw, w, B_raw, None, fetch_all=mode["fetch_all"])
+            pulled[0] = int(rs.rows_fetched)
+            spg = rs.mm.ms_total
+            other = rs.ms_total - (rs.ms_consolidate_b + rs.ms_consolidate_a + rs.ms_fetch_wait + spg)
+            timeline.append([rs.ms_consolidate_b, other, rs.ms_consolidate_a, rs.ms_fetch_wait, spg])
+            fetch_ms.append((rs.ms_fetch, rs.ms_side_stream))
+            return Cm, (rs.a, rs.b, rs.mm)   # views into rs (ctypes keeps it alive)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record(stream)
         Bc, sb = sp.consolidate(ctx, B_raw, sp.ROW_MAJOR, stats=True)
@@ -332,6 +352,30 @@ def run_ours(args):
         del ti, tk
         Cm.free()
         ms = e0.elapsed_time(e1) / args.steps
+        # N > 1: the same step with ALL of B fetched by every rank (what a general, non-banded matrix needs: the
+        # north-star's "B replicated once"), timed the same way, reported under also.full_replicate
+        full_rep = None
+        if world > 1 and rowpart[0] is not None and not mode["fetch_all"] and not args.no_also:
+            mode["fetch_all"] = True
+            n_tl = len(timeline)
+            for _ in range(2):
+                Cx, _ = hot_path(A_raw, B_raw, w); Cx.free()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(args.steps):
+                Cx, fsts = hot_path(A_raw, B_raw, w); Cx.free()
+            f1.record(stream)
+            barrier()
+            tf = torch.tensor([f0.elapsed_time(f1) / args.steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+            full_rep = {"ms_per_step": float(tf.item()), "rows_fetched_rank0": pulled[0],
+                        "timeline_ms_rank0": dict(zip(["consolidate_b", "publish_and_gaps", "consolidate_a", "fetch_wait", "spgemm_incl_prepare"],
+                                                      [float(x) for x in np.mean(np.array(timeline[n_tl + 2:]), axis=0)])),
+                        "fetch_kernel_ms_rank0": float(np.mean([f[0] for f in fetch_ms[-args.steps:]]))}
+            del timeline[n_tl:]
+            mode["fetch_all"] = False
+            Cx, _ = hot_path(A_raw, B_raw, w); Cx.free()   # pulled[0] back to what the headline run fetches
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         sa, sb, st = acc[-1]
         cnt = torch.tensor([st.products, st.nnz_c, sa.n_out + sb.n_out, nA + nB], dtype=torch.float64, device="cuda")
@@ -341,6 +385,9 @@ def run_ours(args):
         ms = float(t.item())
         F, nnzC, cons_out, cons_in = (float(x) for x in cnt.tolist())
         value = F / (ms * 1e-3)
+        if full_rep is not None:
+            full_rep["value"] = F / (full_rep["ms_per_step"] * 1e-3)
+            full_rep["unit"] = UNIT
 
         # per-phase means on this rank
         ms_cons = float(np.mean([a.ms_total + b.ms_total for a, b, _ in acc]))
@@ -473,6 +520,8 @@ def run_ours(args):
         also, cpu = {}, None
         if rank == 0 and world == 1 and not args.no_also:
             also = also_configs(ctx, sp, torch, stream, args, hbm)
+        if rank == 0 and full_rep is not None:
+            also = dict(also, full_replicate=full_rep)
         if rank == 0 and world == 1 and not args.no_cpu:
             cpu = cpu_baseline(args)
 
@@ -485,7 +534,7 @@ def run_ours(args):
                                    "(consolidate A + consolidate B + replicate the needed rows of B + SpGEMM)" if m == 100_000_000 else
                                    f"REDUCED banded triple product, {m} rows (not the headline size)",
                        "rows": m, "nnz_a_raw": cons_in / 2, "nnz_c": nnzC, "products": F,
-                       "partition": f"A rows / B rows split over {world} rank(s); each step every rank fetches, in compressed form (row pointers + cols + vals, 12 B/entry), the rows of B inside the interval hull of the inner indices its block of A references (rank 0 fetched {pulled[0] if pulled[0] is not None else m} of {m} rows; a block whose columns span everything fetches all of B = the plain replicate, SPB_FULL_REPLICATE=1 forces it): pulled from the peers' symmetric memory over NVLink by copy engines (NCCL grouped all-gather of whole shards as fallback), overlapped with consolidate(A)",
+                       "partition": f"A rows / B rows split over {world} rank(s); each step every rank fetches, in compressed form (row pointers + cols + vals, 12 B/entry), the rows of B inside the interval hull of the inner indices its block of A references (rank 0 fetched {pulled[0] if pulled[0] is not None else m} of {m} rows; a block whose columns span everything fetches all of B = the plain replicate, SPB_FULL_REPLICATE=1 forces it and also.full_replicate times it): " + ("fetched by the library's own kernel with loads from the peers' memory (CUDA IPC over NVLink; spb_rowpart_multiply), no host round trip inside a step, overlapped with consolidate(A)" if rowpart[0] is not None else "pulled from the peers' symmetric memory over NVLink by copy engines (SPB_LEGACY_DIST path)"),
                        "l2": "inputs (>= 2 GB per rank) are far larger than the 126 MB L2; no flush needed",
                        "index_type": "int32", "value_type": "f64", "result_fingerprint": fingerprint, "numa_rank0": numa},
             "phases_rank0": {"ms_consolidate_a_plus_b": ms_cons, "ms_spgemm_symbolic_plus_numeric": ms_spgemm,
@@ -497,7 +546,7 @@ def run_ours(args):
                              "spgemm_model_bytes": spgemm_bytes,
                              "spgemm_model_frac": spgemm_bytes / (ms_spgemm * 1e-3) / 1e9 / hbm,
                              "rows_merge": st.rows_merge, "rows_esc": st.rows_esc,
-                             "timeline_ms": dict(zip(["consolidate_b", "replicate_b_launch", "consolidate_a", "replicate_b_wait",
+                             "timeline_ms": dict(zip(["consolidate_b", "publish_and_gaps" if rowpart[0] is not None else "replicate_b_launch", "consolidate_a", "replicate_b_wait",
                                                       "spgemm_incl_prepare"],
                                                      [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)]))},
             "roofline": {"bound": "hbm", "kernel": ("k_radix_pass9<false> (one 9-bit LSD scatter pass, key+value)" if sa.digit_bits == 9 else

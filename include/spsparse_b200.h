@@ -192,6 +192,46 @@ int spb_mm_plan_symbolic(spb_mm_plan *plan, uint64_t panel, spb_mm_stats *stats)
 int spb_mm_plan_panel(spb_mm_plan *plan, uint64_t panel, spb_coo **out, spb_mm_stats *stats /* may be NULL */);
 int spb_mm_plan_destroy(spb_mm_plan *plan);
 
+/* ---- row-partitioned multiply on the GPUs of one node ---------------------------------------
+ * One process per GPU.  The A-row loop of spsparse::multiply carries no state between rows
+ * (multiply_sparse.hpp:192-246): every rank holds a block of the rows of A (blocks that tile A's rows in rank
+ * order) and emits those rows of C = c * diag(si) * A * diag(sj) * B * diag(sk); the ranks' results concatenated
+ * in rank order are the reference's output.  B is sharded by ITS rows (the inner index): rank r owns rows
+ * [row_lo[r], row_lo[r+1]).  Every call each rank consolidates its shard of B,
+ * publishes it in compressed form in a buffer the other ranks have mapped (CUDA IPC, NVLink), and fetches --
+ * with loads from the peers' memory, under its own consolidate(A) -- the rows of B its block of A can
+ * reference: the interval hull of the inner indices of its A entries (a banded block: its shard plus a halo; a
+ * general one: all of B), or all of B when fetch_all != 0.  Sizes, offsets and the hand-shake stay on the
+ * devices; the host is not involved between the kernels of a step.  The reference has no counterpart (it is
+ * single-process); SURVEY.md section 8e.
+ *
+ * spb_rowpart_create   collective: same row_lo[n_ranks+1] (row_lo[0] = 0) and cap_entries (upper bound of the
+ *                      consolidated entries of any rank's shard of B) on every rank
+ * spb_rowpart_handle   64-byte handle of this rank's shard buffer; the caller all-gathers the handles of all ranks
+ *                      (MPI, torch.distributed, a file -- any means) ...
+ * spb_rowpart_attach   ... and hands the n_ranks handles, in rank order, to every rank
+ * spb_rowpart_multiply collective: every rank calls it once per step, also when its own block is empty.  A and B
+ *                      are this rank's raw blocks (any order, duplicates allowed; blocks already flagged sorted
+ *                      {0,1} are used as they are), indices are GLOBAL.  No transposes: op(A) = A, op(B) = B. */
+typedef struct spb_rowpart spb_rowpart;
+typedef struct {
+    spb_consolidate_stats a, b;   /* this rank's block of A, its shard of B */
+    spb_mm_stats mm;
+    uint64_t rows_fetched, entries_fetched;   /* rows / entries of B this rank fetched (own shard included) */
+    float ms_consolidate_a, ms_consolidate_b;
+    float ms_fetch;         /* duration of the fetch kernel on its own stream (overlaps consolidate(A)) */
+    float ms_side_stream;   /* hull + wait for the peers + fetch + scale vector, on the side stream */
+    float ms_fetch_wait;    /* what the multiply still had to wait for after consolidate(A) */
+    float ms_total;
+} spb_rowpart_stats;
+int spb_rowpart_create(spb_ctx *ctx, int rank, int n_ranks, const uint64_t *row_lo, uint64_t cap_entries, spb_rowpart **out);
+int spb_rowpart_handle(spb_rowpart *rp, void *handle, uint64_t handle_bytes /* >= 64 */);
+int spb_rowpart_attach(spb_rowpart *rp, const void *handles /* n_ranks x handle_bytes */, uint64_t handle_bytes);
+int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *scalei, const spb_coo *A_block, const spb_coo *scalej,
+                         const spb_coo *B_shard, const spb_coo *scalek, int policy, int zero_nan, int fetch_all,
+                         spb_coo **out, spb_rowpart_stats *stats /* may be NULL */);
+int spb_rowpart_destroy(spb_rowpart *rp);
+
 /* ---- multiply, matrix*vector  (spsparse::multiply, multiply_sparse.hpp:281-365) -------- */
 int spb_multiply_mv(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,
                     const spb_coo *scalej, const spb_coo *V, int policy, int zero_nan, spb_coo **out);

@@ -37,6 +37,13 @@ class MMStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class RowpartStats(C.Structure):
+    _fields_ = [("a", ConsolidateStats), ("b", ConsolidateStats), ("mm", MMStats),
+                ("rows_fetched", C.c_uint64), ("entries_fetched", C.c_uint64),
+                ("ms_consolidate_a", C.c_float), ("ms_consolidate_b", C.c_float), ("ms_fetch", C.c_float),
+                ("ms_side_stream", C.c_float), ("ms_fetch_wait", C.c_float), ("ms_total", C.c_float)]
+
+
 # every symbol include/spsparse_b200.h declares: (name, restype, argtypes)
 SIGNATURES = {
     "spb_last_error": (C.c_char_p, []),
@@ -75,6 +82,12 @@ SIGNATURES = {
     "spb_mm_plan_symbolic": (C.c_int, [vp, C.c_uint64, C.POINTER(MMStats)]),
     "spb_mm_plan_panel": (C.c_int, [vp, C.c_uint64, C.POINTER(vp), C.POINTER(MMStats)]),
     "spb_mm_plan_destroy": (C.c_int, [vp]),
+    "spb_rowpart_create": (C.c_int, [vp, C.c_int, C.c_int, u64p, C.c_uint64, C.POINTER(vp)]),
+    "spb_rowpart_handle": (C.c_int, [vp, vp, C.c_uint64]),
+    "spb_rowpart_attach": (C.c_int, [vp, vp, C.c_uint64]),
+    "spb_rowpart_multiply": (C.c_int, [vp, C.c_double, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp),
+                                       C.POINTER(RowpartStats)]),
+    "spb_rowpart_destroy": (C.c_int, [vp]),
     "spb_multiply_mv": (C.c_int, [vp, C.c_double, vp, vp, C.c_char, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     "spb_gen_dup_coo": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(vp)]),
     "spb_gen_banded": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(vp)]),

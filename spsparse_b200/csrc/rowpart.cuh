@@ -1,0 +1,202 @@
+// rowpart.cuh -- device side of the row-partitioned multiply on several GPUs of one node (one process per GPU).
+//
+// The reference is single-process; what is split here is its A-row loop (slib/spsparse/multiply_sparse.hpp:192-246 carries no
+// state from one row of A to the next): rank r owns rows [row_lo[r], row_lo[r+1]) of op(A) and the same rows of B (B's rows
+// are the inner index).  Every step each rank consolidates its shard of B, PUBLISHES it in compressed form (local row
+// pointers + column + value of every entry, 12 B per entry) in a buffer that the other ranks have mapped (CUDA IPC over
+// NVLink), and FETCHES the rows of B that its block of A can reference -- the interval hull [lo, hi] of the inner indices of
+// its A entries: everything for a general matrix, its own shard plus a halo for a banded one -- with plain loads from the
+// peers' memory, while consolidate(A) runs.  No host round trip is involved: sizes, offsets and the hand-shake (ready /
+// done step counters written into the peers' memory) all stay on the devices.
+#pragma once
+#include "common.cuh"
+
+constexpr int RP_MAX_RANKS = 16;
+constexpr int RP_FLAG_WORDS = 2 * RP_MAX_RANKS;    // ready[RP_MAX_RANKS], done[RP_MAX_RANKS]
+constexpr u64 RP_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;  // a peer that does not show up within 20 s: give up (error flag), never hang
+
+// One rank's exported region as it is mapped in this process.
+struct RpRegion {
+    u64 *flags;    // [0 .. RP_MAX_RANKS) ready[q]: last step whose shard rank q has published (q writes it into MY region)
+                   // [RP_MAX_RANKS .. )  done[q]: last step in which rank q has finished reading MY shard
+    u32 *ptr;      // [cap_rows + 1] entry offset, inside the shard, of the first entry of each of its rows (+ sentinel)
+    i32 *cols;     // [cap_entries]
+    double *vals;  // [cap_entries]
+};
+
+struct RpArgs {
+    int rank, n_ranks;
+    u64 step;                         // 1, 2, ...
+    u64 row_lo[RP_MAX_RANKS + 1];
+    RpRegion reg[RP_MAX_RANKS];       // reg[rank] is this rank's own region
+    u32 *error;                       // set to 1 when a wait timed out
+};
+
+__device__ __forceinline__ u64 rp_now_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ u64 rp_ld_acquire_sys(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rp_st_release_sys(u64 *p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spins until *p >= want; false (and *error = 1) on time-out
+__device__ __forceinline__ bool rp_wait_ge(const u64 *p, u64 want, u32 *error) {
+    const u64 t0 = rp_now_ns();
+    while (rp_ld_acquire_sys(p) < want) {
+        __nanosleep(200);
+        if (rp_now_ns() - t0 > RP_TIMEOUT_NS) { *error = 1u; return false; }
+    }
+    return true;
+}
+
+// ---- publish: wait until every peer has finished reading the previous publication, copy, raise the ready counters --------
+__global__ void k_rp_wait_done(RpArgs a) {
+    const int q = threadIdx.x;
+    if (q < a.n_ranks && q != a.rank && a.step > 1)
+        rp_wait_ge(a.reg[a.rank].flags + RP_MAX_RANKS + q, a.step - 1, a.error);
+}
+
+// local_ptr: rows_local + 1 offsets into (cols, vals) of the consolidated shard (spb_coo_dense_ptr_range); published re-based to 0
+__global__ void __launch_bounds__(512) k_rp_publish(RpArgs a, const u32 *__restrict__ local_ptr, u32 rows_local,
+                                                    const i32 *__restrict__ cols, const double *__restrict__ vals) {
+    const RpRegion me = a.reg[a.rank];
+    const u32 e0 = local_ptr[0], n = local_ptr[rows_local] - e0;
+    const u64 stride = (u64)gridDim.x * blockDim.x, t0 = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (u64 t = t0; t <= rows_local; t += stride) me.ptr[t] = local_ptr[t] - e0;
+    for (u64 t = t0; t < n; t += stride) {
+        me.cols[t] = ld_stream_i32(cols + e0 + t);
+        me.vals[t] = ld_stream_f64(vals + e0 + t);
+    }
+}
+
+__global__ void k_rp_signal_ready(RpArgs a) {
+    const int q = threadIdx.x;
+    __threadfence_system();
+    if (q < a.n_ranks) rp_st_release_sys(a.reg[q].flags + a.rank, a.step);   // ready[rank] in rank q's region (also my own)
+}
+
+// ---- interval hull of the inner indices of this rank's block of A (raw, unconsolidated entries) ------------------------------
+// hull[0] = min, hull[1] = max (initialised to ~0 / 0 by the host); an empty block leaves lo > hi = nothing to fetch
+__global__ void k_rp_hull(const i32 *__restrict__ a_inner, u64 n, u64 *hull) {
+    u32 lo = 0xffffffffu, hi = 0;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
+        const u32 j = (u32)ld_stream_i32(a_inner + t);
+        lo = min(lo, j);
+        hi = max(hi, j);
+    }
+    lo = __reduce_min_sync(SPB_FULL_MASK, lo);
+    hi = __reduce_max_sync(SPB_FULL_MASK, hi);
+    if (lane_id() == 0 && lo <= hi) {
+        atomicMin((ull *)&hull[0], (ull)lo);
+        atomicMax((ull *)&hull[1], (ull)hi);
+    }
+}
+__global__ void k_rp_hull_set(u64 *hull, u64 lo, u64 hi) { hull[0] = lo; hull[1] = hi; }
+
+// ---- fetch: the rows lo..hi of B from whoever owns them, concatenated in row order ----------------------------------------------
+// g_ptr is indexed by the ABSOLUTE row: g_ptr[j] for j in [lo, hi + 1] is written (offsets into g_cols / g_vals), nothing else --
+// the multiply only ever looks up the inner indices of this rank's A entries, which lie inside the hull.  Work and traffic are
+// O(rows and entries fetched); only the allocation is as long as B has rows.
+// info[0] = entries fetched, info[1] = rows fetched, info[2] = blocks finished (zeroed by the host)
+constexpr int RP_PULL_THREADS = 512;
+constexpr int RP_PULL_UNROLL = 8;
+__global__ void __launch_bounds__(RP_PULL_THREADS) k_rp_pull(RpArgs a, const u64 *__restrict__ hull, u32 *g_ptr, i32 *g_cols,
+                                                             double *g_vals, u64 cap_entries, u64 *info) {
+    __shared__ u64 s_rlo[RP_MAX_RANKS], s_rhi[RP_MAX_RANKS];   // rows [rlo, rhi) of peer g are fetched
+    __shared__ u32 s_elo[RP_MAX_RANKS], s_cnt[RP_MAX_RANKS];   // its entries [elo, elo + cnt)
+    __shared__ u64 s_base[RP_MAX_RANKS + 1];                   // where they go
+    __shared__ u32 s_last;
+    const u32 tid = threadIdx.x;
+    const u64 lo = hull[0], hi = hull[1];
+    if (tid < 32) {
+        // every block works the plan out for itself (two pointer values per peer): no block waits for another block
+        const int g = (int)tid;
+        u64 rlo = 0, rhi = 0;
+        u32 elo = 0, cnt = 0;
+        if (g < a.n_ranks && lo <= hi) {
+            rlo = max(lo, a.row_lo[g]);
+            rhi = min(hi + 1, a.row_lo[g + 1]);
+            if (rlo < rhi) {
+                bool ok = rp_wait_ge(a.reg[a.rank].flags + g, a.step, a.error);   // peer g has published this step's shard
+                if (ok) {
+                    const u32 *p = a.reg[g].ptr;
+                    elo = __ldcg(p + (rlo - a.row_lo[g]));
+                    cnt = __ldcg(p + (rhi - a.row_lo[g])) - elo;
+                } else rhi = rlo;
+            } else rhi = rlo;
+        }
+        const u64 incl = warp_incl_scan((u64)cnt);
+        if (g < a.n_ranks) { s_rlo[g] = rlo; s_rhi[g] = rhi; s_elo[g] = elo; s_cnt[g] = cnt; s_base[g] = incl - cnt; }
+        if (g == a.n_ranks - 1) s_base[a.n_ranks] = incl;
+    }
+    __syncthreads();
+    const u64 total = s_base[a.n_ranks];
+    const bool overflow = total > cap_entries;   // never overrun the buffers: nothing is copied, the host reports it
+    if (overflow && tid == 0) *a.error = 2u;
+    // entries: chunks of RP_PULL_THREADS * RP_PULL_UNROLL, all loads of a chunk in flight before the first store
+    constexpr u64 CHUNK = (u64)RP_PULL_THREADS * RP_PULL_UNROLL;
+    for (int g = 0; g < a.n_ranks && !overflow; ++g) {
+        const u32 cnt = s_cnt[g];
+        if (!cnt) continue;
+        const i32 *sc = a.reg[g].cols + s_elo[g];
+        const double *sv = a.reg[g].vals + s_elo[g];
+        i32 *dc = g_cols + s_base[g];
+        double *dv = g_vals + s_base[g];
+        for (u64 c0 = (u64)blockIdx.x * CHUNK; c0 < cnt; c0 += (u64)gridDim.x * CHUNK) {
+            i32 k[RP_PULL_UNROLL];
+            double v[RP_PULL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < RP_PULL_UNROLL; ++u) {
+                const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
+                if (t < cnt) { k[u] = __ldcg(sc + t); v[u] = __ldcg(sv + t); }   // L2 only: the owner rewrites these every step
+            }
+#pragma unroll
+            for (int u = 0; u < RP_PULL_UNROLL; ++u) {
+                const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
+                if (t < cnt) { dc[t] = k[u]; dv[t] = v[u]; }
+            }
+        }
+        // row pointers of the fetched rows, re-based to where the entries went
+        const u32 *p = a.reg[g].ptr;
+        const u64 rlo = s_rlo[g], rhi = s_rhi[g], r0 = a.row_lo[g];
+        const u32 shift = (u32)s_base[g] - s_elo[g];   // wraps consistently in 32 bits
+        for (u64 j = rlo + (u64)blockIdx.x * blockDim.x + tid; j < rhi; j += (u64)gridDim.x * blockDim.x)
+            g_ptr[j] = __ldcg(p + (j - r0)) + shift;
+    }
+    if (blockIdx.x == 0 && tid == 0 && lo <= hi && !overflow) g_ptr[hi + 1] = (u32)total;
+    // the last block to finish tells every peer that this rank is done with its shard for this step
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd((ull *)&info[2], 1ull) == (ull)gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        if (tid == 0) { info[0] = total; info[1] = lo <= hi ? hi - lo + 1 : 0; }
+        __threadfence_system();
+        if (tid < (u32)a.n_ranks && (int)tid != a.rank) rp_st_release_sys(a.reg[tid].flags + RP_MAX_RANKS + a.rank, a.step);
+    }
+}
+
+// ---- scale vector for the fetched range only: dense[j] / mask[j] for j in [lo, hi] -----------------------------------------
+__global__ void k_rp_zero_range(const u64 *__restrict__ hull, double *dense, unsigned char *mask) {
+    const u64 lo = hull[0], hi = hull[1];
+    if (lo > hi) return;
+    for (u64 j = lo + (u64)blockIdx.x * blockDim.x + threadIdx.x; j <= hi; j += (u64)gridDim.x * blockDim.x) {
+        dense[j] = 0.0;
+        mask[j] = 0;
+    }
+}
+__global__ void k_rp_densify_range(const i32 *__restrict__ idx, const double *__restrict__ val, u64 n, const u64 *__restrict__ hull,
+                                   double *dense, unsigned char *mask, u32 *bad) {
+    const u64 lo = hull[0], hi = hull[1];
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (u64)gridDim.x * blockDim.x) {
+        const u64 j = (u64)(u32)idx[t];
+        if (t && idx[t - 1] >= idx[t]) *bad = 1u;
+        if (j >= lo && j <= hi) { dense[j] = val[t]; mask[j] = 1; }
+    }
+}

@@ -24,6 +24,7 @@
 #include "scan.cuh"
 #include "spgemm.cuh"
 #include "dense_ops.cuh"
+#include "rowpart.cuh"
 
 thread_local std::string g_last_error;
 
@@ -906,9 +907,15 @@ template <typename K> static int allow_ballast(K kernel) {
 }
 
 // A: consolidated, sorted by (a_row_dim, other).  B: consolidated, sorted by (b_inner_dim, other).
+struct PreScale {   // scalej already in dense form (the row-partitioned multiply keeps it across steps and only rewrites the needed range)
+    const double *sj;
+    const unsigned char *sj_mask;
+};
+
 static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_coo *A, int a_row_dim,
                          const spb_coo *sj, const spb_coo *B, int b_inner_dim, const spb_coo *sk,
-                         spb_coo *out, spb_mm_stats *st, Timer &tm, int t_begin, bool symbolic_only = false) {
+                         spb_coo *out, spb_mm_stats *st, Timer &tm, int t_begin, bool symbolic_only = false,
+                         const PreScale *pre = nullptr) {
     Scratch ws(ctx);
     const int a_in = 1 - a_row_dim, b_col = 1 - b_inner_dim;
     const u64 m_rows = A->shape[a_row_dim], n_inner = A->shape[a_in], n_cols = B->shape[b_col];
@@ -928,7 +935,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     u32 *bad_vec;
     CKR(ws.zeroed(&bad_vec, 1));
     if (si) { CKR(densify(ctx, ws, si, m_rows, &d, nullptr, bad_vec)); m.si = d; }
-    if (sj) { CKR(densify(ctx, ws, sj, n_inner, &d, &mask, bad_vec)); m.sj = d; m.sj_mask = mask; }
+    if (pre) { m.sj = pre->sj; m.sj_mask = pre->sj_mask; }
+    else if (sj) { CKR(densify(ctx, ws, sj, n_inner, &d, &mask, bad_vec)); m.sj = d; m.sj_mask = mask; }
     if (sk) { CKR(densify(ctx, ws, sk, n_cols, &d, nullptr, bad_vec)); m.sk = d; }
     const int t_prep = tm.mark();
     double h0 = now_ms();
@@ -1311,7 +1319,6 @@ int spb_coo_dense_ptr_range(spb_ctx *ctx, const spb_coo *a_const, uint64_t lo, u
         CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
         if (ri.nrows) ++ctx->launches, k_scatter_row_len_range<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, lo, hi, len);
         CKR((exclusive_scan<u32, u32>(ctx, ws, len, a->range_ptr, span + 1)));  // writes span + 2 values
-        CK(cudaStreamSynchronize(ctx->stream));
         a->range_lo = lo; a->range_hi = hi;
     }
     *d_ptr = a->range_ptr + 1;
@@ -1925,6 +1932,293 @@ int spb_gen_vector(spb_ctx *ctx, uint64_t seed, uint64_t dim, spb_coo **out) {
     const int so[1] = {0};
     set_order(*out, so);
     return SPB_OK;
+}
+
+}  // extern "C"
+
+// ==================================================================================================
+// row-partitioned multiply on the GPUs of one node (one process per GPU); device side in rowpart.cuh
+// ==================================================================================================
+struct spb_rowpart {
+    spb_ctx *ctx;
+    int rank, n_ranks;
+    u64 row_lo[RP_MAX_RANKS + 1];
+    u64 m;                       // rows of B = inner dimension
+    u64 cap_entries, cap_rows;   // per-rank capacity of the published shard (the same on every rank)
+    size_t off_ptr, off_cols, off_vals, region_bytes;
+    void *region;                // this rank's exported allocation
+    void *peer_base[RP_MAX_RANKS];
+    bool attached;
+    cudaStream_t side;
+    cudaEvent_t ev_main, ev_pub, ev_pull, ev_t[4];
+    u64 step;
+    u32 *g_ptr;                  // [m + 2] row pointer of the fetched rows, indexed by the absolute row
+    i32 *g_cols;
+    double *g_vals;
+    u64 g_cap;
+    u64 *hull, *info;            // device: [2], [4]
+    u32 *error;                  // device
+    double *sj_dense;            // [m] dense scalej; only the fetched range is rewritten each step
+    unsigned char *sj_mask;
+};
+
+static size_t rp_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void rp_layout(spb_rowpart *rp) {
+    rp->off_ptr = rp_align(RP_FLAG_WORDS * sizeof(u64));
+    rp->off_cols = rp->off_ptr + rp_align((rp->cap_rows + 2) * sizeof(u32));
+    rp->off_vals = rp->off_cols + rp_align(rp->cap_entries * sizeof(i32));
+    rp->region_bytes = rp->off_vals + rp_align(rp->cap_entries * sizeof(double));
+}
+
+static void rp_args(const spb_rowpart *rp, RpArgs *a) {
+    memset(a, 0, sizeof *a);
+    a->rank = rp->rank; a->n_ranks = rp->n_ranks; a->step = rp->step; a->error = rp->error;
+    for (int g = 0; g <= rp->n_ranks; ++g) a->row_lo[g] = rp->row_lo[g];
+    for (int g = 0; g < rp->n_ranks; ++g) {
+        char *b = (char *)rp->peer_base[g];
+        a->reg[g].flags = (u64 *)b;
+        a->reg[g].ptr = (u32 *)(b + rp->off_ptr);
+        a->reg[g].cols = (i32 *)(b + rp->off_cols);
+        a->reg[g].vals = (double *)(b + rp->off_vals);
+    }
+}
+
+extern "C" {
+
+int spb_rowpart_destroy(spb_rowpart *rp) {
+    if (!rp) return SPB_OK;
+    cudaSetDevice(rp->ctx->device);
+    cudaStreamSynchronize(rp->ctx->stream);
+    if (rp->side) cudaStreamSynchronize(rp->side);
+    for (int g = 0; g < rp->n_ranks; ++g)
+        if (rp->attached && g != rp->rank && rp->peer_base[g]) cudaIpcCloseMemHandle(rp->peer_base[g]);
+    cudaFree(rp->region);
+    cudaFree(rp->g_ptr); cudaFree(rp->g_cols); cudaFree(rp->g_vals);
+    cudaFree(rp->hull); cudaFree(rp->sj_dense); cudaFree(rp->sj_mask);
+    if (rp->side) cudaStreamDestroy(rp->side);
+    for (cudaEvent_t e : {rp->ev_main, rp->ev_pub, rp->ev_pull, rp->ev_t[0], rp->ev_t[1], rp->ev_t[2], rp->ev_t[3]})
+        if (e) cudaEventDestroy(e);
+    delete rp;
+    return SPB_OK;
+}
+
+int spb_rowpart_create(spb_ctx *ctx, int rank, int n_ranks, const uint64_t *row_lo, uint64_t cap_entries, spb_rowpart **out) {
+    if (!ctx || !row_lo || !out) return spb_fail(SPB_ERR_ARG, "spb_rowpart_create: null argument");
+    if (n_ranks < 1 || n_ranks > RP_MAX_RANKS || rank < 0 || rank >= n_ranks)
+        return spb_fail(SPB_ERR_ARG, "spb_rowpart_create: rank %d of %d (at most %d ranks)", rank, n_ranks, RP_MAX_RANKS);
+    for (int g = 0; g < n_ranks; ++g)
+        if (row_lo[g] > row_lo[g + 1]) return spb_fail(SPB_ERR_ARG, "spb_rowpart_create: row offsets must not decrease");
+    if (row_lo[0] != 0 || row_lo[n_ranks] > (1ull << 31)) return spb_fail(SPB_ERR_ARG, "spb_rowpart_create: bad row offsets");
+    if (cap_entries >= (1ull << 31) || cap_entries * (u64)n_ranks >= (1ull << 32))
+        return spb_fail(SPB_ERR_TOO_LARGE, "spb_rowpart_create: a shard holds fewer than 2^31 entries, all of B fewer than 2^32");
+    CK(cudaSetDevice(ctx->device));
+    spb_rowpart *rp = new spb_rowpart();
+    memset(rp, 0, sizeof *rp);
+    rp->ctx = ctx; rp->rank = rank; rp->n_ranks = n_ranks;
+    u64 rows_max = 0;
+    for (int g = 0; g <= n_ranks; ++g) rp->row_lo[g] = row_lo[g];
+    for (int g = 0; g < n_ranks; ++g) rows_max = std::max<u64>(rows_max, row_lo[g + 1] - row_lo[g]);
+    rp->m = row_lo[n_ranks];
+    rp->cap_entries = cap_entries ? cap_entries : 1;
+    rp->cap_rows = rows_max;
+    rp_layout(rp);
+    *out = rp;
+    auto body = [&]() -> int {
+        if (n_ranks > 1) {
+            CK(cudaMalloc(&rp->region, rp->region_bytes));
+            CK(cudaMemset(rp->region, 0, rp->off_cols));   // step counters and pointers start at 0
+            rp->g_cap = rp->cap_entries * (u64)n_ranks;
+            CK(cudaMalloc((void **)&rp->g_ptr, (rp->m + 2) * sizeof(u32)));
+            CK(cudaMalloc((void **)&rp->g_cols, rp->g_cap * sizeof(i32)));
+            CK(cudaMalloc((void **)&rp->g_vals, rp->g_cap * sizeof(double)));
+            CK(cudaMalloc((void **)&rp->hull, 8 * sizeof(u64)));
+            CK(cudaMemset(rp->hull, 0, 8 * sizeof(u64)));
+            rp->info = rp->hull + 2;
+            rp->error = (u32 *)(rp->hull + 6);
+            int lo_pri = 0, hi_pri = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+            CK(cudaStreamCreateWithPriority(&rp->side, cudaStreamNonBlocking, hi_pri));   // small kernels: ahead of the sort's blocks
+            CK(cudaEventCreateWithFlags(&rp->ev_main, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&rp->ev_pub, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&rp->ev_pull, cudaEventDisableTiming));
+            for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&rp->ev_t[i]));
+        }
+        rp->peer_base[rank] = rp->region;
+        rp->attached = n_ranks == 1;
+        return 0;
+    };
+    int rc = body();
+    if (rc) { spb_rowpart_destroy(rp); *out = nullptr; }
+    return rc;
+}
+
+int spb_rowpart_handle(spb_rowpart *rp, void *handle, uint64_t handle_bytes) {
+    if (!rp || !handle) return spb_fail(SPB_ERR_ARG, "spb_rowpart_handle: null argument");
+    if (handle_bytes < sizeof(cudaIpcMemHandle_t)) return spb_fail(SPB_ERR_ARG, "spb_rowpart_handle: %zu bytes needed", sizeof(cudaIpcMemHandle_t));
+    memset(handle, 0, handle_bytes);
+    if (rp->n_ranks == 1) return SPB_OK;
+    CK(cudaSetDevice(rp->ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, rp->region));
+    memcpy(handle, &h, sizeof h);
+    return SPB_OK;
+}
+
+int spb_rowpart_attach(spb_rowpart *rp, const void *handles, uint64_t handle_bytes) {
+    if (!rp || !handles) return spb_fail(SPB_ERR_ARG, "spb_rowpart_attach: null argument");
+    if (handle_bytes < sizeof(cudaIpcMemHandle_t)) return spb_fail(SPB_ERR_ARG, "spb_rowpart_attach: bad handle size");
+    if (rp->attached) return SPB_OK;
+    CK(cudaSetDevice(rp->ctx->device));
+    for (int g = 0; g < rp->n_ranks; ++g) {
+        if (g == rp->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)g * handle_bytes, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return spb_fail(SPB_ERR_CUDA, "cannot map the shard buffer of rank %d (cudaIpcOpenMemHandle: %s); the ranks must be "
+                            "processes on one node whose GPUs have peer access", g, cudaGetErrorString(e));
+        rp->peer_base[g] = p;
+    }
+    rp->attached = true;
+    return SPB_OK;
+}
+
+int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb_coo *A, const spb_coo *sj, const spb_coo *B,
+                         const spb_coo *sk, int policy, int zero_nan, int fetch_all, spb_coo **out, spb_rowpart_stats *stats) {
+    if (!rp || !A || !B || !out) return spb_fail(SPB_ERR_ARG, "spb_rowpart_multiply: null argument");
+    if (!rp->attached) return spb_fail(SPB_ERR_ARG, "spb_rowpart_multiply: spb_rowpart_attach has not been called");
+    if (A->rank != 2 || B->rank != 2) return spb_fail(SPB_ERR_ARG, "A and B must be rank-2 arrays");
+    if (policy < 0 || policy > 2) return spb_fail(SPB_ERR_ARG, "unknown duplicate policy %d", policy);
+    CKR(scale_ok(si, "scalei")); CKR(scale_ok(sj, "scalej")); CKR(scale_ok(sk, "scalek"));
+    spb_ctx *ctx = rp->ctx;
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (A->shape[1] != B->shape[0])  // multiply_sparse.hpp:172-174
+        return spb_fail(SPB_ERR_INNER_DIM, "Inner dimensions for A (%ld) and B (%ld) must match!", (long)A->shape[1], (long)B->shape[0]);
+    if (B->shape[0] != rp->m) return spb_fail(SPB_ERR_ARG, "B has %llu rows, the partition was made for %llu", (ull)B->shape[0], (ull)rp->m);
+    const int row_major[2] = {0, 1};
+    const u64 shape[2] = {A->shape[0], B->shape[1]};
+    spb_coo *r = nullptr;
+    CKR(coo_new(ctx, 2, shape, 0, false, &r));
+    r->owned = true;
+    *out = r;
+    Timer tm(ctx->stream);
+    const int t0 = tm.mark();
+    spb_coo *Ac = nullptr, *Bc = nullptr;
+    const int rank = rp->rank, n_ranks = rp->n_ranks;
+    const u64 r0 = rp->row_lo[rank], r1 = rp->row_lo[rank + 1];
+    // Every rank runs every step of the hand-shake, also when its own operands are empty: the peers count on it.
+    const bool nothing = C == 0.0 || (si && si->n == 0) || (sj && sj->n == 0) || (sk && sk->n == 0);   // multiply_sparse.hpp:178-184
+    auto body = [&]() -> int {
+        // ---- B shard: consolidate by (row, col); already consolidated shards are used as they are -------------------------
+        const spb_coo *Buse = B;
+        if (!(B->sort_order[0] == 0 && B->sort_order[1] == 1)) {
+            CKR(consolidate_core(ctx, B, row_major, row_major, policy, true, zero_nan, &Bc, stats ? &stats->b : nullptr));
+            Buse = Bc;
+        }
+        const int t_b = tm.mark();
+        if (n_ranks == 1) {
+            const spb_coo *Ause = A;
+            if (!(A->sort_order[0] == 0 && A->sort_order[1] == 1)) {
+                CKR(consolidate_core(ctx, A, row_major, row_major, policy, true, zero_nan, &Ac, stats ? &stats->a : nullptr));
+                Ause = Ac;
+            }
+            const int t_a = tm.mark();
+            if (!nothing && Ause->n && Buse->n)
+                CKR(multiply_core(ctx, C, si, Ause, 0, sj, Buse, 0, sk, r, stats ? &stats->mm : nullptr, tm, t_a));
+            if (stats) {
+                stats->ms_consolidate_b = tm.ms(t0, t_b); stats->ms_consolidate_a = tm.ms(t_b, t_a);
+                stats->rows_fetched = rp->m; stats->entries_fetched = Buse->n;
+                const int t_end = tm.mark();
+                stats->ms_total = tm.ms(t0, t_end);
+            }
+            return 0;
+        }
+        if (Buse->n > rp->cap_entries)
+            return spb_fail(SPB_ERR_TOO_LARGE, "the shard of B has %llu entries, the partition was created for %llu", (ull)Buse->n, (ull)rp->cap_entries);
+        ++rp->step;
+        RpArgs ra;
+        rp_args(rp, &ra);
+        // ---- publish the shard (main stream) -------------------------------------------------------------------------------
+        u32 *local_ptr = nullptr;
+        CKR(spb_coo_dense_ptr_range(ctx, Buse, r0, r1, &local_ptr));
+        CK(cudaMemsetAsync(rp->info, 0, 6 * sizeof(u64), ctx->stream));   // counters of the fetch, error and bad-vector flags
+        CK(cudaEventRecord(rp->ev_main, ctx->stream));   // A (and B) are complete on the caller's stream from here on
+        ++ctx->launches, k_rp_wait_done<<<1, 32, 0, ctx->stream>>>(ra);
+        ++ctx->launches, k_rp_publish<<<(u32)ctx->sm_count * 2, 512, 0, ctx->stream>>>(ra, local_ptr, (u32)(r1 - r0), Buse->idx[1], Buse->val);
+        ++ctx->launches, k_rp_signal_ready<<<1, 32, 0, ctx->stream>>>(ra);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(rp->ev_pub, ctx->stream));
+        // ---- side stream: hull of A's inner indices, fetch of those rows of B, scalej for that range ---------------------
+        CK(cudaStreamWaitEvent(rp->side, rp->ev_main, 0));
+        CK(cudaEventRecord(rp->ev_t[0], rp->side));
+        if (fetch_all && rp->m) ++ctx->launches, k_rp_hull_set<<<1, 1, 0, rp->side>>>(rp->hull, 0ull, rp->m - 1);
+        else {
+            ++ctx->launches, k_rp_hull_set<<<1, 1, 0, rp->side>>>(rp->hull, ~0ull, 0ull);   // empty until an entry of A is seen
+            if (A->n) ++ctx->launches, k_rp_hull<<<grid_for(A->n, 256, (u32)ctx->sm_count * 4), 256, 0, rp->side>>>(A->idx[1], A->n, rp->hull);
+        }
+        CK(cudaStreamWaitEvent(rp->side, rp->ev_pub, 0));
+        CK(cudaEventRecord(rp->ev_t[1], rp->side));
+        ++ctx->launches, k_rp_pull<<<fetch_all ? 96u : 32u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, rp->g_cols, rp->g_vals, rp->g_cap, rp->info);
+        CK(cudaEventRecord(rp->ev_t[2], rp->side));
+        u32 *bad_vec = (u32 *)(rp->hull + 7);
+        if (sj) {
+            if (!rp->sj_dense) {
+                CK(cudaMalloc((void **)&rp->sj_dense, (rp->m ? rp->m : 1) * sizeof(double)));
+                CK(cudaMalloc((void **)&rp->sj_mask, rp->m ? rp->m : 1));
+            }
+            ++ctx->launches, k_rp_zero_range<<<(u32)ctx->sm_count, 512, 0, rp->side>>>(rp->hull, rp->sj_dense, rp->sj_mask);
+            if (sj->n) ++ctx->launches, k_rp_densify_range<<<grid_for(sj->n, 256, (u32)ctx->sm_count * 4), 256, 0, rp->side>>>(sj->idx[0], sj->val, sj->n, rp->hull, rp->sj_dense, rp->sj_mask, bad_vec);
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(rp->ev_t[3], rp->side));
+        CK(cudaEventRecord(rp->ev_pull, rp->side));
+        // ---- A block (main stream, while the fetch runs) ---------------------------------------------------------------------
+        const spb_coo *Ause = A;
+        if (!(A->sort_order[0] == 0 && A->sort_order[1] == 1)) {
+            CKR(consolidate_core(ctx, A, row_major, row_major, policy, true, zero_nan, &Ac, stats ? &stats->a : nullptr));
+            Ause = Ac;
+        }
+        const int t_a = tm.mark();
+        CK(cudaStreamWaitEvent(ctx->stream, rp->ev_pull, 0));
+        const int t_w = tm.mark();
+        // ---- multiply against the fetched rows ----------------------------------------------------------------------------------
+        spb_coo Bv;
+        memset(&Bv, 0, sizeof Bv);
+        Bv.rank = 2; Bv.shape[0] = B->shape[0]; Bv.shape[1] = B->shape[1];
+        Bv.n = Buse->n * (u64)n_ranks;          // estimate (kernel-variant heuristics only); the count fetched is in stats
+        Bv.idx[0] = nullptr; Bv.idx[1] = rp->g_cols; Bv.val = rp->g_vals;
+        Bv.sort_order[0] = 0; Bv.sort_order[1] = 1;
+        Bv.dense_ptr = rp->g_ptr; Bv.dense_ptr_owned = false;
+        PreScale pre = {rp->sj_dense, rp->sj_mask};
+        if (!nothing && Ause->n)
+            CKR(multiply_core(ctx, C, si, Ause, 0, sj, &Bv, 0, sk, r, stats ? &stats->mm : nullptr, tm, t_w, false, sj ? &pre : nullptr));
+        u64 h_info[6];
+        CK(cudaMemcpyAsync(h_info, rp->info, sizeof h_info, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const u32 h_err = (u32)h_info[4], h_bad = (u32)(h_info[5]);
+        if (h_err == 2) return spb_fail(SPB_ERR_TOO_LARGE, "the rows of B this rank needs hold %llu entries; the partition's buffers hold %llu", (ull)h_info[0], (ull)rp->g_cap);
+        if (h_err) return spb_fail(SPB_ERR_CUDA, "row-partitioned multiply: a peer did not publish its shard of B within %llu s", (ull)(RP_TIMEOUT_NS / 1000000000ull));
+        if (sj && h_bad) return bad_scale_vector();
+        if (stats) {
+            stats->entries_fetched = h_info[0]; stats->rows_fetched = h_info[1];
+            stats->mm.nnz_b = h_info[0];
+            stats->ms_consolidate_b = tm.ms(t0, t_b); stats->ms_consolidate_a = tm.ms(t_b, t_a); stats->ms_fetch_wait = tm.ms(t_a, t_w);
+            float f = 0;
+            cudaEventElapsedTime(&f, rp->ev_t[1], rp->ev_t[2]); stats->ms_fetch = f;
+            cudaEventElapsedTime(&f, rp->ev_t[0], rp->ev_t[3]); stats->ms_side_stream = f;
+            const int t_end = tm.mark();
+            stats->ms_total = tm.ms(t0, t_end);
+        }
+        return 0;
+    };
+    int rc = body();
+    spb_coo_free(ctx, Ac);
+    spb_coo_free(ctx, Bc);
+    if (rc) { spb_coo_free(ctx, r); *out = nullptr; }
+    return rc;
 }
 
 }  // extern "C"

@@ -21,6 +21,58 @@ def row_range(m: int, rank: int, world: int) -> tuple[int, int]:
     return rank * m // world, (rank + 1) * m // world
 
 
+HANDLE_BYTES = 64
+
+
+def exchange_handles(handle: bytes, rank: int, world: int) -> bytes:
+    """All-gathers one fixed-size opaque handle per rank (rank order) over torch.distributed -- gloo or NCCL alike."""
+    assert len(handle) == HANDLE_BYTES
+    if world == 1:
+        return handle
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+    allh = torch.empty(world * HANDLE_BYTES, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine)
+    return bytes(allh.cpu().tolist())
+
+
+class RowPartition:
+    """The row-partitioned multiply behind the C ABI (spb_rowpart_*, include/spsparse_b200.h): one process per GPU, rank r
+    owns rows [r*m/world, (r+1)*m/world) of A and of B.  The library publishes / fetches the shards of B through
+    peer-mapped memory itself; this class only carries the one-off exchange of the 64-byte buffer handles."""
+
+    def __init__(self, ctx, rank: int, world: int, m: int, cap_entries: int):
+        import ctypes as C
+        from ._lib import check, vp
+        self.ctx, self.rank, self.world, self.m = ctx, rank, world, m
+        row_lo = (C.c_uint64 * (world + 1))(*[g * m // world for g in range(world + 1)])
+        h = vp()
+        check(ctx.lib.spb_rowpart_create(ctx.h, rank, world, row_lo, int(cap_entries), C.byref(h)))
+        self.h = h
+        buf = (C.c_ubyte * HANDLE_BYTES)()
+        check(ctx.lib.spb_rowpart_handle(self.h, buf, HANDLE_BYTES))
+        allh = exchange_handles(bytes(buf), rank, world)
+        allbuf = (C.c_ubyte * len(allh)).from_buffer_copy(allh)
+        check(ctx.lib.spb_rowpart_attach(self.h, allbuf, HANDLE_BYTES))
+        if world > 1:
+            dist.barrier()   # every rank has mapped every buffer before anybody's first step
+
+    def multiply(self, Cst, scalei, A_block, scalej, B_shard, scalek, duplicate_policy=1, zero_nan=False, fetch_all=False):
+        """-> (this rank's rows of C, RowpartStats).  Collective: every rank calls it once per step."""
+        import ctypes as C
+        from ._lib import RowpartStats, check, vp
+        from .coo import CooArray, _h
+        out, st = vp(), RowpartStats()
+        check(self.ctx.lib.spb_rowpart_multiply(self.h, float(Cst), _h(scalei), A_block.h, _h(scalej), B_shard.h, _h(scalek),
+                                                int(duplicate_policy), int(bool(zero_nan)), int(bool(fetch_all)), C.byref(out), C.byref(st)))
+        return CooArray(self.ctx, out), st
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.spb_rowpart_destroy(self.h)
+            self.h = None
+
+
 def _gather_uneven(full: torch.Tensor, offs, local: torch.Tensor, rank: int, world: int):
     """Each rank's `local` lands in full[offs[g]:offs[g+1]] on every rank.  Returns pending works.
     NCCL: one grouped call (torch coalesces the per-shard broadcasts into a single launch, so all links

@@ -449,3 +449,41 @@ def test_pool_trim(ctx):
     freed = ctypes.c_uint64()
     assert ctx.lib.spb_ctx_trim(ctx.h, ctypes.byref(freed)) == 0 and freed.value >= (1 << 20) * 16
     assert ctx.lib.spb_ctx_trim(ctx.h, ctypes.byref(freed)) == 0 and freed.value == 0
+
+
+def test_row_partitioned_multiply_on_two_gpus():
+    """spb_rowpart_* (one process per GPU, shards of B fetched from the peers' memory): tests/multi/rowpart_check.py under
+    torchrun on 2 GPUs -- skipped on a single-GPU box (bench.py --gpus N checks the result fingerprint at every N)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tests", "multi", "rowpart_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_row_partition_with_one_rank(ctx, orc):
+    """n_ranks = 1: spb_rowpart_multiply is consolidate(B) + consolidate(A) + multiply, no peers -- same answer as the oracle."""
+    import spsparse_b200 as sp
+    from spsparse_b200.dist import RowPartition
+    from _gpu import up, down
+    for s in (2003, 2004, 2008):
+        c = _cases.mm_case(s, big=True)
+        if c["tA"] != "." or c["tB"] != ".":
+            c = dict(c, A=orc.transpose(c["A"], (1, 0)) if c["tA"] == "T" else c["A"], B=orc.transpose(c["B"], (1, 0)) if c["tB"] == "T" else c["B"])
+        m = c["B"].shape[0]
+        rp = RowPartition(ctx, 0, 1, m, c["B"].n + 1)
+        hs = [up(ctx, x) for x in (c["si"], c["A"], c["sj"], c["B"], c["sk"])]
+        Cm, st = rp.multiply(c["C"], hs[0], hs[1], hs[2], hs[3], hs[4], c["policy"], c["zero_nan"])
+        got = down(Cm)
+        for h in hs + [Cm]:
+            if h is not None:
+                h.free()
+        rp.close()
+        want = orc.multiply_mm(c["C"], c["si"], c["A"], ".", c["sj"], c["B"], ".", c["sk"], c["policy"], c["zero_nan"])
+        assert _cases.same_coo(got, want), s

@@ -125,3 +125,61 @@ def test_pruned_plan_and_assembly_random():
                 assert len(got) == row_len[r] and np.all(got == r)
             else:
                 assert len(got) == 0
+
+
+def test_rowpart_pull_plan_emulation():
+    """The plan arithmetic of k_rp_pull (tools/emulate_rowpart_pull.py restates it): for random shard sizes and hulls, every
+    row of the hull comes back with exactly its entries through the absolute-row pointer, and nothing outside is written."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from emulate_rowpart_pull import pull
+    rng = np.random.default_rng(321)
+    for trial in range(300):
+        world = int(rng.integers(1, 9))
+        rows = [int(rng.integers(0, 30)) for _ in range(world)]
+        row_lo = np.concatenate([[0], np.cumsum(rows)]).astype(np.int64)
+        m = int(row_lo[-1])
+        if m == 0:
+            continue
+        row_len = rng.integers(0, 5, m)
+        ptrs, cols, vals = [], [], []
+        for g in range(world):
+            ln = row_len[row_lo[g]:row_lo[g + 1]]
+            ptrs.append(np.concatenate([[0], np.cumsum(ln)]).astype(np.int64))
+            cols.append(np.repeat(np.arange(row_lo[g], row_lo[g + 1]), ln).astype(np.int32))   # payload = the entry's global row
+            vals.append(rng.random(int(ln.sum())))
+        lo = int(rng.integers(0, m)); hi = int(rng.integers(lo, m))
+        if trial % 7 == 0:
+            lo, hi = 0, m - 1
+        if trial % 11 == 0:
+            lo, hi = 1, 0                                                                        # empty block of A: nothing fetched
+        g_ptr, g_cols, g_vals, total = pull(row_lo, ptrs, cols, vals, lo, hi, m)
+        if lo > hi:
+            assert total == 0 and np.all(g_ptr == -1)
+            continue
+        assert total == int(row_len[lo:hi + 1].sum()) and g_ptr[lo] == 0 and g_ptr[hi + 1] == total
+        assert np.all(g_ptr[:lo] == -1) and np.all(g_ptr[hi + 2:] == -1)
+        for j in range(lo, hi + 1):
+            seg = g_cols[g_ptr[j]:g_ptr[j + 1]]
+            assert len(seg) == row_len[j] and np.all(seg == j)
+
+
+def _handles_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from spsparse_b200.dist import HANDLE_BYTES, exchange_handles
+    mine = bytes([(rank * 37 + i) % 256 for i in range(HANDLE_BYTES)])
+    allh = exchange_handles(mine, rank, world)
+    ok = all(allh[g * HANDLE_BYTES:(g + 1) * HANDLE_BYTES] == bytes([(g * 37 + i) % 256 for i in range(HANDLE_BYTES)]) for g in range(world))
+    open(os.path.join(out_dir, f"h{rank}.txt"), "w").write("ok" if ok and len(allh) == world * HANDLE_BYTES else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_handle_exchange_gloo(tmp_path):
+    """The one host-side step of the row-partitioned multiply behind the C ABI: every rank ends up with every rank's 64-byte
+    buffer handle, in rank order (gloo, world size 2; on the GPU box the same call runs over NCCL)."""
+    world = 2
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_handles_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert [open(os.path.join(str(tmp_path), f"h{r}.txt")).read() for r in range(world)] == ["ok"] * world
