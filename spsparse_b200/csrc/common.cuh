@@ -83,6 +83,35 @@ __device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- bulk asynchronous copies global -> shared memory (TMA's 1-D form, cp.async.bulk) completing on an mbarrier ------------
+// One thread arms the barrier with the byte count and issues the copy; the data movement costs no registers and no
+// issue slots, and everybody waits on the barrier's phase.  Addresses and size must be multiples of 16 bytes.
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {  // makes the initialised barriers visible to the async proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, u32 bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra MBAR_DONE;\n"
+                 "bra MBAR_WAIT;\n"
+                 "MBAR_DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // warp-level inclusive scan
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan(T v) {

@@ -81,9 +81,11 @@ __global__ void __launch_bounds__(R9_RADIX / 2) k_bucket_starts9(u32 *hist) {
 }
 
 // PassArgs as for k_radix_pass, with bucket_start[512] and lookback[tiles][512] (8-byte aligned); rank_mode unused.
-template <bool PASS0>
+template <bool PASS0, bool BULK = false>
 __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortInput in) {
-    extern __shared__ __align__(16) unsigned char smem_raw9[];
+    static_assert(!(PASS0 && BULK), "pass 0 reads the caller's struct-of-arrays input");
+    __shared__ __align__(8) u64 s_mbar[2];   // BULK: see k_radix_pass
+    extern __shared__ __align__(128) unsigned char smem_raw9[];
     u64 *s_keys = reinterpret_cast<u64 *>(smem_raw9);
     double *s_vals = reinterpret_cast<double *>(s_keys + RS_TILE);
     u32 *s_cnt2 = reinterpret_cast<u32 *>(s_vals + RS_TILE);   // [RS_WARPS][256]: counters of digits 2t (low half) and 2t+1; later: global bases [512]
@@ -91,13 +93,24 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
     u32 *s_misc = s_cnt2 + RS_WARPS * (R9_RADIX / 2);          // [0] tile, [1..8] warp sums, [12] valid items
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_misc[0] = atomicAdd(a.ticket, 1u);
+    if (tid == 0) {
+        s_misc[0] = atomicAdd(a.ticket, 1u);
+        if (BULK) { mbar_init(&s_mbar[0], 1); mbar_init(&s_mbar[1], 1); mbar_fence_init(); }
+    }
     for (int t = tid; t < RS_WARPS * (R9_RADIX / 2); t += RS_THREADS) s_cnt2[t] = 0;
     __syncthreads();
     const u32 tile = s_misc[0];
     const u32 n = PASS0 ? in.n : *a.n_ptr;
     const u64 tile_base = (u64)tile * RS_TILE;
     if (tile_base >= n) return;
+    if (BULK && tid == 0) {
+        const u32 valid = n - tile_base < (u64)RS_TILE ? (u32)(n - tile_base) : (u32)RS_TILE;
+        const u32 bytes = (valid * 8u + 15u) & ~15u;
+        mbar_expect_tx(&s_mbar[0], bytes);
+        bulk_load(s_keys, a.keys_in + tile_base, bytes, &s_mbar[0]);
+        mbar_expect_tx(&s_mbar[1], bytes);
+        bulk_load(s_vals, a.vals_in + tile_base, bytes, &s_mbar[1]);
+    }
 
     // ---- load (warp-striped: item order inside the tile is (warp, k, lane)) ------------------
     const u64 wbase = tile_base + (u64)warp * (32 * RS_IPT) + lane;
@@ -124,6 +137,14 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
                 key[h + k] = pack_key(hi[k], lo[k], in.bits_lo);
                 valid_bits |= (ok ? 1u : 0u) << (h + k);
             }
+        }
+    } else if (BULK) {
+        mbar_wait(&s_mbar[0], 0);
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const bool ok = wbase + (u64)k * 32 < n;
+            key[k] = ok ? s_keys[warp * (32 * RS_IPT) + k * 32 + lane] : 0;
+            valid_bits |= (ok ? 1u : 0u) << k;
         }
     } else {
 #pragma unroll
@@ -217,10 +238,17 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
     {
         const double *vsrc = PASS0 ? in.val : a.vals_in;
         double v[RS_IPT];
+        if (BULK) {
+            mbar_wait(&s_mbar[1], 0);
 #pragma unroll
-        for (int k = 0; k < RS_IPT; ++k) {
-            u64 i = wbase + (u64)k * 32;
-            v[k] = ((valid_bits >> k) & 1u) ? ld_stream_f64(vsrc + i) : 0.0;
+            for (int k = 0; k < RS_IPT; ++k) v[k] = s_vals[warp * (32 * RS_IPT) + k * 32 + lane];
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int k = 0; k < RS_IPT; ++k) {
+                u64 i = wbase + (u64)k * 32;
+                v[k] = ((valid_bits >> k) & 1u) ? ld_stream_f64(vsrc + i) : 0.0;
+            }
         }
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k)

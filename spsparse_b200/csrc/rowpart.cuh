@@ -15,13 +15,16 @@ constexpr int RP_MAX_RANKS = 16;
 constexpr int RP_FLAG_WORDS = 2 * RP_MAX_RANKS;    // ready[RP_MAX_RANKS], done[RP_MAX_RANKS]
 constexpr u64 RP_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;  // a peer that does not show up within 20 s: give up (error flag), never hang
 
-// One rank's exported region as it is mapped in this process.
+// One rank's exported region as it is mapped in this process.  cols / vals point at the SHARD, which sits in the middle of a
+// larger allocation: `slack` entries of room on either side take the halo rows fetched from the neighbouring ranks, so that a
+// rank whose block of A only reaches a little beyond its own rows multiplies against [lower halo | own shard | upper halo]
+// in place -- its own shard, consolidated straight into this buffer, is never copied.
 struct RpRegion {
     u64 *flags;    // [0 .. RP_MAX_RANKS) ready[q]: last step whose shard rank q has published (q writes it into MY region)
                    // [RP_MAX_RANKS .. )  done[q]: last step in which rank q has finished reading MY shard
     u32 *ptr;      // [cap_rows + 1] entry offset, inside the shard, of the first entry of each of its rows (+ sentinel)
-    i32 *cols;     // [cap_entries]
-    double *vals;  // [cap_entries]
+    i32 *cols;     // [cap_entries] (+ slack before and after)
+    double *vals;  // [cap_entries] (+ slack before and after)
 };
 
 struct RpArgs {
@@ -29,6 +32,7 @@ struct RpArgs {
     u64 step;                         // 1, 2, ...
     u64 row_lo[RP_MAX_RANKS + 1];
     RpRegion reg[RP_MAX_RANKS];       // reg[rank] is this rank's own region
+    u32 slack;                        // entries of room before and after every shard
     u32 *error;                       // set to 1 when a wait timed out
 };
 
@@ -75,6 +79,14 @@ __global__ void __launch_bounds__(512) k_rp_publish(RpArgs a, const u32 *__restr
     }
 }
 
+// the shard was consolidated straight into the region: only its row pointers are published.  Entries of rows outside the
+// shard's range (local_ptr[0] != 0) would shift everything: the caller's partition is wrong, error 4.
+__global__ void __launch_bounds__(512) k_rp_publish_ptr(RpArgs a, const u32 *__restrict__ local_ptr, u32 rows_local, u32 n_shard) {
+    const RpRegion me = a.reg[a.rank];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (local_ptr[0] != 0 || local_ptr[rows_local] != n_shard)) *a.error = 4u;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t <= rows_local; t += (u64)gridDim.x * blockDim.x) me.ptr[t] = local_ptr[t];
+}
+
 __global__ void k_rp_signal_ready(RpArgs a) {
     const int q = threadIdx.x;
     __threadfence_system();
@@ -106,19 +118,23 @@ __global__ void k_rp_hull_set(u64 *hull, u64 lo, u64 hi) { hull[0] = lo; hull[1]
 // info[0] = entries fetched, info[1] = rows fetched, info[2] = blocks finished (zeroed by the host)
 constexpr int RP_PULL_THREADS = 512;
 constexpr int RP_PULL_UNROLL = 8;
+// info[0] = entries fetched, info[1] = rows fetched, info[2] = blocks finished (zeroed by the host), info[3] = outcome:
+// 1 = done in place, 2 = done by copying, 3 = the halos do not fit the slack (nothing done, the peers NOT released: the host
+// launches the copying variant)
+template <bool IN_PLACE>
 __global__ void __launch_bounds__(RP_PULL_THREADS) k_rp_pull(RpArgs a, const u64 *__restrict__ hull, u32 *g_ptr, i32 *g_cols,
                                                              double *g_vals, u64 cap_entries, u64 *info) {
     __shared__ u64 s_rlo[RP_MAX_RANKS], s_rhi[RP_MAX_RANKS];   // rows [rlo, rhi) of peer g are fetched
     __shared__ u32 s_elo[RP_MAX_RANKS], s_cnt[RP_MAX_RANKS];   // its entries [elo, elo + cnt)
     __shared__ u64 s_base[RP_MAX_RANKS + 1];                   // where they go
-    __shared__ u32 s_last;
+    __shared__ u32 s_last, s_fit;
     const u32 tid = threadIdx.x;
     const u64 lo = hull[0], hi = hull[1];
     if (tid < 32) {
         // every block works the plan out for itself (two pointer values per peer): no block waits for another block
         const int g = (int)tid;
         u64 rlo = 0, rhi = 0;
-        u32 elo = 0, cnt = 0;
+        u32 elo = 0, cnt = 0, n_own = 0;
         if (g < a.n_ranks && lo <= hi) {
             rlo = max(lo, a.row_lo[g]);
             rhi = min(hi + 1, a.row_lo[g + 1]);
@@ -131,52 +147,92 @@ __global__ void __launch_bounds__(RP_PULL_THREADS) k_rp_pull(RpArgs a, const u64
                 } else rhi = rlo;
             } else rhi = rlo;
         }
-        const u64 incl = warp_incl_scan((u64)cnt);
-        if (g < a.n_ranks) { s_rlo[g] = rlo; s_rhi[g] = rhi; s_elo[g] = elo; s_cnt[g] = cnt; s_base[g] = incl - cnt; }
-        if (g == a.n_ranks - 1) s_base[a.n_ranks] = incl;
+        if (IN_PLACE) {
+            // own shard stays where it is (offset 0 of my region's shard); lower halos end right before it, upper ones start
+            // right after its last entry
+            if (g == a.rank) {
+                rp_wait_ge(a.reg[a.rank].flags + g, a.step, a.error);
+                n_own = __ldcg(a.reg[g].ptr + (a.row_lo[g + 1] - a.row_lo[g]));
+            }
+            n_own = __shfl_sync(SPB_FULL_MASK, n_own, a.rank);
+            const u32 c_lo = g < a.rank ? cnt : 0, c_hi = (g > a.rank && g < a.n_ranks) ? cnt : 0;
+            const u64 in_lo = warp_incl_scan((u64)c_lo), in_hi = warp_incl_scan((u64)c_hi);
+            const u64 tot_lo = __shfl_sync(SPB_FULL_MASK, in_lo, 31), tot_hi = __shfl_sync(SPB_FULL_MASK, in_hi, 31);
+            // positions relative to the first entry of my shard (negative = inside the lower slack), biased by slack
+            u64 base = a.slack;                                               // own
+            if (g < a.rank) base = a.slack - tot_lo + (in_lo - c_lo);
+            else if (g > a.rank) base = (u64)a.slack + n_own + (in_hi - c_hi);
+            if (g < a.n_ranks) { s_rlo[g] = rlo; s_rhi[g] = rhi; s_elo[g] = elo; s_cnt[g] = cnt; s_base[g] = base; }
+            if (g == 0) { s_base[a.n_ranks] = tot_lo + tot_hi; s_fit = (tot_lo <= a.slack && tot_hi <= a.slack) ? 1u : 0u; }
+        } else {
+            const u64 incl = warp_incl_scan((u64)cnt);
+            if (g < a.n_ranks) { s_rlo[g] = rlo; s_rhi[g] = rhi; s_elo[g] = elo; s_cnt[g] = cnt; s_base[g] = incl - cnt; }
+            if (g == a.n_ranks - 1) s_base[a.n_ranks] = incl;
+            if (g == 0) s_fit = 1u;
+        }
     }
     __syncthreads();
-    const u64 total = s_base[a.n_ranks];
-    const bool overflow = total > cap_entries;   // never overrun the buffers: nothing is copied, the host reports it
+    const u64 total = s_base[a.n_ranks];     // entries copied
+    if (IN_PLACE && !s_fit) {                // the host switches to the copying variant; the peers stay un-released until then
+        if (blockIdx.x == 0 && tid == 0) info[3] = 3;
+        return;
+    }
+    const bool overflow = !IN_PLACE && total > cap_entries;   // never overrun the buffers: nothing is copied, the host reports it
     if (overflow && tid == 0) *a.error = 2u;
+    // IN_PLACE: everything is addressed relative to (my shard - slack) inside my own region
+    i32 *const out_c = IN_PLACE ? a.reg[a.rank].cols - a.slack : g_cols;
+    double *const out_v = IN_PLACE ? a.reg[a.rank].vals - a.slack : g_vals;
     // entries: chunks of RP_PULL_THREADS * RP_PULL_UNROLL, all loads of a chunk in flight before the first store
     constexpr u64 CHUNK = (u64)RP_PULL_THREADS * RP_PULL_UNROLL;
     for (int g = 0; g < a.n_ranks && !overflow; ++g) {
         const u32 cnt = s_cnt[g];
-        if (!cnt) continue;
-        const i32 *sc = a.reg[g].cols + s_elo[g];
-        const double *sv = a.reg[g].vals + s_elo[g];
-        i32 *dc = g_cols + s_base[g];
-        double *dv = g_vals + s_base[g];
-        for (u64 c0 = (u64)blockIdx.x * CHUNK; c0 < cnt; c0 += (u64)gridDim.x * CHUNK) {
-            i32 k[RP_PULL_UNROLL];
-            double v[RP_PULL_UNROLL];
+        const u64 rlo = s_rlo[g], rhi = s_rhi[g], r0 = a.row_lo[g];
+        if (rlo >= rhi) continue;
+        const bool own_in_place = IN_PLACE && g == a.rank;
+        if (cnt && !own_in_place) {
+            const i32 *sc = a.reg[g].cols + s_elo[g];
+            const double *sv = a.reg[g].vals + s_elo[g];
+            i32 *dc = out_c + s_base[g];
+            double *dv = out_v + s_base[g];
+            for (u64 c0 = (u64)blockIdx.x * CHUNK; c0 < cnt; c0 += (u64)gridDim.x * CHUNK) {
+                i32 k[RP_PULL_UNROLL];
+                double v[RP_PULL_UNROLL];
 #pragma unroll
-            for (int u = 0; u < RP_PULL_UNROLL; ++u) {
-                const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
-                if (t < cnt) { k[u] = __ldcg(sc + t); v[u] = __ldcg(sv + t); }   // L2 only: the owner rewrites these every step
-            }
+                for (int u = 0; u < RP_PULL_UNROLL; ++u) {
+                    const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
+                    if (t < cnt) { k[u] = __ldcg(sc + t); v[u] = __ldcg(sv + t); }   // L2 only: the owner rewrites these every step
+                }
 #pragma unroll
-            for (int u = 0; u < RP_PULL_UNROLL; ++u) {
-                const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
-                if (t < cnt) { dc[t] = k[u]; dv[t] = v[u]; }
+                for (int u = 0; u < RP_PULL_UNROLL; ++u) {
+                    const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
+                    if (t < cnt) { dc[t] = k[u]; dv[t] = v[u]; }
+                }
             }
         }
-        // row pointers of the fetched rows, re-based to where the entries went
+        // row pointers of the fetched rows, re-based to where the entries are (own rows in place: offset slack)
         const u32 *p = a.reg[g].ptr;
-        const u64 rlo = s_rlo[g], rhi = s_rhi[g], r0 = a.row_lo[g];
-        const u32 shift = (u32)s_base[g] - s_elo[g];   // wraps consistently in 32 bits
+        const u32 shift = own_in_place ? a.slack : (u32)s_base[g] - s_elo[g];   // wraps consistently in 32 bits
         for (u64 j = rlo + (u64)blockIdx.x * blockDim.x + tid; j < rhi; j += (u64)gridDim.x * blockDim.x)
             g_ptr[j] = __ldcg(p + (j - r0)) + shift;
     }
-    if (blockIdx.x == 0 && tid == 0 && lo <= hi && !overflow) g_ptr[hi + 1] = (u32)total;
+    if (blockIdx.x == 0 && tid == 0 && lo <= hi && !overflow) {
+        // end of the last fetched row
+        int gl = 0;
+        for (int g = 0; g < a.n_ranks; ++g) if (s_rlo[g] < s_rhi[g]) gl = g;
+        const u32 shift = (IN_PLACE && gl == a.rank) ? a.slack : (u32)s_base[gl] - s_elo[gl];
+        g_ptr[hi + 1] = s_elo[gl] + s_cnt[gl] + shift;
+    }
     // the last block to finish tells every peer that this rank is done with its shard for this step
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd((ull *)&info[2], 1ull) == (ull)gridDim.x - 1;
     __syncthreads();
     if (s_last) {
-        if (tid == 0) { info[0] = total; info[1] = lo <= hi ? hi - lo + 1 : 0; }
+        if (tid == 0) {
+            u64 fetched = 0;
+            for (int g = 0; g < a.n_ranks; ++g) fetched += s_cnt[g];
+            info[0] = fetched; info[1] = lo <= hi ? hi - lo + 1 : 0; info[3] = IN_PLACE ? 1 : 2;
+        }
         __threadfence_system();
         if (tid < (u32)a.n_ranks && (int)tid != a.rank) rp_st_release_sys(a.reg[tid].flags + RP_MAX_RANKS + a.rank, a.step);
     }

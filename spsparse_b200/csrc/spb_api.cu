@@ -120,6 +120,7 @@ struct spb_ctx {
     u64 hash_min_products;   // long rows with at least this many products use the bitmap + hash-accumulator kernels; ~0 = never (SPB_HASH_MIN_PRODUCTS)
     int hash_variant;        // 0: 1024 threads x 10240 outputs per item, 1: 512 x 5120 (two blocks per SM), 2: 256 x 2560 (four)  (SPB_HASH_VARIANT)
     u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
+    bool bulk_load;          // radix passes after the first bring their tile in with cp.async.bulk (SPB_BULK_LOAD, default on)
     DevPool pool;
 };
 
@@ -238,6 +239,9 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     CK(cudaFuncSetAttribute(k_reduce_segsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RfSmem)));
     CK(cudaFuncSetAttribute(k_radix_pass9<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass9<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_pass9<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
+    c->bulk_load = getenv("SPB_BULK_LOAD") ? atoi(getenv("SPB_BULK_LOAD")) != 0 : true;
     const char *s = getenv("SPB_MERGE_MAX_PRODUCTS");
     c->merge_max_products = s ? (u32)strtoul(s, nullptr, 10) : 1024u;
     s = getenv("SPB_ESC_CHUNK");
@@ -491,8 +495,13 @@ static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passe
             SortInput dummy;
             memset(&dummy, 0, sizeof dummy);
             ++ctx->launches;
-            if (nine) k_radix_pass9<false><<<tiles, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, dummy);
-            else k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            if (ctx->bulk_load) {
+                if (nine) k_radix_pass9<false, true><<<tiles, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, dummy);
+                else k_radix_pass<false, true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            } else {
+                if (nine) k_radix_pass9<false><<<tiles, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, dummy);
+                else k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            }
             u64 *tk = kin; kin = kout; kout = tk;
             double *tv = vin; vin = vout; vout = tv;
         }
@@ -676,11 +685,26 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
 
 // consolidate `in` into a fresh array sorted by `so`; `ref_so` is the order the reference would have
 // used at this call site (decides which NaNs form the "leading run" when zero_nan).
+// ext_lo / ext_val (rank 2 only): caller-owned device buffers of in->n entries that receive the second sort dimension's index
+// vector and the values instead of pool memory (the row-partitioned multiply has its shard of B consolidated straight
+// into the buffer its peers read).
 static int consolidate_core(spb_ctx *ctx, const spb_coo *in, const int *so, const int *ref_so, int policy,
-                            bool drop_zero, int zero_nan, spb_coo **out, spb_consolidate_stats *st) {
+                            bool drop_zero, int zero_nan, spb_coo **out, spb_consolidate_stats *st,
+                            i32 *ext_lo = nullptr, double *ext_val = nullptr) {
     if (in->n >= (1ull << 31)) return spb_fail(SPB_ERR_TOO_LARGE, "%llu entries: one array holds fewer than 2^31 (the reference's own cap, algorithm.hpp:419)", (ull)in->n);
     spb_coo *r = nullptr;
-    CKR(coo_new(ctx, in->rank, in->shape, in->n, true, &r));
+    if (ext_lo && ext_val && in->rank == 2) {
+        CKR(coo_new(ctx, in->rank, in->shape, in->n, false, &r));
+        r->owned = true;   // the leading index vector comes from the pool; releasing the two external pointers is a no-op
+        if (ctx->pool.alloc((void **)&r->idx[so[0]], (in->n ? in->n : 1) * sizeof(i32)) != cudaSuccess) {
+            delete r;
+            return spb_fail(SPB_ERR_CUDA, "out of device memory");
+        }
+        r->idx[so[1]] = ext_lo;
+        r->val = ext_val;
+    } else {
+        CKR(coo_new(ctx, in->rank, in->shape, in->n, true, &r));
+    }
     set_order(r, so);
     if (st) memset(st, 0, sizeof *st);
     if (in->n == 0) { *out = r; return SPB_OK; }  // algorithm.hpp:263,318
@@ -865,7 +889,9 @@ static int esc_sort_reduce(spb_ctx *ctx, u64 *kA, double *vA, u32 count, int key
             a.shift = p * RS_RADIX_BITS;
             a.rank_mode = 0;
         a.rank_mode = getenv("SPB_RANK_MODE") ? atoi(getenv("SPB_RANK_MODE")) : 0;
-            ++ctx->launches, k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            ++ctx->launches;
+            if (ctx->bulk_load) k_radix_pass<false, true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
+            else k_radix_pass<false><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, dummy);
             u64 *tk = kin; kin = kout; kout = tk;
             double *tv = vin; vin = vout; vout = tv;
         }
@@ -1945,6 +1971,8 @@ struct spb_rowpart {
     u64 row_lo[RP_MAX_RANKS + 1];
     u64 m;                       // rows of B = inner dimension
     u64 cap_entries, cap_rows;   // per-rank capacity of the published shard (the same on every rank)
+    u64 slack;                   // entries of room before and after the shard (halo rows of the neighbours)
+    int mode;                    // 0: halos fetched in place around the own shard; 1: everything copied (sticky once needed)
     size_t off_ptr, off_cols, off_vals, region_bytes;
     void *region;                // this rank's exported allocation
     void *peer_base[RP_MAX_RANKS];
@@ -1967,8 +1995,8 @@ static size_t rp_align(size_t x) { return (x + 255) & ~(size_t)255; }
 static void rp_layout(spb_rowpart *rp) {
     rp->off_ptr = rp_align(RP_FLAG_WORDS * sizeof(u64));
     rp->off_cols = rp->off_ptr + rp_align((rp->cap_rows + 2) * sizeof(u32));
-    rp->off_vals = rp->off_cols + rp_align(rp->cap_entries * sizeof(i32));
-    rp->region_bytes = rp->off_vals + rp_align(rp->cap_entries * sizeof(double));
+    rp->off_vals = rp->off_cols + rp_align((rp->cap_entries + 2 * rp->slack) * sizeof(i32));
+    rp->region_bytes = rp->off_vals + rp_align((rp->cap_entries + 2 * rp->slack) * sizeof(double));
 }
 
 static void rp_args(const spb_rowpart *rp, RpArgs *a) {
@@ -1979,9 +2007,10 @@ static void rp_args(const spb_rowpart *rp, RpArgs *a) {
         char *b = (char *)rp->peer_base[g];
         a->reg[g].flags = (u64 *)b;
         a->reg[g].ptr = (u32 *)(b + rp->off_ptr);
-        a->reg[g].cols = (i32 *)(b + rp->off_cols);
-        a->reg[g].vals = (double *)(b + rp->off_vals);
+        a->reg[g].cols = (i32 *)(b + rp->off_cols) + rp->slack;     // the shard itself; the slack lies on either side
+        a->reg[g].vals = (double *)(b + rp->off_vals) + rp->slack;
     }
+    a->slack = (u32)rp->slack;
 }
 
 extern "C" {
@@ -2022,16 +2051,16 @@ int spb_rowpart_create(spb_ctx *ctx, int rank, int n_ranks, const uint64_t *row_
     rp->m = row_lo[n_ranks];
     rp->cap_entries = cap_entries ? cap_entries : 1;
     rp->cap_rows = rows_max;
+    rp->slack = ((rp->cap_entries / 16 > 4096 ? rp->cap_entries / 16 : 4096) + 63) & ~63ull;   // multiple of 64 entries: alignment kept
+    rp->mode = 0;
     rp_layout(rp);
     *out = rp;
     auto body = [&]() -> int {
         if (n_ranks > 1) {
             CK(cudaMalloc(&rp->region, rp->region_bytes));
             CK(cudaMemset(rp->region, 0, rp->off_cols));   // step counters and pointers start at 0
-            rp->g_cap = rp->cap_entries * (u64)n_ranks;
+            rp->g_cap = rp->cap_entries * (u64)n_ranks;   // the copy buffers themselves are allocated when first needed
             CK(cudaMalloc((void **)&rp->g_ptr, (rp->m + 2) * sizeof(u32)));
-            CK(cudaMalloc((void **)&rp->g_cols, rp->g_cap * sizeof(i32)));
-            CK(cudaMalloc((void **)&rp->g_vals, rp->g_cap * sizeof(double)));
             CK(cudaMalloc((void **)&rp->hull, 8 * sizeof(u64)));
             CK(cudaMemset(rp->hull, 0, 8 * sizeof(u64)));
             rp->info = rp->hull + 2;
@@ -2112,14 +2141,14 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
     // Every rank runs every step of the hand-shake, also when its own operands are empty: the peers count on it.
     const bool nothing = C == 0.0 || (si && si->n == 0) || (sj && sj->n == 0) || (sk && sk->n == 0);   // multiply_sparse.hpp:178-184
     auto body = [&]() -> int {
-        // ---- B shard: consolidate by (row, col); already consolidated shards are used as they are -------------------------
-        const spb_coo *Buse = B;
-        if (!(B->sort_order[0] == 0 && B->sort_order[1] == 1)) {
-            CKR(consolidate_core(ctx, B, row_major, row_major, policy, true, zero_nan, &Bc, stats ? &stats->b : nullptr));
-            Buse = Bc;
-        }
-        const int t_b = tm.mark();
         if (n_ranks == 1) {
+            // consolidate by (row, col); operands already consolidated that way are used as they are
+            const spb_coo *Buse = B;
+            if (!(B->sort_order[0] == 0 && B->sort_order[1] == 1)) {
+                CKR(consolidate_core(ctx, B, row_major, row_major, policy, true, zero_nan, &Bc, stats ? &stats->b : nullptr));
+                Buse = Bc;
+            }
+            const int t_b = tm.mark();
             const spb_coo *Ause = A;
             if (!(A->sort_order[0] == 0 && A->sort_order[1] == 1)) {
                 CKR(consolidate_core(ctx, A, row_major, row_major, policy, true, zero_nan, &Ac, stats ? &stats->a : nullptr));
@@ -2136,22 +2165,37 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
             }
             return 0;
         }
-        if (Buse->n > rp->cap_entries)
-            return spb_fail(SPB_ERR_TOO_LARGE, "the shard of B has %llu entries, the partition was created for %llu", (ull)Buse->n, (ull)rp->cap_entries);
         ++rp->step;
         RpArgs ra;
         rp_args(rp, &ra);
-        // ---- publish the shard (main stream) -------------------------------------------------------------------------------
+        if (B->n > rp->cap_entries)
+            return spb_fail(SPB_ERR_TOO_LARGE, "the shard of B has %llu entries, the partition was created for %llu", (ull)B->n, (ull)rp->cap_entries);
+        // ---- B shard (main stream): consolidated straight into the buffer the peers read, once they are done with the
+        //      previous step's shard; then its row pointers are published and the ready counters raised -------------------------
+        CK(cudaMemsetAsync(rp->info, 0, 6 * sizeof(u64), ctx->stream));   // counters of the fetch, error and bad-vector flags
+        ++ctx->launches, k_rp_wait_done<<<1, 32, 0, ctx->stream>>>(ra);
+        const spb_coo *Buse = B;
+        const bool b_sorted = B->sort_order[0] == 0 && B->sort_order[1] == 1;
+        if (!b_sorted) {
+            CKR(consolidate_core(ctx, B, row_major, row_major, policy, true, zero_nan, &Bc, stats ? &stats->b : nullptr,
+                                 ra.reg[rank].cols, ra.reg[rank].vals));
+            Buse = Bc;
+        }
+        const int t_b = tm.mark();
         u32 *local_ptr = nullptr;
         CKR(spb_coo_dense_ptr_range(ctx, Buse, r0, r1, &local_ptr));
-        CK(cudaMemsetAsync(rp->info, 0, 6 * sizeof(u64), ctx->stream));   // counters of the fetch, error and bad-vector flags
         CK(cudaEventRecord(rp->ev_main, ctx->stream));   // A (and B) are complete on the caller's stream from here on
-        ++ctx->launches, k_rp_wait_done<<<1, 32, 0, ctx->stream>>>(ra);
-        ++ctx->launches, k_rp_publish<<<(u32)ctx->sm_count * 2, 512, 0, ctx->stream>>>(ra, local_ptr, (u32)(r1 - r0), Buse->idx[1], Buse->val);
+        if (b_sorted) ++ctx->launches, k_rp_publish<<<(u32)ctx->sm_count * 2, 512, 0, ctx->stream>>>(ra, local_ptr, (u32)(r1 - r0), Buse->idx[1], Buse->val);
+        else ++ctx->launches, k_rp_publish_ptr<<<(u32)ctx->sm_count, 512, 0, ctx->stream>>>(ra, local_ptr, (u32)(r1 - r0), (u32)Buse->n);
         ++ctx->launches, k_rp_signal_ready<<<1, 32, 0, ctx->stream>>>(ra);
         CK(cudaGetLastError());
         CK(cudaEventRecord(rp->ev_pub, ctx->stream));
         // ---- side stream: hull of A's inner indices, fetch of those rows of B, scalej for that range ---------------------
+        const bool copy_mode = fetch_all || rp->mode == 1;
+        if (copy_mode && !rp->g_cols) {
+            CK(cudaMalloc((void **)&rp->g_cols, rp->g_cap * sizeof(i32)));
+            CK(cudaMalloc((void **)&rp->g_vals, rp->g_cap * sizeof(double)));
+        }
         CK(cudaStreamWaitEvent(rp->side, rp->ev_main, 0));
         CK(cudaEventRecord(rp->ev_t[0], rp->side));
         if (fetch_all && rp->m) ++ctx->launches, k_rp_hull_set<<<1, 1, 0, rp->side>>>(rp->hull, 0ull, rp->m - 1);
@@ -2161,7 +2205,9 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
         }
         CK(cudaStreamWaitEvent(rp->side, rp->ev_pub, 0));
         CK(cudaEventRecord(rp->ev_t[1], rp->side));
-        ++ctx->launches, k_rp_pull<<<fetch_all ? 96u : 32u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, rp->g_cols, rp->g_vals, rp->g_cap, rp->info);
+        ++ctx->launches;
+        if (copy_mode) k_rp_pull<false><<<96u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, rp->g_cols, rp->g_vals, rp->g_cap, rp->info);
+        else k_rp_pull<true><<<32u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, nullptr, nullptr, 0, rp->info);
         CK(cudaEventRecord(rp->ev_t[2], rp->side));
         u32 *bad_vec = (u32 *)(rp->hull + 7);
         if (sj) {
@@ -2182,6 +2228,27 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
             Ause = Ac;
         }
         const int t_a = tm.mark();
+        bool in_place = !copy_mode;
+        if (in_place) {
+            // did the halos fit the slack?  (the fetch is long finished: consolidate(A) ran meanwhile)
+            u64 outcome = 0;
+            CK(cudaEventSynchronize(rp->ev_pull));
+            CK(cudaMemcpyAsync(&outcome, rp->info + 3, sizeof outcome, cudaMemcpyDeviceToHost, rp->side));
+            CK(cudaStreamSynchronize(rp->side));
+            if (outcome == 3) {
+                // no: this block of A reaches far into the neighbours' rows.  Copy everything (now, and from now on).
+                rp->mode = 1;
+                in_place = false;
+                if (!rp->g_cols) {
+                    CK(cudaMalloc((void **)&rp->g_cols, rp->g_cap * sizeof(i32)));
+                    CK(cudaMalloc((void **)&rp->g_vals, rp->g_cap * sizeof(double)));
+                }
+                CK(cudaMemsetAsync(rp->info, 0, 4 * sizeof(u64), rp->side));
+                ++ctx->launches, k_rp_pull<false><<<96u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, rp->g_cols, rp->g_vals, rp->g_cap, rp->info);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(rp->ev_pull, rp->side));
+            }
+        }
         CK(cudaStreamWaitEvent(ctx->stream, rp->ev_pull, 0));
         const int t_w = tm.mark();
         // ---- multiply against the fetched rows ----------------------------------------------------------------------------------
@@ -2189,7 +2256,9 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
         memset(&Bv, 0, sizeof Bv);
         Bv.rank = 2; Bv.shape[0] = B->shape[0]; Bv.shape[1] = B->shape[1];
         Bv.n = Buse->n * (u64)n_ranks;          // estimate (kernel-variant heuristics only); the count fetched is in stats
-        Bv.idx[0] = nullptr; Bv.idx[1] = rp->g_cols; Bv.val = rp->g_vals;
+        Bv.idx[0] = nullptr;
+        Bv.idx[1] = in_place ? ra.reg[rank].cols - rp->slack : rp->g_cols;   // in place: [lower halo | own shard | upper halo]
+        Bv.val = in_place ? ra.reg[rank].vals - rp->slack : rp->g_vals;
         Bv.sort_order[0] = 0; Bv.sort_order[1] = 1;
         Bv.dense_ptr = rp->g_ptr; Bv.dense_ptr_owned = false;
         PreScale pre = {rp->sj_dense, rp->sj_mask};
@@ -2200,6 +2269,7 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
         CK(cudaStreamSynchronize(ctx->stream));
         const u32 h_err = (u32)h_info[4], h_bad = (u32)(h_info[5]);
         if (h_err == 2) return spb_fail(SPB_ERR_TOO_LARGE, "the rows of B this rank needs hold %llu entries; the partition's buffers hold %llu", (ull)h_info[0], (ull)rp->g_cap);
+        if (h_err == 4) return spb_fail(SPB_ERR_ARG, "the shard of B holds entries of rows outside [%llu, %llu): not this rank's rows", (ull)r0, (ull)r1);
         if (h_err) return spb_fail(SPB_ERR_CUDA, "row-partitioned multiply: a peer did not publish its shard of B within %llu s", (ull)(RP_TIMEOUT_NS / 1000000000ull));
         if (sj && h_bad) return bad_scale_vector();
         if (stats) {

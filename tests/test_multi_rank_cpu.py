@@ -161,6 +161,21 @@ def test_rowpart_pull_plan_emulation():
         for j in range(lo, hi + 1):
             seg = g_cols[g_ptr[j]:g_ptr[j + 1]]
             assert len(seg) == row_len[j] and np.all(seg == j)
+        # the in-place variant, as every rank would run it: own shard untouched, halos in the slack around it
+        from emulate_rowpart_pull import pull_in_place
+        for rank in range(world):
+            slack = int(rng.integers(0, 40))
+            res = pull_in_place(row_lo, ptrs, cols, vals, lo, hi, m, rank, slack)
+            need_lo = int(row_len[lo:max(lo, min(hi + 1, row_lo[rank]))].sum())
+            need_hi = int(row_len[max(lo, min(hi + 1, row_lo[rank + 1])):hi + 1].sum())
+            if need_lo > slack or need_hi > slack:
+                assert res is None
+                continue
+            p2, bc, bv = res
+            assert np.all(p2[:lo] == -1) and np.all(p2[hi + 2:] == -1)
+            for j in range(lo, hi + 1):
+                seg = bc[p2[j]:p2[j + 1]]
+                assert len(seg) == row_len[j] and np.all(seg == j), (trial, rank, j)
 
 
 def _handles_worker(rank, world, port, out_dir):
