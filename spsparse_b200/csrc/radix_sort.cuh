@@ -189,7 +189,6 @@ struct PassArgs {
 // per thread; the values arrive while the keys are being ranked.
 template <bool PASS0, bool BULK = false>
 __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortInput in) {
-    static_assert(!(PASS0 && BULK), "pass 0 reads the caller's struct-of-arrays input");
     __shared__ __align__(8) u64 s_mbar[2];
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);
@@ -208,7 +207,17 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
     const u32 n = PASS0 ? in.n : *a.n_ptr;
     const u64 tile_base = (u64)tile * RS_TILE;
     if (tile_base >= n) return;
-    if (BULK && tid == 0) {
+    if (BULK && PASS0 && tid == 0) {
+        // pass 0, FULL tiles only (the host runs the last, partial tile through the non-bulk kernel: the caller's arrays end
+        // where they end): row indices into the first half of the key buffer, column indices into the second, values in place
+        i32 *s_idx = reinterpret_cast<i32 *>(s_keys);
+        mbar_expect_tx(&s_mbar[0], (in.lo ? 2u : 1u) * RS_TILE * 4u);
+        bulk_load(s_idx, in.hi + tile_base, RS_TILE * 4u, &s_mbar[0]);
+        if (in.lo) bulk_load(s_idx + RS_TILE, in.lo + tile_base, RS_TILE * 4u, &s_mbar[0]);
+        mbar_expect_tx(&s_mbar[1], RS_TILE * 8u);
+        bulk_load(s_vals, in.val + tile_base, RS_TILE * 8u, &s_mbar[1]);
+    }
+    if (BULK && !PASS0 && tid == 0) {
         // (a last tile with an odd number of entries reads 8 bytes past entry n - 1: inside the buffer, whose size is rounded up)
         const u32 valid = n - tile_base < (u64)RS_TILE ? (u32)(n - tile_base) : (u32)RS_TILE;
         const u32 bytes = (valid * 8u + 15u) & ~15u;
@@ -222,7 +231,19 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
     const u64 wbase = tile_base + (u64)warp * (32 * RS_IPT) + lane;
     u64 key[RS_IPT];
     u32 valid_bits = 0;
-    if (PASS0) {
+    if (PASS0 && BULK) {
+        mbar_wait(&s_mbar[0], 0);
+        mbar_wait(&s_mbar[1], 0);
+        const i32 *s_idx = reinterpret_cast<const i32 *>(s_keys);
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const u32 q = warp * (32 * RS_IPT) + k * 32 + lane;
+            const i32 hi = s_idx[q], lo = in.lo ? s_idx[RS_TILE + q] : 0;
+            const bool ok = ((u32)hi < in.extent_hi) && ((u32)lo < in.extent_lo) && input_kept(in, (u32)(tile_base + q), s_vals[q]);
+            key[k] = pack_key(hi, lo, in.bits_lo);
+            valid_bits |= (ok ? 1u : 0u) << k;
+        }
+    } else if (PASS0) {
         // two batches of 8 so that at most 8 x (hi, lo, val) loads are in flight per thread; the value
         // is only tested here (drop rule) and re-read from L2 when it is staged below
 #pragma unroll

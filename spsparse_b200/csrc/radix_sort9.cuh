@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(R9_RADIX / 2) k_bucket_starts9(u32 *hist) {
 // PassArgs as for k_radix_pass, with bucket_start[512] and lookback[tiles][512] (8-byte aligned); rank_mode unused.
 template <bool PASS0, bool BULK = false>
 __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortInput in) {
-    static_assert(!(PASS0 && BULK), "pass 0 reads the caller's struct-of-arrays input");
     __shared__ __align__(8) u64 s_mbar[2];   // BULK: see k_radix_pass
     extern __shared__ __align__(128) unsigned char smem_raw9[];
     u64 *s_keys = reinterpret_cast<u64 *>(smem_raw9);
@@ -103,7 +102,15 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
     const u32 n = PASS0 ? in.n : *a.n_ptr;
     const u64 tile_base = (u64)tile * RS_TILE;
     if (tile_base >= n) return;
-    if (BULK && tid == 0) {
+    if (BULK && PASS0 && tid == 0) {   // see k_radix_pass
+        i32 *s_idx = reinterpret_cast<i32 *>(s_keys);
+        mbar_expect_tx(&s_mbar[0], (in.lo ? 2u : 1u) * RS_TILE * 4u);
+        bulk_load(s_idx, in.hi + tile_base, RS_TILE * 4u, &s_mbar[0]);
+        if (in.lo) bulk_load(s_idx + RS_TILE, in.lo + tile_base, RS_TILE * 4u, &s_mbar[0]);
+        mbar_expect_tx(&s_mbar[1], RS_TILE * 8u);
+        bulk_load(s_vals, in.val + tile_base, RS_TILE * 8u, &s_mbar[1]);
+    }
+    if (BULK && !PASS0 && tid == 0) {
         const u32 valid = n - tile_base < (u64)RS_TILE ? (u32)(n - tile_base) : (u32)RS_TILE;
         const u32 bytes = (valid * 8u + 15u) & ~15u;
         mbar_expect_tx(&s_mbar[0], bytes);
@@ -116,7 +123,19 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
     const u64 wbase = tile_base + (u64)warp * (32 * RS_IPT) + lane;
     u64 key[RS_IPT];
     u32 valid_bits = 0;
-    if (PASS0) {
+    if (PASS0 && BULK) {
+        mbar_wait(&s_mbar[0], 0);
+        mbar_wait(&s_mbar[1], 0);
+        const i32 *s_idx = reinterpret_cast<const i32 *>(s_keys);
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            const u32 q = warp * (32 * RS_IPT) + k * 32 + lane;
+            const i32 hi = s_idx[q], lo = in.lo ? s_idx[RS_TILE + q] : 0;
+            const bool ok = ((u32)hi < in.extent_hi) && ((u32)lo < in.extent_lo) && input_kept(in, (u32)(tile_base + q), s_vals[q]);
+            key[k] = pack_key(hi, lo, in.bits_lo);
+            valid_bits |= (ok ? 1u : 0u) << k;
+        }
+    } else if (PASS0) {
 #pragma unroll
         for (int h = 0; h < RS_IPT; h += 8) {
             i32 hi[8], lo[8];

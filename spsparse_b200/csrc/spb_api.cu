@@ -240,6 +240,8 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     CK(cudaFuncSetAttribute(k_radix_pass9<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass9<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_pass<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_radix_pass9<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_radix_pass9<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R9_SMEM_BYTES));
     c->bulk_load = getenv("SPB_BULK_LOAD") ? atoi(getenv("SPB_BULK_LOAD")) != 0 : true;
     const char *s = getenv("SPB_MERGE_MAX_PRODUCTS");
@@ -485,9 +487,20 @@ static int run_radix_passes(spb_ctx *ctx, Scratch &ws, int first_pass, int passe
         if (p == 0 && first_pass == 0) {
             // pass 0 reads the caller's arrays and writes buffer A
             a.keys_in = nullptr; a.vals_in = nullptr; a.keys_out = kA; a.vals_out = vA;
-            ++ctx->launches;
-            if (nine) k_radix_pass9<true><<<tiles, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, *in0);
-            else k_radix_pass<true><<<tiles, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            // full tiles through the bulk-copy kernel when the caller's arrays allow 16-byte transfers, the last (partial)
+            // tile -- or everything -- through the plain one; both draw tile numbers from the same ticket counter
+            const bool aligned = ((((uintptr_t)in0->hi) | ((uintptr_t)in0->lo) | ((uintptr_t)in0->val)) & 15u) == 0;
+            const u32 tiles_bulk = (ctx->bulk_load && aligned) ? n_cap / RS_TILE : 0;
+            if (tiles_bulk) {
+                ++ctx->launches;
+                if (nine) k_radix_pass9<true, true><<<tiles_bulk, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, *in0);
+                else k_radix_pass<true, true><<<tiles_bulk, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            }
+            if (tiles > tiles_bulk) {
+                ++ctx->launches;
+                if (nine) k_radix_pass9<true><<<tiles - tiles_bulk, RS_THREADS, R9_SMEM_BYTES, ctx->stream>>>(a, *in0);
+                else k_radix_pass<true><<<tiles - tiles_bulk, RS_THREADS, RS_SMEM_BYTES, ctx->stream>>>(a, *in0);
+            }
             kin = kA; vin = vA; kout = kB; vout = vB;
             if (tm) *mark_after_first = tm->mark();
         } else {
@@ -594,25 +607,27 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     int t1 = t_passes, t2 = t_passes;
     u64 *const ks_rows = ks;      // grouped by row, insertion order inside: what both variants start from
     double *const vs_rows = vs;
+    // One host synchronisation per consolidate in the common case: the in-row sort and the reduce pass are both launched
+    // before the counters are read.  Only when rows longer than SEG_MAX turn up (hub rows) is the reduce pass run again,
+    // after those rows have been re-sorted by their full key.
+    bool long_rows_fixed = false;
     for (int attempt = 0;; ++attempt) {
         ks = ks_rows; vs = vs_rows;
+        u64 *ko = (ks == kA) ? kB : kA;
+        double *vo = (vs == vA) ? vB : vA;
+        const u32 stiles = (u32)div_up(n, SG_TILE);
         if (seg && !fused) {
             // rows are grouped (insertion order inside): order every row by column
-            u64 *ko = (ks == kA) ? kB : kA;
-            double *vo = (vs == vA) ? vB : vA;
-            const u32 stiles = (u32)div_up(n, SG_TILE);
-            ++ctx->launches;
-            if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
-            else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
-            CK(cudaGetLastError());
-            u32 hc[6];
-            CK(cudaMemcpyAsync(hc, counters, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            const u32 n_kept = hc[0], h_long = hc[5];
-            if (h_long && !hc[1]) {
-                // rows longer than SEG_MAX exist: their entries (left in place above) are pulled out in order, sorted by the
-                // full key with the radix passes, and put back -- the pulled-out sequence is ascending in the row, so sorted
-                // position i goes back where gathered position i came from
+            if (!long_rows_fixed) {
+                ++ctx->launches;
+                if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+                else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+                CK(cudaGetLastError());
+            } else {
+                // rows longer than SEG_MAX exist (h[0] kept entries, h[5] of them in such rows): their entries (left in place
+                // above) are pulled out in order, sorted by the full key with the radix passes, and put back -- the
+                // pulled-out sequence is ascending in the row, so sorted position i goes back where gathered position i came from
+                const u32 n_kept = h[0], h_long = h[5];
                 unsigned char *flags;
                 u64 *slot, *lk, *lk2, *lks;
                 double *lv, *lv2, *lvs;
@@ -662,10 +677,12 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
 
         CK(cudaMemcpyAsync(h, counters, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (fused && h[5] && !h[1] && attempt == 0) {
-            // rows longer than SEG_MAX: start over from the row-grouped array with the separate kernels
+        if (h[5] && !h[1] && attempt == 0 && seg) {
+            // rows longer than SEG_MAX: the reduce pass just run saw them unsorted -- do it again.  The fused kernel has no
+            // path for them: start over from the row-grouped array with the separate kernels.
             fused = false;
-            CK(cudaMemsetAsync(counters + 2, 0, 4 * sizeof(u32), ctx->stream));  // out count, long runs, rows, long-row entries
+            long_rows_fixed = true;
+            CK(cudaMemsetAsync(counters + 2, 0, 3 * sizeof(u32), ctx->stream));  // out count, long runs, rows (h[5] is re-counted)
             continue;
         }
         break;
@@ -978,25 +995,27 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
     CKR(ws.zeroed(&stats, 8));
     const u32 cap = (u32)ctx->sm_count * 32;
-    // longest row of op(A): picks the leanest register-merge kernels that still cover every mergeable row
-    {
-        spb_coo *Am = const_cast<spb_coo *>(A);
-        if (!Am->max_row_len && nrows) {
-            u32 *mx;
-            CKR(ws.zeroed(&mx, 1));
-            ++ctx->launches, k_row_maxlen<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m.arow_start, nrows, mx);
-            CK(cudaMemcpyAsync(&Am->max_row_len, mx, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-        }
+    // longest row of op(A): picks the leanest register-merge kernels that still cover every mergeable row.  Only the count
+    // kernel's choice for long B rows needs it up front; otherwise the count kernel itself reports it (stats[6]) and it is
+    // read back with the other counters -- one host round trip less per multiply of a freshly consolidated A.
+    const double avg_b_len = n_inner ? (double)B->n / (double)n_inner : 0.0;
+    spb_coo *Am = const_cast<spb_coo *>(A);
+    const bool maxlen_up_front = !Am->max_row_len && nrows && (avg_b_len > 16.0 || getenv("SPB_MERGE_NL_COUNT"));
+    if (maxlen_up_front) {
+        u32 *mx;
+        CKR(ws.zeroed(&mx, 1));
+        ++ctx->launches, k_row_maxlen<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m.arow_start, nrows, mx);
+        CK(cudaMemcpyAsync(&Am->max_row_len, mx, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
     }
-    const u32 a_maxlen = A->max_row_len;
-    const int nl_fit = a_maxlen <= 2 ? 2 : a_maxlen <= 4 ? 4 : a_maxlen <= 6 ? 6 : 8;
+    const bool maxlen_known = A->max_row_len != 0;
+    u32 a_maxlen = maxlen_known ? A->max_row_len : 0xffffffffu;   // unknown: the 8-list count kernel covers every row
+    int nl_fit = a_maxlen <= 2 ? 2 : a_maxlen <= 4 ? 4 : a_maxlen <= 6 ? 6 : 8;
     // Measured (tools/merge_sweep.py): the lean builds win where B rows are long (config 3: count 2.92 -> 2.35 ms);
     // with 5-entry B rows (config 5) the count kernel is fastest as the 8-list build (7.0 ms against 9.8 ms for the
     // 6-list one at a third more warps), while the numeric kernel still prefers the lean one (10.9 -> 8.8 ms).
-    const double avg_b_len = n_inner ? (double)B->n / (double)n_inner : 0.0;
     const int nl_count = getenv("SPB_MERGE_NL_COUNT") ? atoi(getenv("SPB_MERGE_NL_COUNT")) : (avg_b_len > 16.0 ? nl_fit : 8);
-    const int nl_num = getenv("SPB_MERGE_NL_NUMERIC") ? atoi(getenv("SPB_MERGE_NL_NUMERIC")) : nl_fit;
+    int nl_num = getenv("SPB_MERGE_NL_NUMERIC") ? atoi(getenv("SPB_MERGE_NL_NUMERIC")) : nl_fit;
     const int blk_count = getenv("SPB_MERGE_BLOCKS_COUNT") ? atoi(getenv("SPB_MERGE_BLOCKS_COUNT")) : 0;
     const int blk_num = getenv("SPB_MERGE_BLOCKS_NUMERIC") ? atoi(getenv("SPB_MERGE_BLOCKS_NUMERIC")) : 0;
     {
@@ -1021,10 +1040,22 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     ull h_stats[8];
     u32 *hash_rows = nullptr;
     u32 h_bad = 0;
+    // the rows are placed right away, as if there were no long rows (true for banded / regridding matrices): the output
+    // count then comes back with the counters in ONE round trip; with long rows the scan is repeated further down
+    u64 nnz_c_spec = 0;
+    CKR(ws.get(&c_ptr, (u64)nrows + 1));
+    CKR((exclusive_scan<u32, u64>(ctx, ws, row_cnt, c_ptr, nrows)));
     CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&h_bad, bad_vec, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&nnz_c_spec, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (h_bad) return bad_scale_vector();
+    if (!maxlen_known) {
+        Am->max_row_len = (u32)h_stats[6];
+        a_maxlen = A->max_row_len;
+        nl_fit = a_maxlen <= 2 ? 2 : a_maxlen <= 4 ? 4 : a_maxlen <= 6 ? 6 : 8;
+        if (!getenv("SPB_MERGE_NL_NUMERIC")) nl_num = nl_fit;
+    }
     if (h_stats[2]) {
         // long rows exist: products per A entry, their prefix sums, products per long row
         u32 *ent_f;
@@ -1145,11 +1176,12 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
 
     // ---- place the rows ---------------------------------------------------------------------------
     const int t_esc = tm.mark();
-    CKR(ws.get(&c_ptr, (u64)nrows + 1));
-    CKR((exclusive_scan<u32, u64>(ctx, ws, row_cnt, c_ptr, nrows)));
-    u64 nnz_c = 0;
-    CK(cudaMemcpyAsync(&nnz_c, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    u64 nnz_c = nnz_c_spec;
+    if (h_stats[2]) {   // long rows have filled in their counts since the speculative scan
+        CKR((exclusive_scan<u32, u64>(ctx, ws, row_cnt, c_ptr, nrows)));
+        CK(cudaMemcpyAsync(&nnz_c, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     const int t_sym = tm.mark();
     if (tracing()) fprintf(stderr, "[spb] mm: symbolic host %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (symbolic_only) {
@@ -1256,7 +1288,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         }
     }
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (h_stats[5]) CK(cudaStreamSynchronize(ctx->stream));   // h_shrunk is in flight
     if (h_shrunk) {
         // some hash-accumulator outputs summed to exact zero and were dropped: close the gaps (rare)
         unsigned char *keep;

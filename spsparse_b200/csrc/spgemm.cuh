@@ -210,7 +210,7 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
 // with half the registers and twice the warps.
 template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 4 ? 8 : NLMAX <= 6 ? 6 : 5; };
 
-// stats: [0] F of merged rows, [1] rows merged, [2] rows ESC
+// stats: [0] F of merged rows, [1] rows merged, [2] rows ESC, [6] longest row of op(A) (entries)
 template <int NLMAX>
 __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
     }
     u64 f_merge = (cls == ROW_MERGE) ? f : 0;
     u32 n_merge = (cls == ROW_MERGE), n_esc = (cls == ROW_ESC);
+    const u32 mylen = r < m.nrows ? m.arow_start[r + 1] - m.arow_start[r] : 0u;
+    const u32 maxlen = __reduce_max_sync(SPB_FULL_MASK, mylen);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         f_merge += __shfl_xor_sync(SPB_FULL_MASK, f_merge, o);
@@ -243,6 +245,7 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
         if (f_merge) atomicAdd(&stats[0], (ull)f_merge);
         if (n_merge) atomicAdd(&stats[1], (ull)n_merge);
         if (n_esc) atomicAdd(&stats[2], (ull)n_esc);
+        if (maxlen > (u32)stats[6]) atomicMax(&stats[6], (ull)maxlen);   // (plain read first: the maximum settles after a few blocks)
     }
 }
 

@@ -10,5 +10,5 @@ run t_cons 600 python -m pytest tests/test_gpu_consolidate.py -x -q -p no:cachep
 run t_full 600 python -m pytest tests/test_gpu_full_size.py -x -q -p no:cacheprovider -k "config2 or config5"
 SPB_BULK_LOAD=1 run bench_bulk1 300 python bench.py --no-e2e --no-cpu --no-also --steps 5 --warmup 3
 SPB_BULK_LOAD=0 run bench_bulk0 300 python bench.py --no-e2e --no-cpu --no-also --steps 5 --warmup 3
-SPB_BULK_LOAD=1 run probe1 100 python tools/radix9_probe.py 5e8 3
-SPB_BULK_LOAD=0 run probe0 100 python tools/radix9_probe.py 5e8 3
+SPB_BULK_LOAD=1 run probe1 100 python tools/radix9_probe.py 1e8 3
+SPB_BULK_LOAD=0 run probe0 100 python tools/radix9_probe.py 1e8 3
