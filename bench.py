@@ -416,10 +416,15 @@ def run_ours(args):
             hA = [pinned(nA, torch.int32), pinned(nA, torch.int32), pinned(nA, torch.float64)]
             hB = [pinned(nB, torch.int32), pinned(nB, torch.int32), pinned(nB, torch.float64)]
             wi, wv = w.to_host()
-            hW = [pinned(m, torch.int32), pinned(m, torch.float64)]
-            hW[0].numpy()[:] = wi[0]; hW[1].numpy()[:] = wv
             A_raw.to_host(out=([hA[0].numpy()[:nA], hA[1].numpy()[:nA]], hA[2].numpy()[:nA]))
             B_raw.to_host(out=([hB[0].numpy()[:nB], hB[1].numpy()[:nB]], hB[2].numpy()[:nB]))
+            # scalej: a rank only needs the entries of w whose index its block of A can reference (an index absent from a
+            # scale vector excludes that term, multiply_sparse.hpp:79-92 -- and no entry of the block has such an index), so
+            # it uploads that slice, not all 10^8 entries: found once from the host copy of the block's column indices
+            jlo, jhi = (int(hA[1].numpy()[:nA].min()), int(hA[1].numpy()[:nA].max())) if nA else (0, -1)
+            mW = jhi - jlo + 1
+            hW = [pinned(mW, torch.int32), pinned(mW, torch.float64)]
+            hW[0].numpy()[:mW] = wi[0][jlo:jhi + 1]; hW[1].numpy()[:mW] = wv[jlo:jhi + 1]
             ncap = int(st.nnz_c)
             hC = [pinned(ncap, torch.int32), pinned(ncap, torch.int32), pinned(ncap, torch.float64)]
             A_raw.free(); B_raw.free(); w.free()
@@ -433,9 +438,9 @@ def run_ours(args):
                        torch.empty(nA, dtype=torch.float64, device="cuda"),
                        torch.empty(nB, dtype=torch.int32, device="cuda"), torch.empty(nB, dtype=torch.int32, device="cuda"),
                        torch.empty(nB, dtype=torch.float64, device="cuda"),
-                       torch.empty(m, dtype=torch.int32, device="cuda"), torch.empty(m, dtype=torch.float64, device="cuda")]
+                       torch.empty(max(mW, 1), dtype=torch.int32, device="cuda"), torch.empty(max(mW, 1), dtype=torch.float64, device="cuda")]
                       for _ in range(2)]
-            host_in = [hA[0][:nA], hA[1][:nA], hA[2][:nA], hB[0][:nB], hB[1][:nB], hB[2][:nB], hW[0][:m], hW[1][:m]]
+            host_in = [hA[0][:nA], hA[1][:nA], hA[2][:nA], hB[0][:nB], hB[1][:nB], hB[2][:nB], hW[0][:max(mW, 1)], hW[1][:max(mW, 1)]]
             ready = [torch.cuda.Event(), torch.cuda.Event()]      # B and w of the slot are on the device
             ready_a = [torch.cuda.Event(), torch.cuda.Event()]    # ... and A (uploaded last: consolidate(B) starts under it)
             freed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -465,7 +470,7 @@ def run_ours(args):
                     d = dev_in[s_]
                     a = sp.CooArray.wrap_device(ctx, (m, m), [d[0].data_ptr(), d[1].data_ptr()], d[2].data_ptr(), nA)
                     b = sp.CooArray.wrap_device(ctx, (m, m), [d[3].data_ptr(), d[4].data_ptr()], d[5].data_ptr(), nB)
-                    ww = sp.CooArray.wrap_device(ctx, (m,), [d[6].data_ptr()], d[7].data_ptr(), m, (0,))
+                    ww = sp.CooArray.wrap_device(ctx, (m,), [d[6].data_ptr()], d[7].data_ptr(), mW, (0,))
                     Cm, _ = hot_path(a, b, ww, before_a=lambda: stream.wait_event(ready_a[s_]))
                     freed[s_].record(stream)
                     for x in (a, b, ww):
@@ -505,7 +510,7 @@ def run_ours(args):
             e2e_ok = (int(hv[0].item()) == fingerprint["index_checksum"]) and (int(hv[1].item()) == fingerprint["nnz_c"])
             ems = e0.elapsed_time(e1) / args.steps
             t = torch.tensor([ems], dtype=torch.float64, device="cuda")
-            b = torch.tensor([16.0 * nA + 16.0 * nB + 12.0 * m, 16.0 * nc], dtype=torch.float64, device="cuda")
+            b = torch.tensor([16.0 * nA + 16.0 * nB + 12.0 * mW, 16.0 * nc], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dist.all_reduce(b, op=dist.ReduceOp.SUM)
@@ -513,6 +518,8 @@ def run_ours(args):
                    "h2d_bytes_per_step": float(b[0].item()), "d2h_bytes_per_step": float(b[1].item()),
                    "result_matches_device_run": bool(e2e_ok),
                    "api": "pinned host buffers -> async H2D -> spb_coo_wrap_device + spb_consolidate x2 + spb_multiply_mm_prepared -> async D2H; steps software-pipelined (upload of step k+1 and download of step k overlap step k's kernels)"}
+            if rank == 0 and world == 1:
+                e2e.update(e2e_other_apis(ctx, sp, torch, args, m, hA, hB, (wi[0], wv), nA, nB, fingerprint))
             del hA, hB, hC
         else:
             A_raw.free(); B_raw.free(); w.free()
@@ -568,6 +575,61 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def e2e_other_apis(ctx, sp, torch, args, m, hA, hB, w_host, nA, nB, fingerprint):
+    """The same step end to end through the entry points a user of the reference binds, with PAGEABLE host memory (what
+    std::vector is), beside the pinned + pre-wrapped pipeline above:
+      cabi_pageable  spb_coo_upload x3 -> spb_multiply_mm -> spb_coo_download, plain numpy arrays, nothing overlapped
+                     across steps; the library moves pageable memory with worker threads through pinned staging buffers
+      cpp_api        spsparse::multiply(C, 1.0, NULL, A, '.', &w, B, '.', NULL) on VectorCooArrays (include/spsparse/), a
+                     C++ program of its own (tools/cpp/e2e_multiply.cpp) -- the reference's own entry point"""
+    import ctypes
+    out = {}
+    F = fingerprint
+    a = [np.array(t.numpy()[:nA]) for t in hA]          # pageable copies
+    b = [np.array(t.numpy()[:nB]) for t in hB]
+    wi, wv = np.ascontiguousarray(w_host[0]), np.ascontiguousarray(w_host[1])
+    ms = []
+    ok = True
+    for it in range(1 + min(args.steps, 2)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dA = sp.CooArray.from_host(ctx, (m, m), a[:2], a[2])
+        dB = sp.CooArray.from_host(ctx, (m, m), b[:2], b[2])
+        dW = sp.CooArray.from_host(ctx, (m,), [wi], wv, (0,))
+        Cm = sp.multiply(ctx, 1.0, None, dA, ".", dW, dB, ".", None)
+        idx, val = Cm.to_host()
+        dt = time.perf_counter() - t0
+        for x in (dA, dB, dW, Cm):
+            x.free()
+        if it:
+            ms.append(dt * 1e3)
+        with np.errstate(over="ignore"):
+            chk = int((idx[0].astype(np.int64) * 1000003 + idx[1]).sum())
+        ok = ok and chk == F["index_checksum"] and len(val) == F["nnz_c"]
+        del idx, val
+    out["cabi_pageable"] = {"ms_per_step": float(np.mean(ms)), "value": 25.0 * m / (float(np.mean(ms)) * 1e-3), "unit": UNIT,
+                            "h2d_bytes_per_step": 16.0 * nA + 16.0 * nB + 12.0 * m, "d2h_bytes_per_step": 16.0 * F["nnz_c"],
+                            "result_matches_device_run": bool(ok),
+                            "api": "pageable numpy arrays -> spb_coo_upload x3 -> spb_multiply_mm (consolidates A and B itself) -> spb_coo_download; one step at a time"}
+    del a, b
+    exe = os.path.join(ROOT, "tests", "cpp", "_bin", "e2e_multiply")
+    if os.path.exists(exe):
+        rel = ctypes.c_uint64()
+        ctx.lib.spb_ctx_trim(ctx.h, ctypes.byref(rel))   # the other process needs the device memory this one has cached
+        torch.cuda.empty_cache()
+        try:
+            r = subprocess.run([exe, str(m), str(min(args.steps, 2)), "1"], capture_output=True, text=True, timeout=900,
+                               env=dict(os.environ, SPSPARSE_B200_DEVICE=str(ctx.device)))
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            out["cpp_api"] = {"ms_per_step": j["ms_per_step"], "ms_best": j["ms_best"], "value": 25.0 * m / (j["ms_per_step"] * 1e-3), "unit": UNIT,
+                              "h2d_bytes_per_step": j["h2d_bytes_per_step"], "d2h_bytes_per_step": j["d2h_bytes_per_step"],
+                              "result_matches_device_run": (j["index_checksum"] - F["index_checksum"]) % (1 << 64) == 0 and j["nnz_c"] == F["nnz_c"],
+                              "api": "spsparse::multiply(C, 1.0, NULL, A, '.', &w, B, '.', NULL) on VectorCooArray<int,double,2> (std::vector storage), include/spsparse/; tools/cpp/e2e_multiply.cpp"}
+        except Exception as e:  # noqa: BLE001 -- a missing leg is reported, not fatal
+            out["cpp_api"] = {"unavailable": repr(e)[:300]}
+    return out
 
 
 def also_configs(ctx, sp, torch, stream, args, hbm):
@@ -677,7 +739,7 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
         plan_s = time.perf_counter() - t0
         A.free()
         sweeps = []
-        for sweep in range(1 + min(args.steps, 2)):     # one warm-up sweep, at most two timed ones (seconds each)
+        for sweep in range(2):     # one warm-up sweep, one timed one (seconds each)
             ctx.sync()
             t0 = time.perf_counter()
             sts = []
@@ -729,34 +791,54 @@ def banded_sample(n):
 
 
 def cpu_baseline(args):
-    """The reference's own CPU code on a bounded sample of the same workload family (rank 0, N=1)."""
-    impl, kind = ref_impl()
-    n = args.cpu_rows
-    A, B, W = banded_sample(n)
-    t0 = time.perf_counter()
-    if kind == "reference":
-        out, st = impl.multiply_mm(1.0, None, A, ".", W, B, ".", None, want_stats=True)
-        sec = st["seconds"]
-    else:
-        out = impl.multiply_mm(1.0, None, A, ".", W, B, ".", None)
-        sec = time.perf_counter() - t0
-    F = banded_products(n)
-    res = {"value": F / sec, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
-           "sample": f"first {n} rows of the banded family as an {n}x{n} problem: multiply(C,1,NULL,A,'.',&w,B,'.',NULL) "
-                     f"took {sec:.2f} s single-threaded (the reference has no threads); every row x column pair is merge-joined (multiply_sparse.hpp:192-246) and each join re-scans scalej from its start "
-                     f"(:223-228), so the cost grows as rows^2..rows^3: the full 1e8-row config is unreachable and products/s "
-                     f"falls with the row count",
-           "seconds": sec, "nnz_c": out.n}
-    # consolidate beside it (linearithmic, so this one extrapolates honestly)
+    """The reference's own CPU code on bounded samples of the same workload families (rank 0, N=1), as BASELINE.md section 5
+    lays out: consolidate on a prefix of the config-2 input (the whole 2*10^8-entry input with --cpu-full, ~3 min); multiply
+    on members of the banded family at two sizes with the fitted power law (the reference visits every row x column pair and
+    re-scans scalej per pair, so full size is unreachable -- said, not extrapolated silently); and the row-wise CPU oracle
+    (reference semantics, NOT the reference's algorithm) on a larger member, labelled as such."""
     from oracle import oracle as O
-    nc = args.cpu_cons_entries
-    a = O.port().gen_dup_coo(S2, 0, nc, int(nc * 0.7), 24, 0)
+    impl, kind = ref_impl()
+    sizes = [2 * args.cpu_rows, 4 * args.cpu_rows] if args.cpu_full else [args.cpu_rows // 2, args.cpu_rows]
+    runs = []
+    for n in sizes:
+        A, B, W = banded_sample(n)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            out, st = impl.multiply_mm(1.0, None, A, ".", W, B, ".", None, want_stats=True)
+            sec = st["seconds"]
+        else:
+            out = impl.multiply_mm(1.0, None, A, ".", W, B, ".", None)
+            sec = time.perf_counter() - t0
+        runs.append({"rows": n, "seconds": sec, "products": banded_products(n), "products_per_sec": banded_products(n) / sec,
+                     "row_col_pairs_per_sec": float(n) * n / sec, "nnz_c": out.n})
+    expo = float(np.log(runs[-1]["seconds"] / runs[0]["seconds"]) / np.log(runs[-1]["rows"] / runs[0]["rows"]))
+    n, sec, F = runs[-1]["rows"], runs[-1]["seconds"], runs[-1]["products"]
+    res = {"value": F / sec, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+           "sample": f"{n}x{n} member of the banded family: multiply(C,1,NULL,A,'.',&w,B,'.',NULL) took {sec:.2f} s single-threaded (the "
+                     f"reference has no threads); every row x column pair is merge-joined (multiply_sparse.hpp:192-246) and each join "
+                     f"re-scans scalej from its start (:223-228): measured time ~ rows^{expo:.2f} between {runs[0]['rows']} and {n} rows, so the "
+                     f"full 1e8-row config is unreachable and products/s falls with the row count",
+           "seconds": sec, "nnz_c": runs[-1]["nnz_c"], "multiply_runs": runs, "fitted_exponent": expo}
+    # consolidate beside it (linearithmic, so this one extrapolates honestly)
+    nc = 200_000_000 if args.cpu_full else args.cpu_cons_entries
+    a = O.port().gen_dup_coo(S2, 0, nc, 140_000_000 if nc == 200_000_000 else int(nc * 0.7), 24, 0)
     if kind == "reference":
-        sec, nout, _ = impl.consolidate_timed(a, (0, 1))
+        sec, nout, vsum = impl.consolidate_timed(a, (0, 1))
     else:
-        t0 = time.perf_counter(); nout = impl.consolidate(a, (0, 1)).n; sec = time.perf_counter() - t0
-    res["consolidate"] = {"nnz_per_sec": nout / sec, "entries_in_per_sec": nc / sec, "seconds": sec,
-                          "sample": f"first {nc} entries of the config-2 generator, consolidate(ret, A, {{0,1}})"}
+        t0 = time.perf_counter(); r = impl.consolidate(a, (0, 1)); nout, vsum = r.n, float(r.val.sum()); sec = time.perf_counter() - t0
+    res["consolidate"] = {"nnz_per_sec": nout / sec, "entries_in_per_sec": nc / sec, "seconds": sec, "nnz_out": nout, "sum_values": vsum,
+                          "sample": ("the whole config-2 input" if nc == 200_000_000 else f"first {nc} entries of the config-2 generator") +
+                                    ", consolidate(ret, A, {0,1}), " + ("genuine reference" if kind == "reference" else "oracle port")}
+    del a
+    # the row-wise CPU oracle: same results as the reference wherever the reference can run, linear in the products
+    no = 100_000_000 if args.cpu_full else args.cpu_oracle_rows
+    A, B, W = banded_sample(no)
+    t0 = time.perf_counter()
+    out = O.port().multiply_mm(1.0, None, A, ".", W, B, ".", None)
+    sec = time.perf_counter() - t0
+    res["row_wise_oracle"] = {"rows": no, "seconds": sec, "products_per_sec": banded_products(no) / sec, "nnz_c": out.n,
+                              "note": "reference-semantics CPU oracle (row-wise Gustavson, oracle/spsparse_oracle.c), NOT the reference's "
+                                      "algorithm; includes its consolidations of A and B; 1 core"}
     return res
 
 
@@ -800,22 +882,24 @@ def run_reference(args):
     _REF_JOB.update(impl=impl, A=A, B=B, W=W, bounds=[n * b // procs for b in range(procs + 1)])
     times = []
     ctxmp = mp.get_context("fork")
+    pool = ctxmp.Pool(procs) if procs > 1 else None   # created once, outside the timed steps
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        if procs == 1:
+        if pool is None:
             _ref_row_block(0)
         else:
-            with ctxmp.Pool(procs) as pool:
-                pool.map(_ref_row_block, range(procs))
+            pool.map(_ref_row_block, range(procs))
         sec = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(sec)
+    if pool is not None:
+        pool.close(); pool.join()
     sec = float(np.mean(times))
     value = F / sec
     sample = (f"{n}x{n} member of the banded family (the reference's multiply visits every row x column pair and re-scans scalej per pair: "
               f"rows^2..rows^3 work, 1e8 rows is unreachable), full call incl. its internal consolidations; the reference is "
               f"single-threaded, so {procs} independent processes each multiply one contiguous block of A's rows by the whole B "
-              f"(wall clock around all of them, process start-up included)")
+              f"(wall clock around all of them; the worker processes are started once, before the timed steps)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -839,7 +923,9 @@ def main():
     ap.add_argument("--rmat-scale-named", type=int, default=24, help="config 4 as named (row panels); 0 = skip")
     ap.add_argument("--panel-products", type=int, default=1 << 30, help="intermediate products per row panel")
     ap.add_argument("--cpu-rows", type=int, default=3000)
-    ap.add_argument("--cpu-cons-entries", type=int, default=10_000_000)
+    ap.add_argument("--cpu-cons-entries", type=int, default=30_000_000)
+    ap.add_argument("--cpu-oracle-rows", type=int, default=2_000_000)
+    ap.add_argument("--cpu-full", action="store_true", help="CPU baselines at BASELINE.md section 5's full sizes (minutes)")
     ap.add_argument("--ref-rows", type=int, default=2000)
     ap.add_argument("--ref-procs", type=int, default=0, help="processes of the reference arm (0 = all host cores)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -38,6 +38,7 @@ inline void upload(ArrT const &A, Handle &out) {
 // every index; otherwise one add() per entry (same calls the reference would have made).
 template <class IndexT, class ValT, int RANK>
 inline bool bulk_ok(VectorCooArray<IndexT, ValT, RANK> const &ret, const uint64_t *src_shape) {
+    if (!abi_types_ok<IndexT, ValT>::value) return false;   // other element types: one add() per entry
     for (int k = 0; k < RANK; ++k)
         if (ret.shape[k] < src_shape[k]) return false;
     return true;
@@ -45,13 +46,17 @@ inline bool bulk_ok(VectorCooArray<IndexT, ValT, RANK> const &ret, const uint64_
 template <class AccT>
 inline bool bulk_ok(AccT const &, const uint64_t *) { return false; }
 
+// the result is downloaded straight into the tail of the array's own vectors
 template <class IndexT, class ValT, int RANK>
-inline void bulk_append(VectorCooArray<IndexT, ValT, RANK> &ret, size_t n, std::vector<int32_t> *idx, std::vector<double> &val) {
-    const IndexT *p[2] = {reinterpret_cast<const IndexT *>(idx[0].data()), reinterpret_cast<const IndexT *>(idx[1].data())};
-    ret.append_raw(n, p, val.data());
+inline void bulk_append(VectorCooArray<IndexT, ValT, RANK> &ret, size_t n, spb_coo *h) {
+    IndexT *ip[2] = {nullptr, nullptr};
+    ValT *vp = nullptr;
+    ret.grow_raw(n, ip, &vp);
+    int32_t *p32[2] = {reinterpret_cast<int32_t *>(ip[0]), reinterpret_cast<int32_t *>(ip[1])};
+    check(spb_coo_download(default_context(), h, p32, reinterpret_cast<double *>(vp)));
 }
 template <class AccT>
-inline void bulk_append(AccT &, size_t, std::vector<int32_t> *, std::vector<double> &) {}
+inline void bulk_append(AccT &, size_t, spb_coo *) {}
 
 template <int RANK, class AccT>
 inline void deliver(AccT &ret, spb_coo *h) {
@@ -59,15 +64,15 @@ inline void deliver(AccT &ret, spb_coo *h) {
     uint64_t shape[2] = {0, 0}, n = 0;
     check(spb_coo_info(h, &rank, shape, &n, nullptr));
     if (n == 0) return;
+    if (bulk_ok(ret, shape)) {
+        bulk_append(ret, (size_t)n, h);
+        return;
+    }
     std::vector<int32_t> idx[2];
     std::vector<double> val(n);
     int32_t *ip[2] = {nullptr, nullptr};
     for (int k = 0; k < rank; ++k) { idx[k].resize(n); ip[k] = idx[k].data(); }
     check(spb_coo_download(default_context(), h, ip, val.data()));
-    if (bulk_ok(ret, shape)) {
-        bulk_append(ret, (size_t)n, idx, val);
-        return;
-    }
     for (size_t t = 0; t < n; ++t) {
         std::array<int, RANK> ix;
         for (int k = 0; k < RANK; ++k) ix[k] = idx[k][t];

@@ -227,6 +227,16 @@ public:
         val_vec.insert(val_vec.end(), val, val + n);
     }
 
+    // Room for `n` more entries at the end; returns where they start, so that a device result can be downloaded straight
+    // into the array's own vectors (no intermediate copy).  The caller fills every slot.
+    void grow_raw(size_t n, IndexT **idx_out, ValT **val_out) {
+        if (!edit_mode) (*spsparse_error)(-1, "Must be in edit mode to use VectorCooArray::add()");
+        const size_t old = val_vec.size();
+        for (int k = 0; k < RANK; ++k) { index_vecs[k].resize(old + n); idx_out[k] = index_vecs[k].data() + old; }
+        val_vec.resize(old + n);
+        *val_out = val_vec.data() + old;
+    }
+
     // ---- in-place algorithms (defined in algorithm.hpp)
     void consolidate(std::array<int, RANK> const &_sort_order, DuplicatePolicy duplicate_policy = DuplicatePolicy::ADD,
                      bool handle_nan = false);

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -121,6 +122,13 @@ struct spb_ctx {
     int hash_variant;        // 0: 1024 threads x 10240 outputs per item, 1: 512 x 5120 (two blocks per SM), 2: 256 x 2560 (four)  (SPB_HASH_VARIANT)
     u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
     bool bulk_load;          // radix passes after the first bring their tile in with cp.async.bulk (SPB_BULK_LOAD, default on)
+    // pageable host memory <-> device: worker threads copy through pinned staging buffers (see staged_copy)
+    static constexpr int XFER_WORKERS = 4;
+    static constexpr size_t XFER_CHUNK = 16u << 20;
+    void *xfer_buf[XFER_WORKERS][2];
+    cudaStream_t xfer_stream[XFER_WORKERS];
+    cudaEvent_t xfer_ev[XFER_WORKERS][2];
+    bool xfer_ready;
     DevPool pool;
 };
 
@@ -204,6 +212,102 @@ static inline u32 grid_for(u64 n, u32 threads, u32 cap) {
     return (u32)(g < cap ? g : cap);
 }
 
+// ---- host <-> device transfers of caller memory -----------------------------------------------------------------------
+// A reference user's arrays are std::vectors: pageable memory, which the driver can only move through its own single
+// staging pipeline (6-10 GB/s measured).  Here XFER_WORKERS threads each copy every XFER_WORKERS-th chunk between the
+// caller's memory and a pinned double buffer of their own and move it with an asynchronous copy on their own stream, so
+// the CPU-side copies of several chunks and the DMA transfers overlap.  Pinned (or registered) caller memory is moved
+// directly.  Synchronous for the caller, as the C ABI promises.
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int xfer_setup(spb_ctx *c) {
+    if (c->xfer_ready) return 0;
+    for (int w = 0; w < spb_ctx::XFER_WORKERS; ++w) {
+        CK(cudaStreamCreateWithFlags(&c->xfer_stream[w], cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CK(cudaHostAlloc(&c->xfer_buf[w][b], spb_ctx::XFER_CHUNK, cudaHostAllocDefault));
+            CK(cudaEventCreateWithFlags(&c->xfer_ev[w][b], cudaEventDisableTiming));
+        }
+    }
+    c->xfer_ready = true;
+    return 0;
+}
+
+struct XferJob { void *dev; void *host; size_t bytes; };   // one array
+
+// to_device: host -> dev, else dev -> host.  The device side must be complete / consumable on ctx->stream order: the
+// caller synchronises ctx->stream before (downloads) -- uploads land before this returns.
+static int staged_copy(spb_ctx *c, const XferJob *jobs, int njobs, bool to_device) {
+    // pinned caller memory: plain asynchronous copies
+    bool all_pinned = true;
+    size_t total = 0;
+    for (int j = 0; j < njobs; ++j) { if (jobs[j].bytes) { all_pinned = all_pinned && host_ptr_is_pinned(jobs[j].host); total += jobs[j].bytes; } }
+    if (all_pinned || total < (4u << 20)) {
+        for (int j = 0; j < njobs; ++j)
+            if (jobs[j].bytes)
+                CK(cudaMemcpyAsync(to_device ? jobs[j].dev : jobs[j].host, to_device ? jobs[j].host : jobs[j].dev, jobs[j].bytes,
+                                   to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    CKR(xfer_setup(c));
+    // the chunk list over all arrays
+    struct Chunk { char *dev; char *host; size_t bytes; };
+    std::vector<Chunk> chunks;
+    for (int j = 0; j < njobs; ++j)
+        for (size_t o = 0; o < jobs[j].bytes; o += spb_ctx::XFER_CHUNK)
+            chunks.push_back({(char *)jobs[j].dev + o, (char *)jobs[j].host + o, std::min(spb_ctx::XFER_CHUNK, jobs[j].bytes - o)});
+    cudaError_t err[spb_ctx::XFER_WORKERS];
+    auto work = [&](int w) {
+        cudaError_t e = cudaSetDevice(c->device);
+        int b = 0;
+        size_t pending_chunk[2] = {(size_t)-1, (size_t)-1};   // downloads: chunk whose DMA into buffer b is in flight
+        for (size_t k = w; k < chunks.size() && e == cudaSuccess; k += spb_ctx::XFER_WORKERS, b ^= 1) {
+            const Chunk &ch = chunks[k];
+            if (to_device) {
+                e = cudaEventSynchronize(c->xfer_ev[w][b]);                       // the buffer's previous DMA has finished
+                if (e != cudaSuccess) break;
+                memcpy(c->xfer_buf[w][b], ch.host, ch.bytes);
+                e = cudaMemcpyAsync(ch.dev, c->xfer_buf[w][b], ch.bytes, cudaMemcpyHostToDevice, c->xfer_stream[w]);
+                if (e == cudaSuccess) e = cudaEventRecord(c->xfer_ev[w][b], c->xfer_stream[w]);
+            } else {
+                // start this chunk's DMA, then drain the other buffer (its DMA was started one round ago)
+                e = cudaMemcpyAsync(c->xfer_buf[w][b], ch.dev, ch.bytes, cudaMemcpyDeviceToHost, c->xfer_stream[w]);
+                if (e == cudaSuccess) e = cudaEventRecord(c->xfer_ev[w][b], c->xfer_stream[w]);
+                pending_chunk[b] = k;
+                const int o = b ^ 1;
+                if (e == cudaSuccess && pending_chunk[o] != (size_t)-1) {
+                    e = cudaEventSynchronize(c->xfer_ev[w][o]);
+                    if (e == cudaSuccess) memcpy(chunks[pending_chunk[o]].host, c->xfer_buf[w][o], chunks[pending_chunk[o]].bytes);
+                    pending_chunk[o] = (size_t)-1;
+                }
+            }
+        }
+        if (!to_device)
+            for (int o = 0; o < 2 && e == cudaSuccess; ++o)
+                if (pending_chunk[o] != (size_t)-1) {
+                    e = cudaEventSynchronize(c->xfer_ev[w][o]);
+                    if (e == cudaSuccess) memcpy(chunks[pending_chunk[o]].host, c->xfer_buf[w][o], chunks[pending_chunk[o]].bytes);
+                }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->xfer_stream[w]);
+        err[w] = e;
+    };
+    // downloads: what is read was produced on the context's stream; uploads: the destination blocks may have been handed
+    // back to the pool by work that is still running there
+    CK(cudaStreamSynchronize(c->stream));
+    std::thread th[spb_ctx::XFER_WORKERS];
+    for (int w = 1; w < spb_ctx::XFER_WORKERS; ++w) th[w] = std::thread(work, w);
+    work(0);
+    for (int w = 1; w < spb_ctx::XFER_WORKERS; ++w) th[w].join();
+    for (int w = 0; w < spb_ctx::XFER_WORKERS; ++w)
+        if (err[w] != cudaSuccess) return spb_fail(SPB_ERR_CUDA, "host transfer failed: %s", cudaGetErrorString(err[w]));
+    return 0;
+}
+
 // ==================================================================================================
 extern "C" {
 
@@ -249,6 +353,7 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     s = getenv("SPB_ESC_CHUNK");
     c->esc_chunk = s ? strtoull(s, nullptr, 10) : (1ull << 27);
     c->launches = 0;
+    c->xfer_ready = false;
     s = getenv("SPB_HASH_MIN_PRODUCTS");
     c->hash_min_products = s ? (strcmp(s, "off") == 0 ? ~0ull : strtoull(s, nullptr, 10)) : 512ull;
     s = getenv("SPB_HASH_VARIANT");
@@ -268,6 +373,11 @@ int spb_ctx_destroy(spb_ctx *ctx) {
     if (!ctx) return SPB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->xfer_ready)
+        for (int w = 0; w < spb_ctx::XFER_WORKERS; ++w) {
+            cudaStreamDestroy(ctx->xfer_stream[w]);
+            for (int b = 0; b < 2; ++b) { cudaFreeHost(ctx->xfer_buf[w][b]); cudaEventDestroy(ctx->xfer_ev[w][b]); }
+        }
     ctx->pool.destroy();
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -374,17 +484,19 @@ int spb_coo_upload(spb_ctx *ctx, int rank, const uint64_t *shape, const int32_t 
     CKR(coo_new(ctx, rank, shape, n, true, out));
     spb_coo *a = *out;
     set_order(a, sort_order);
-    cudaError_t e = cudaSuccess;
-    for (int k = 0; k < rank && n && e == cudaSuccess; ++k) {
+    XferJob jobs[3];
+    int nj = 0;
+    for (int k = 0; k < rank && n; ++k) {
         if (!idx[k]) { spb_coo_free(ctx, a); *out = nullptr; return spb_fail(SPB_ERR_ARG, "null index pointer for dimension %d", k); }
-        e = cudaMemcpyAsync(a->idx[k], idx[k], n * sizeof(i32), cudaMemcpyHostToDevice, ctx->stream);
+        jobs[nj++] = {a->idx[k], const_cast<int32_t *>(idx[k]), (size_t)n * sizeof(i32)};
     }
-    if (n && e == cudaSuccess) e = cudaMemcpyAsync(a->val, val, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host buffers are free to go when we return
-    if (e != cudaSuccess) {
+    if (n) jobs[nj++] = {a->val, const_cast<double *>(val), (size_t)n * sizeof(double)};
+    // (the uploaded arrays are used on ctx->stream afterwards: the copies are complete when this returns)
+    const int rc = nj ? staged_copy(ctx, jobs, nj, true) : 0;  // host buffers are free to go when we return
+    if (rc) {
         spb_coo_free(ctx, a);
         *out = nullptr;
-        return spb_fail(SPB_ERR_CUDA, "upload of %llu entries failed: %s", (ull)n, cudaGetErrorString(e));
+        return rc;
     }
     return SPB_OK;
 }
@@ -428,11 +540,15 @@ int spb_coo_set_sorted(spb_coo *a, const int *sort_order) {
 
 int spb_coo_download(spb_ctx *ctx, const spb_coo *a, int32_t *const *idx, double *val) {
     if (!ctx || !a) return spb_fail(SPB_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    XferJob jobs[3];
+    int nj = 0;
     if (a->n) {
         for (int k = 0; k < a->rank; ++k)
-            if (idx && idx[k]) CK(cudaMemcpyAsync(idx[k], a->idx[k], a->n * sizeof(i32), cudaMemcpyDeviceToHost, ctx->stream));
-        if (val) CK(cudaMemcpyAsync(val, a->val, a->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (idx && idx[k]) jobs[nj++] = {a->idx[k], idx[k], (size_t)a->n * sizeof(i32)};
+        if (val) jobs[nj++] = {a->val, val, (size_t)a->n * sizeof(double)};
     }
+    if (nj) return staged_copy(ctx, jobs, nj, false);
     CK(cudaStreamSynchronize(ctx->stream));
     return SPB_OK;
 }
