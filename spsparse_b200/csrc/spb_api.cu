@@ -358,8 +358,7 @@ int spb_ctx_create(int device, void *cuda_stream, spb_ctx **out) {
     c->hash_min_products = s ? (strcmp(s, "off") == 0 ? ~0ull : strtoull(s, nullptr, 10)) : 512ull;
     s = getenv("SPB_HASH_VARIANT");
     c->hash_variant = s ? atoi(s) : 2;  // R-MAT scale 20, numeric pass: 1 x 1024 threads 82 ms, 2 x 512 72.9 ms, 4 x 256 70.3 ms
-    CK(cudaFuncSetAttribute(k_hash_symbolic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
-    CK(cudaFuncSetAttribute(k_hash_symbolic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
+    CK(cudaFuncSetAttribute(k_hash_symbolic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(HASH_MAX_COLS / 8)));
     CK(cudaFuncSetAttribute(k_hash_numeric<1024, 10240, 16384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<1024, 10240, 16384>)));
     CK(cudaFuncSetAttribute(k_hash_numeric<512, 5120, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<512, 5120, 8192>)));
     CK(cudaFuncSetAttribute(k_hash_numeric<256, 2560, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<256, 2560, 4096>)));
@@ -1109,7 +1108,9 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     ull *stats;  // [0] F merged rows, [1] rows merged, [2] rows long, [3] F ESC rows, [4] F HASH rows, [5] rows HASH
     CKR(ws.get(&row_cls, nrows));
     CKR(ws.zeroed(&row_cnt, (u64)nrows + 1));
+    ull *mstats;  // the count kernel's striped counters (MC_STRIPES x 8), summed on the host
     CKR(ws.zeroed(&stats, 8));
+    CKR(ws.zeroed(&mstats, (u64)MC_STRIPES * 8));
     const u32 cap = (u32)ctx->sm_count * 32;
     // longest row of op(A): picks the leanest register-merge kernels that still cover every mergeable row.  Only the count
     // kernel's choice for long B rows needs it up front; otherwise the count kernel itself reports it (stats[6]) and it is
@@ -1144,7 +1145,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         const int carve_c = getenv("SPB_MERGE_CARVEOUT_COUNT") ? atoi(getenv("SPB_MERGE_CARVEOUT_COUNT")) : (avg_b_row > 16.0 ? 25 : -1);
 #define SPB_LAUNCH_COUNT(NL) do { if (bal) CKR(allow_ballast(k_merge_count<NL>)); \
         if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
-        k_merge_count<NL><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, stats); } while (0)
+        k_merge_count<NL><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); } while (0)
         if (nl_count <= 2 && nl_fit <= 2) SPB_LAUNCH_COUNT(2);
         else if (nl_count <= 4 && nl_fit <= 4) SPB_LAUNCH_COUNT(4);
         else if (nl_count <= 6 && nl_fit <= 6) SPB_LAUNCH_COUNT(6);
@@ -1161,10 +1162,16 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     u64 nnz_c_spec = 0;
     CKR(ws.get(&c_ptr, (u64)nrows + 1));
     CKR((exclusive_scan<u32, u64>(ctx, ws, row_cnt, c_ptr, nrows)));
-    CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
+    ull h_mstats[MC_STRIPES * 8];
+    CK(cudaMemcpyAsync(h_mstats, mstats, sizeof h_mstats, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&h_bad, bad_vec, sizeof h_bad, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&nnz_c_spec, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    memset(h_stats, 0, sizeof h_stats);
+    for (int sx = 0; sx < MC_STRIPES; ++sx) {
+        for (int q = 0; q < 3; ++q) h_stats[q] += h_mstats[sx * 8 + q];
+        if (h_mstats[sx * 8 + 6] > h_stats[6]) h_stats[6] = h_mstats[sx * 8 + 6];
+    }
     if (h_bad) return bad_scale_vector();
     if (!maxlen_known) {
         Am->max_row_len = (u32)h_stats[6];
@@ -1185,8 +1192,10 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         if (hash_ok) CKR(ws.get(&hash_rows, h_stats[2]));
         ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, ctx->hash_min_products, hash_rows, stats);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h_stats, stats, sizeof h_stats, cudaMemcpyDeviceToHost, ctx->stream));
+        ull h_long[8];
+        CK(cudaMemcpyAsync(h_long, stats, sizeof h_long, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        h_stats[3] = h_long[3]; h_stats[4] = h_long[4]; h_stats[5] = h_long[5];   // [0..2], [6] came from the count kernel's stripes
         ws.release(ent_f);
     }
 
@@ -1212,18 +1221,34 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         }
         ha.n_win = (u32)div_up(n_cols ? n_cols : 1, win_cols);
         ha.win_cols = (u32)win_cols;
-        if (ha.n_win > 1) CKR(ws.zeroed(&ha.win_cnt, (u64)ha.nrows * ha.n_win));
+        const u64 units = (u64)ha.nrows * ha.n_win;
+        CKR(ws.get(&ha.win_cnt, units));
+        CKR(ws.get(&ha.win_pre, units));
+        CKR(ws.get(&ha.seg_off, units));
+        // the rows' output columns, written by the one bitmap pass before the rows are placed: at most one per product
+        u64 tmp_cap = h_stats[4];
+        if (tmp_cap > (u64)ha.nrows * n_cols) tmp_cap = (u64)ha.nrows * n_cols;
+        CKR(ws.get(&ha.tmp_k, tmp_cap));
         ha.wpw = (u32)(div_up(div_up(ha.n_win > 1 ? win_cols : n_cols, 32), HS_WARPS) + 31) & ~31u;
         ha.cap = hash_cap;
         ha.row_cnt = row_cnt;
-        hs_grid = (u64)ha.nrows * ha.n_win < (u64)ctx->sm_count ? ha.nrows * ha.n_win : (u32)ctx->sm_count;
+        hs_grid = units < (u64)ctx->sm_count ? (u32)units : (u32)ctx->sm_count;
         hs_smem = (size_t)HS_WARPS * ha.wpw * sizeof(u32);
         CKR(ws.zeroed(&ha.next, 4));
         ha.shrunk = ha.next + 1;
         ha.n_items = ha.next + 2;
-        CKR(ws.zeroed(&ha.split_total, 1));
+        CKR(ws.zeroed(&ha.split_total, 2));
+        ha.tmp_cursor = ha.split_total + 1;
         CKR(ws.get(&ha.row_split, ha.nrows));
-        ++ctx->launches, k_hash_symbolic<false><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
+        if (ha.n_win > 1 && (u64)m.nnz_a * (ha.n_win - 1) <= (1ull << 30) && !getenv("SPB_HASH_NO_WIN_BOUNDS")) {
+            // wide matrix: where every window begins in every B row, found by one parallel kernel (4 GB of positions at most;
+            // beyond that the bitmap kernel searches for itself)
+            u32 *wb;
+            CKR(ws.get(&wb, (u64)m.nnz_a * (ha.n_win - 1)));
+            ++ctx->launches, k_hash_win_bounds<<<ha.nrows < 65535u * 16u ? ha.nrows : 65535u * 16u, 128, 0, ctx->stream>>>(m, ha, wb);
+            ha.win_bound = wb;
+        }
+        ++ctx->launches, k_hash_symbolic<<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());
     }
 
@@ -1354,13 +1379,12 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     u32 h_shrunk = 0;
     int t_hemit0 = tm.mark(), t_hemit1 = t_hemit0, t_hsplit = t_hemit0, t_hnum = t_hemit0;
     if (h_stats[5] && nnz_c) {
-        // emit pass: the bitmap again, now writing the rows' columns into C and cutting the rows into work items
+        // the rows are placed: cut them into work items (the columns were listed by the bitmap pass of the symbolic phase)
         u32 h_items = 0;
         const u64 max_items = h_stats[5] + nnz_c / hash_cap + 1;
         CKR(ws.get(&ha.items, max_items));
-        CK(cudaMemsetAsync(ha.next, 0, sizeof(u32), ctx->stream));
         ha.c_ptr = c_ptr; ha.c_i = out->idx[0]; ha.c_k = out->idx[1]; ha.c_v = out->val;
-        ++ctx->launches, k_hash_symbolic<true><<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
+        ++ctx->launches, k_hash_items<<<grid_for((u64)ha.nrows * 32, 256, (u32)ctx->sm_count * 8), 256, 0, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());
         ull h_split = 0;
         t_hemit1 = t_hsplit = t_hnum = tm.mark();

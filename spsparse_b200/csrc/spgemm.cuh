@@ -210,7 +210,11 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
 // with half the registers and twice the warps.
 template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 4 ? 8 : NLMAX <= 6 ? 6 : 5; };
 
-// stats: [0] F of merged rows, [1] rows merged, [2] rows ESC, [6] longest row of op(A) (entries)
+// stats: MC_STRIPES stripes of 8 counters, one cache line apart in pairs -- [0] F of merged rows, [1] rows merged, [2] rows
+// ESC, [6] longest row of op(A) (entries); a block adds its totals to stripe blockIdx % MC_STRIPES and the host sums the
+// stripes.  (One set of counters for the whole grid, one atomic per warp, made this kernel wait for the L2 atomic unit of a
+// single address: 6 M atomics on one cache line in a 6.5 ms kernel.)
+constexpr int MC_STRIPES = 64;
 template <int NLMAX>
 __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
@@ -241,11 +245,17 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
         n_merge += __shfl_xor_sync(SPB_FULL_MASK, n_merge, o);
         n_esc += __shfl_xor_sync(SPB_FULL_MASK, n_esc, o);
     }
-    if (lane_id() == 0) {
-        if (f_merge) atomicAdd(&stats[0], (ull)f_merge);
-        if (n_merge) atomicAdd(&stats[1], (ull)n_merge);
-        if (n_esc) atomicAdd(&stats[2], (ull)n_esc);
-        if (maxlen > (u32)stats[6]) atomicMax(&stats[6], (ull)maxlen);   // (plain read first: the maximum settles after a few blocks)
+    __shared__ ull s_tot[4][4];   // [warp][F, rows merged, rows ESC, longest row]
+    const u32 warp = threadIdx.x >> 5;
+    if (lane_id() == 0) { s_tot[warp][0] = f_merge; s_tot[warp][1] = n_merge; s_tot[warp][2] = n_esc; s_tot[warp][3] = maxlen; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const u32 q = threadIdx.x;
+        ull t = s_tot[0][q];
+        for (u32 w = 1; w < (blockDim.x >> 5); ++w) t = q == 3 ? max(t, s_tot[w][q]) : t + s_tot[w][q];
+        ull *mine = stats + (size_t)(blockIdx.x % MC_STRIPES) * 8;
+        if (q == 3) { if (t) atomicMax(&mine[6], t); }
+        else if (t) atomicAdd(&mine[q], t);
     }
 }
 
@@ -364,8 +374,14 @@ struct HashArgs {
     u32 cap;             // outputs per numeric work item (HASH_CAP of the numeric kernel that will run)
     u32 n_win;           // column windows per row: the bitmap covers win_cols columns at a time (1 when they all fit)
     u32 win_cols;        // multiple of 32
-    u32 *win_cnt;        // [nrows * n_win] count pass: outputs of (row, window); only used when n_win > 1
-    u32 *row_cnt;        // count pass: number of distinct, unmasked output columns of the row (zeroed; windows add up)
+    u32 *win_cnt;        // [nrows * n_win] outputs of (row, window)
+    u32 *row_cnt;        // number of distinct, unmasked output columns of the row (zeroed; windows add up)
+    i32 *tmp_k;          // the output columns of the hash rows, one ascending segment per (row, window), segments in no particular order
+    ull *tmp_cursor;     // entries of tmp_k handed out
+    u64 *seg_off;        // [nrows * n_win] where the segment of (row, window) starts in tmp_k
+    u32 *win_pre;        // [nrows * n_win] outputs of the row in earlier windows (k_hash_items)
+    const u32 *win_bound; // [nnz_a * (n_win - 1)] or nullptr: win_bound[e * (n_win - 1) + w - 1] = first position of the B row of A
+                         // entry e whose column is >= w * win_cols (k_hash_win_bounds); nullptr: searched inside the bitmap kernel
     const u64 *c_ptr;    // emit + numeric
     i32 *c_i, *c_k;
     double *c_v;
@@ -426,13 +442,77 @@ __device__ __forceinline__ void stage_entries(u32 bs, u32 len, u32 *st_bs, u32 *
 
 __device__ __forceinline__ u32 hn_lower_bound(const i32 *__restrict__ b_k, u32 lo, u32 hi, i32 key);
 
+// Where every column window begins in the B row of every entry of the ROW_HASH rows: one independent search per (entry,
+// window boundary), hundreds of thousands in flight -- inside the bitmap kernel the same searches were two chains of
+// dependent L2 round trips in front of every (row, window) unit, 45 % of its time at 2^24 columns (11 windows).
+__global__ void __launch_bounds__(128) k_hash_win_bounds(MMOperands m, HashArgs a, u32 *win_bound) {
+    const u32 nb = a.n_win - 1;
+    for (u32 hrow = blockIdx.x; hrow < a.nrows; hrow += gridDim.x) {
+        const u32 r = a.rows[hrow];
+        const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
+        for (u32 t = threadIdx.x; t < len * nb; t += blockDim.x) {
+            const u32 x = t / nb, w = t % nb + 1;
+            const i32 j = m.a_j[s + x];
+            const u64 col = (u64)w * a.win_cols;
+            const u32 bs = m.bptr[j], be = m.bptr[j + 1];
+            win_bound[(u64)(s + x) * nb + (w - 1)] = col <= (u64)INT32_MAX ? hn_lower_bound(m.b_k, bs, be, (i32)col) : be;
+        }
+    }
+}
+
+// column of output number t (ascending) of ROW_HASH row hrow: the windows' segments of tmp_k in window order
+__device__ __forceinline__ i32 hash_col(const HashArgs &a, u32 hrow, u32 t) {
+    const u64 u0 = (u64)hrow * a.n_win;
+    if (a.n_win == 1) return a.tmp_k[a.seg_off[u0] + t];
+    const u32 *pre = a.win_pre + u0;
+    u32 lo = 0, hi = a.n_win;   // last window w with pre[w] <= t (empty windows share their successor's prefix: the last one holds t)
+    while (hi - lo > 1) {
+        const u32 mid = lo + (hi - lo) / 2;
+        if (pre[mid] <= t) lo = mid; else hi = mid;
+    }
+    return a.tmp_k[a.seg_off[u0 + lo] + (t - pre[lo])];
+}
+
+// After the bitmap pass: per ROW_HASH row (one warp each) the prefix of its windows' counts, its work items (<= cap outputs
+// each, cut by output rank over the whole row) and its block of split[] (k_hash_splits)
+__global__ void __launch_bounds__(256) k_hash_items(MMOperands m, HashArgs a) {
+    const u32 lane = lane_id();
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 hrow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); hrow < a.nrows; hrow += warps) {
+        const u32 r = a.rows[hrow];
+        const u64 u0 = (u64)hrow * a.n_win;
+        u32 run = 0;
+        for (u32 w0 = 0; w0 < a.n_win; w0 += 32) {
+            const u32 w = w0 + lane;
+            const u32 c = w < a.n_win ? a.win_cnt[u0 + w] : 0;
+            const u32 incl = warp_incl_scan(c);
+            if (w < a.n_win) a.win_pre[u0 + w] = run + incl - c;
+            run += __shfl_sync(SPB_FULL_MASK, incl, 31);
+        }
+        const u32 total = run;   // == row_cnt[r]
+        const u32 n_items = (total + a.cap - 1) / a.cap;
+        u32 item0 = 0;
+        if (lane == 0 && n_items) {
+            item0 = atomicAdd(a.n_items, n_items);
+            if (n_items > 1) a.row_split[hrow] = atomicAdd(a.split_total, (ull)(n_items - 1) * (m.arow_start[r + 1] - m.arow_start[r]));
+        }
+        item0 = __shfl_sync(SPB_FULL_MASK, item0, 0);
+        for (u32 p = lane; p < n_items; p += 32) a.items[item0 + p] = ((u64)hrow << 32) | p;
+    }
+}
+
 // ---- symbolic: bitmap --------------------------------------------------------------------------------------------
 // Matrices with more columns than the bitmap holds are handled in column windows of win_cols columns: a work unit is
 // (row, window); every B row is narrowed to the window by two searches when it is staged.
-template <bool EMIT>
+// ONE pass (round 1 ran the bitmap twice, once to count and once to emit): when a (row, window)'s bitmap is complete its
+// set bits are counted, a segment of that many entries is taken from the temporary column list tmp_k (an atomic cursor:
+// segments land in no particular order, seg_off remembers where) and the columns are written there in ascending order.
+// The rows' output counts (row_cnt) come out of the same pass; the numeric kernel later copies the columns into C.
 __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, HashArgs a) {
+    constexpr bool EMIT = true;
     extern __shared__ u32 s_bitmap[];  // HS_WARPS * a.wpw words
-    __shared__ u32 s_row, s_item0, s_grab, s_winbase;
+    __shared__ u32 s_row, s_grab;
+    __shared__ u64 s_segbase;
     __shared__ u32 s_wsum[2][HS_WARPS];
     __shared__ u32 s_bs[HS_THREADS], s_pre[HS_THREADS + 1];
     __shared__ u32 s_gcnt[HASH_MAX_COLS / 1024];  // set bits per group of 32 bitmap words, then their exclusive prefix
@@ -459,7 +539,11 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
                 if (!m.sj_mask || m.sj_mask[j]) {
                     bs = m.bptr[j];
                     u32 be = m.bptr[j + 1];
-                    if (a.n_win > 1 && bs < be) {
+                    if (a.n_win > 1 && a.win_bound) {
+                        const u32 *wb = a.win_bound + (u64)ent * (a.n_win - 1);
+                        if (win > 0) bs = wb[win - 1];
+                        if (win + 1 < a.n_win) be = wb[win];
+                    } else if (a.n_win > 1 && bs < be) {
                         bs = hn_lower_bound(m.b_k, bs, be, (i32)col0);
                         if ((u64)col0 + a.win_cols <= (u64)INT32_MAX) be = hn_lower_bound(m.b_k, bs, be, (i32)(col0 + a.win_cols));
                     }
@@ -568,29 +652,28 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             if (l0) s_glist[lbefore] = (unsigned short)g0;
             if (l1) s_glist[lbefore + l0] = (unsigned short)g1;
         }
-        // work items of the numeric pass are cut from the whole row: the row's first window creates them
-        const u32 row_total = a.n_win > 1 ? (u32)(a.c_ptr[r + 1] - a.c_ptr[r]) : total;
-        const u32 n_items = win == 0 ? (row_total + a.cap - 1) / a.cap : 0;
         if (tid == 0) {
-            if (win == 0) {
-                s_item0 = atomicAdd(a.n_items, n_items);
-                if (n_items > 1) a.row_split[hrow] = atomicAdd(a.split_total, (ull)(n_items - 1) * (e - s));
-            }
-            u32 before_win = 0;  // outputs of this row in earlier windows
-            for (u32 w2 = 0; w2 < win; ++w2) before_win += a.win_cnt[(u64)hrow * a.n_win + w2];
-            s_winbase = before_win;
+            const u64 unit = (u64)hrow * a.n_win + win;
+            s_segbase = total ? atomicAdd(a.tmp_cursor, (ull)total) : 0ull;
+            a.seg_off[unit] = s_segbase;
+            a.win_cnt[unit] = total;
+            if (total) atomicAdd(&a.row_cnt[r], total);
             s_grab = 0;
         }
         __syncthreads();
         // ---- ... and the columns are written, one non-empty group per warp at a time (grabbed from a counter: the
         //      groups of a power-law row differ in weight by orders of magnitude): the lanes hold 32 consecutive
         //      words, so their outputs are consecutive in C ------------------------------------------------------------
-        const i32 irow = m.arow_id[r];
-        const u64 base = a.c_ptr[r] + s_winbase;
-        for (;;) {
-            u32 i = 0;
-            if (lane == 0) i = atomicAdd(&s_grab, 1u);
-            i = __shfl_sync(SPB_FULL_MASK, i, 0);
+        const u64 base = s_segbase;
+        // sparse units (a couple of outputs per group): the groups are dealt to the warps in turn, no counter; dense ones
+        // (hub rows: groups of up to 1024 outputs next to groups of one) are grabbed one at a time
+        const bool dealt = total <= 4 * n_live;
+        for (u32 turn = warp;; turn += HS_WARPS) {
+            u32 i = turn;
+            if (!dealt) {
+                if (lane == 0) i = atomicAdd(&s_grab, 1u);
+                i = __shfl_sync(SPB_FULL_MASK, i, 0);
+            }
             if (i >= n_live) break;
             const u32 g = s_glist[i];
             const u32 w = g * 32 + lane;
@@ -599,12 +682,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             const u32 c = __popc(bits);
             const u32 incl = warp_incl_scan(c);
             u64 pos = base + s_gcnt[g] + incl - c;
-            for (; bits; bits &= bits - 1, ++pos) {
-                a.c_i[pos] = irow;
-                a.c_k[pos] = (i32)(col0 + w * 32 + __ffs(bits) - 1);
-            }
+            for (; bits; bits &= bits - 1, ++pos) a.tmp_k[pos] = (i32)(col0 + w * 32 + __ffs(bits) - 1);
         }
-        for (u32 p = tid; p < n_items; p += HS_THREADS) a.items[s_item0 + p] = ((u64)hrow << 32) | p;
     }
 }
 
@@ -642,7 +721,7 @@ __global__ void __launch_bounds__(256) k_hash_splits(MMOperands m, HashArgs a, u
         const u32 total = (u32)(a.c_ptr[r + 1] - base);
         const u32 n_items = (total + a.cap - 1) / a.cap;
         const u32 per = (total + n_items - 1) / n_items;
-        const i32 key = a.c_k[base + (u64)part * per];
+        const i32 key = hash_col(a, sr, part * per);
         u32 *dst = split + a.row_split[sr] + (u64)(part - 1) * len;
         for (u32 x = threadIdx.x; x < len; x += blockDim.x) {
             const i32 j = m.a_j[s + x];
@@ -712,7 +791,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_hash_numeric(MMOperands m, Ha
 #pragma unroll
         for (int u = 0; u < KPT; ++u) {
             const u32 t = tid + u * NT;
-            mykey[u] = t < n_out ? (u32)a.c_k[base + o_lo + t] : EMPTY;
+            mykey[u] = t < n_out ? (u32)hash_col(a, sr, o_lo + t) : EMPTY;
         }
         // windows of the B rows (k_hash_splits): where this item starts / the next one starts
         const u32 *split_lo = nullptr, *split_hi = nullptr;
@@ -839,15 +918,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_hash_numeric(MMOperands m, Ha
         const i32 irow = m.arow_id[r];
         double a_scale = 1.0;
         if (m.si) a_scale = m.si[irow];
-        for (u32 t = tid; t < n_out; t += NT) {
+#pragma unroll
+        for (int u = 0; u < KPT; ++u) {
+            const u32 t = tid + u * NT;
+            if (t >= n_out) break;
             const double sum = sm.acc[t];
             double b_scale = 1.0;
-            if (m.sk) b_scale = m.sk[a.c_k[base + o_lo + t]];
+            if (m.sk) b_scale = m.sk[mykey[u]];
             __stcs(a.c_v + base + o_lo + t, __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale));  // :242
-            if (!(sum != 0.0)) {  // :238 (NaN != 0 is kept).  Tombstone: the host closes the gaps afterwards
-                a.c_i[base + o_lo + t] = -1;
-                ++dropped;
-            }
+            __stcs(a.c_k + base + o_lo + t, (i32)mykey[u]);
+            const bool dead = !(sum != 0.0);  // :238 (NaN != 0 is kept).  Tombstone: the host closes the gaps afterwards
+            __stcs(a.c_i + base + o_lo + t, dead ? -1 : irow);
+            dropped += dead;
         }
         HN_TICK(c_out);
     }
