@@ -65,6 +65,68 @@ __global__ void __launch_bounds__(512) k_sort_hist9(SortInput in, int passes, in
     if (oob) counters[1] = 1;
 }
 
+// The same histogram with 128-bit loads: a thread takes FOUR CONSECUTIVE entries per trip -- one 16-byte load of row indices,
+// one of column indices, two of values -- and two trips' loads are in flight before the first counter is touched.  Needs
+// 16-byte aligned arrays (the host falls back to k_sort_hist / k_sort_hist9 otherwise); the last n % 4 entries are taken
+// one by one.  BITS = 8 or 9.
+template <int BITS>
+__global__ void __launch_bounds__(512) k_sort_hist_v4(SortInput in, int passes, int shift0, u32 *hist, u32 *counters) {
+    constexpr int RADIX = 1 << BITS;
+    constexpr int MAXP = BITS == 9 ? R9_MAX_PASSES : RS_MAX_PASSES;
+    __shared__ u32 s_h[MAXP * RADIX];
+    for (int t = threadIdx.x; t < passes * RADIX; t += blockDim.x) s_h[t] = 0;
+    __syncthreads();
+    u32 kept = 0, oob = 0;
+    auto count = [&](u64 i, i32 hi, i32 lo, double v) {
+        if ((u32)hi >= in.extent_hi || (u32)lo >= in.extent_lo) { oob = 1; return; }
+        if (!input_kept(in, (u32)i, v)) return;
+        ++kept;
+        u64 key = pack_key(hi, lo, in.bits_lo) >> shift0;
+        for (int p = 0; p < passes; ++p) {
+            atomicAdd(&s_h[p * RADIX + (u32)(key & (RADIX - 1))], 1u);
+            key >>= BITS;
+        }
+    };
+    const u64 quads = in.n / 4;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const int4 *hi4 = reinterpret_cast<const int4 *>(in.hi), *lo4 = reinterpret_cast<const int4 *>(in.lo);
+    const double2 *v2 = reinterpret_cast<const double2 *>(in.val);
+    constexpr int HU = 2;
+    for (u64 q0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; q0 < quads; q0 += HU * stride) {
+        int4 h[HU], l[HU];
+        double2 va[HU], vb[HU];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+            const u64 q = q0 + u * stride < quads ? q0 + u * stride : q0;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(h[u].x), "=r"(h[u].y), "=r"(h[u].z), "=r"(h[u].w) : "l"(hi4 + q));
+            if (in.lo) asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(l[u].x), "=r"(l[u].y), "=r"(l[u].z), "=r"(l[u].w) : "l"(lo4 + q));
+            else l[u] = make_int4(0, 0, 0, 0);
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(va[u].x), "=d"(va[u].y) : "l"(v2 + 2 * q));
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(vb[u].x), "=d"(vb[u].y) : "l"(v2 + 2 * q + 1));
+        }
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+            const u64 q = q0 + u * stride;
+            if (q >= quads) break;
+            count(4 * q, h[u].x, l[u].x, va[u].x);
+            count(4 * q + 1, h[u].y, l[u].y, va[u].y);
+            count(4 * q + 2, h[u].z, l[u].z, vb[u].x);
+            count(4 * q + 3, h[u].w, l[u].w, vb[u].y);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (in.n & 3)) {
+        const u64 i = quads * 4 + threadIdx.x;
+        count(i, in.hi[i], in.lo ? in.lo[i] : 0, in.val[i]);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < passes * RADIX; t += blockDim.x)
+        if (s_h[t]) atomicAdd(&hist[t], s_h[t]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(SPB_FULL_MASK, kept, o);
+    if (lane_id() == 0 && kept) atomicAdd(&counters[0], kept);
+    if (oob) counters[1] = 1;
+}
+
 // exclusive scan of each pass's 512 counts -> first output slot of each digit (in place); thread t: digits 2t, 2t+1
 __global__ void __launch_bounds__(R9_RADIX / 2) k_bucket_starts9(u32 *hist) {
     __shared__ u32 s_w[R9_RADIX / 64];

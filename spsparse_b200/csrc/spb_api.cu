@@ -69,7 +69,9 @@ struct DevPool {
         std::lock_guard<std::mutex> g(mu_);
         const size_t want = round_up(bytes);
         auto it = free_.lower_bound(want);
-        if (it != free_.end() && it->first <= want + want / 8) {  // at most 12.5% slack
+        // at most 12.5% slack -- 50% for blocks of 64 MB and more: the panels of a row-panel multiply ask for a different
+        // multi-GB size every time, and a cudaMalloc of that size stalls the stream for milliseconds
+        if (it != free_.end() && it->first <= want + (want >= (64u << 20) ? want / 2 : want / 8)) {
             *out = it->second;
             live_[*out] = it->first;
             cached_bytes -= it->first;
@@ -696,11 +698,18 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         ++ctx->launches, k_first_kept_key<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
         ++ctx->launches, k_first_kept_pos<<<grid_for(n, 256, sgrid * 2), 256, 0, ctx->stream>>>(in0, first_kept);
     }
+    // 128-bit loads when the caller's arrays allow them (SPB_VEC_LOAD=0: the scalar kernels)
+    const bool vec4 = ((((uintptr_t)in0.hi) | ((uintptr_t)in0.lo) | ((uintptr_t)in0.val)) & 15u) == 0 && n >= 4096 &&
+                      !(getenv("SPB_VEC_LOAD") && atoi(getenv("SPB_VEC_LOAD")) == 0);
     if (nine) {
-        ++ctx->launches, k_sort_hist9<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
+        ++ctx->launches;
+        if (vec4) k_sort_hist_v4<9><<<grid_for(n / 4, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
+        else k_sort_hist9<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
         ++ctx->launches, k_bucket_starts9<<<passes, R9_RADIX / 2, 0, ctx->stream>>>(hist);
     } else {
-        ++ctx->launches, k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
+        ++ctx->launches;
+        if (vec4) k_sort_hist_v4<8><<<grid_for(n / 4, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
+        else k_sort_hist<<<grid_for(n, 512, sgrid), 512, 0, ctx->stream>>>(in0, passes, shift0, hist, counters);
         ++ctx->launches, k_bucket_starts<<<passes, RS_RADIX, 0, ctx->stream>>>(hist);
     }
     CK(cudaGetLastError());
@@ -1383,6 +1392,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         u32 h_items = 0;
         const u64 max_items = h_stats[5] + nnz_c / hash_cap + 1;
         CKR(ws.get(&ha.items, max_items));
+        CKR(ws.get(&ha.item_key, max_items));
         ha.c_ptr = c_ptr; ha.c_i = out->idx[0]; ha.c_k = out->idx[1]; ha.c_v = out->val;
         ++ctx->launches, k_hash_items<<<grid_for((u64)ha.nrows * 32, 256, (u32)ctx->sm_count * 8), 256, 0, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());

@@ -211,7 +211,7 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
 template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 4 ? 8 : NLMAX <= 6 ? 6 : 5; };
 
 // stats: MC_STRIPES stripes of 8 counters, one cache line apart in pairs -- [0] F of merged rows, [1] rows merged, [2] rows
-// ESC, [6] longest row of op(A) (entries); a block adds its totals to stripe blockIdx % MC_STRIPES and the host sums the
+// ESC, [6] longest row of op(A) (entries); a warp adds its totals to one stripe (warps take the stripes in turn) and the host sums the
 // stripes.  (One set of counters for the whole grid, one atomic per warp, made this kernel wait for the L2 atomic unit of a
 // single address: 6 M atomics on one cache line in a 6.5 ms kernel.)
 constexpr int MC_STRIPES = 64;
@@ -245,17 +245,13 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
         n_merge += __shfl_xor_sync(SPB_FULL_MASK, n_merge, o);
         n_esc += __shfl_xor_sync(SPB_FULL_MASK, n_esc, o);
     }
-    __shared__ ull s_tot[4][4];   // [warp][F, rows merged, rows ESC, longest row]
-    const u32 warp = threadIdx.x >> 5;
-    if (lane_id() == 0) { s_tot[warp][0] = f_merge; s_tot[warp][1] = n_merge; s_tot[warp][2] = n_esc; s_tot[warp][3] = maxlen; }
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        const u32 q = threadIdx.x;
-        ull t = s_tot[0][q];
-        for (u32 w = 1; w < (blockDim.x >> 5); ++w) t = q == 3 ? max(t, s_tot[w][q]) : t + s_tot[w][q];
-        ull *mine = stats + (size_t)(blockIdx.x % MC_STRIPES) * 8;
-        if (q == 3) { if (t) atomicMax(&mine[6], t); }
-        else if (t) atomicAdd(&mine[q], t);
+    if (lane_id() == 0) {
+        // one stripe per warp in turn: 64 addresses share what a single one had to take
+        ull *mine = stats + (size_t)((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) % MC_STRIPES) * 8;
+        if (f_merge) atomicAdd(&mine[0], (ull)f_merge);
+        if (n_merge) atomicAdd(&mine[1], (ull)n_merge);
+        if (n_esc) atomicAdd(&mine[2], (ull)n_esc);
+        if (maxlen > (u32)mine[6]) atomicMax(&mine[6], (ull)maxlen);
     }
 }
 
@@ -385,6 +381,7 @@ struct HashArgs {
     const u64 *c_ptr;    // emit + numeric
     i32 *c_i, *c_k;
     double *c_v;
+    i32 *item_key;       // k_hash_items: first output column of every work item (the lower bound of its column window)
     u64 *items;          // emit: (index into rows[] << 32 | part), appended in any order
     u32 *n_items;
     u64 *row_split;      // emit: per ROW_HASH row cut into W > 1 items, the offset of its (W-1) x (row entries) block in split[]
@@ -497,7 +494,12 @@ __global__ void __launch_bounds__(256) k_hash_items(MMOperands m, HashArgs a) {
             if (n_items > 1) a.row_split[hrow] = atomicAdd(a.split_total, (ull)(n_items - 1) * (m.arow_start[r + 1] - m.arow_start[r]));
         }
         item0 = __shfl_sync(SPB_FULL_MASK, item0, 0);
-        for (u32 p = lane; p < n_items; p += 32) a.items[item0 + p] = ((u64)hrow << 32) | p;
+        __syncwarp();   // win_pre of this row is complete (hash_col reads it)
+        const u32 per = n_items ? (total + n_items - 1) / n_items : 0;
+        for (u32 p = lane; p < n_items; p += 32) {
+            a.items[item0 + p] = ((u64)hrow << 32) | p;
+            a.item_key[item0 + p] = hash_col(a, hrow, p * per);   // looked up once here, not by every thread of k_hash_splits
+        }
     }
 }
 
@@ -721,7 +723,7 @@ __global__ void __launch_bounds__(256) k_hash_splits(MMOperands m, HashArgs a, u
         const u32 total = (u32)(a.c_ptr[r + 1] - base);
         const u32 n_items = (total + a.cap - 1) / a.cap;
         const u32 per = (total + n_items - 1) / n_items;
-        const i32 key = hash_col(a, sr, part * per);
+        const i32 key = a.item_key[item];
         u32 *dst = split + a.row_split[sr] + (u64)(part - 1) * len;
         for (u32 x = threadIdx.x; x < len; x += blockDim.x) {
             const i32 j = m.a_j[s + x];
