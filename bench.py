@@ -396,13 +396,14 @@ def run_ours(args):
         ms_prep = float(np.mean([s.ms_prepare for _, _, s in acc]))
         pass_bytes = 32.0 * sa.n_kept  # one radix pass: read 8B key + 8B value, write both
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
         if os.path.exists(tp):  # dram__bytes_read+write of this kernel from an `ncu --set full` capture of this command
             tj = json.load(open(tp))
-            traffic = tj["dram_bytes_per_entry"] * sa.n_kept
-            traffic_src = f"{tj['dram_bytes_per_entry']:.2f} B/entry measured by ncu at {tj['entries_per_launch']} entries/launch ({tj['report']})"
-            if sa.digit_bits == 9:  # the capture is of the 8-bit pass kernel; the 9-bit one has not been under ncu yet
-                traffic, traffic_src = None, "no ncu capture of k_radix_pass9 yet; the 8-bit pass kernel, same reads and writes per entry: " + traffic_src
+            tj = tj.get("k_radix_pass9" if sa.digit_bits == 9 else "k_radix_pass", tj if "dram_bytes_per_entry" in tj else None)
+            if tj:
+                traffic = tj["dram_bytes_per_entry"] * sa.n_kept
+                traffic_src = (f"{tj['dram_bytes_per_entry']:.2f} B/entry measured by ncu ({tj['kernel']}, {tj['entries_per_launch']} entries/launch, "
+                               f"{tj['report']})")
         pass_gbs = pass_bytes / (ms_pass * 1e-3) / 1e9 if ms_pass > 0 else 0.0
         spgemm_bytes = 16.0 * st.products + 56.0 * st.nnz_a + 16.0 * st.nnz_c + 16.0 * st.rows_a
         # P = ceil(key bits / 8) passes of the MODEL, whatever the implementation runs
@@ -558,14 +559,14 @@ def run_ours(args):
                              "timeline_ms": dict(zip(["consolidate_b", "publish_and_gaps" if rowpart[0] is not None else "replicate_b_launch", "consolidate_a", "replicate_b_wait",
                                                       "spgemm_incl_prepare"],
                                                      [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)]))},
-            "roofline": {"bound": "hbm", "kernel": ("k_radix_pass9<false> (one 9-bit LSD scatter pass, key+value)" if sa.digit_bits == 9 else
-                                                    "k_radix_pass<false> (one 8-bit LSD scatter pass, key+value)"),
+            "roofline": {"bound": "hbm", "kernel": ("k_radix_pass9<false, BULK> (one 9-bit LSD scatter pass, key+value)" if sa.digit_bits == 9 else
+                                                    "k_radix_pass<false, BULK> (one 8-bit LSD scatter pass, key+value)"),
                          "achieved": pass_gbs, "peak": hbm, "unit": "GB/s", "frac": pass_gbs / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "bytes_per_launch": pass_bytes, "ms_per_launch": ms_pass,
                          "peak_source": peak_src,
-                         "note": ("9-bit digits: three passes over the 27-bit row part instead of four 8-bit ones; one 9-bit pass was "
-                                  "measured 17 % slower than an 8-bit one (which ran at 0.61 of the peak), the consolidate 8 % faster "
-                                  "(profiles/r01_radix9_ab.txt)") if sa.digit_bits == 9 else None},
+                         "note": ("9-bit digits: three passes over the 27-bit row part instead of four 8-bit ones (a 9-bit pass costs 10 % more "
+                                  "than an 8-bit one, three of them less than four); tiles loaded by cp.async.bulk + mbarrier "
+                                  "(profiles/r02_notes.md)") if sa.digit_bits == 9 else None},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(l1 - l0),
@@ -643,8 +644,24 @@ def e2e_cpp_api(ctx, torch, args, m, fingerprint):
     return out.get("cpp_api")
 
 
+def kernel_roofline(kernel, key, algo_bytes, ms, hbm, units=None, unit_name=None):
+    """Roofline sub-block of one config's dominant kernel: algorithmic bytes of a launch / its duration (CUDA events inside the
+    library) against the measured copy peak, and -- when profiles/r02_ncu_traffic.json has a capture of that kernel -- the DRAM
+    bytes ncu measured, scaled to this launch by the capture's bytes per unit."""
+    blk = {"kernel": kernel, "bound": "hbm", "bytes_per_launch": float(algo_bytes), "ms_per_launch": float(ms),
+           "achieved": float(algo_bytes) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "peak": hbm, "unit": "GB/s", "traffic": None}
+    blk["frac"] = blk["achieved"] / hbm
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get(key)
+        if tj and units is not None and "dram_bytes_per_" + (unit_name or "entry") in tj:
+            blk["traffic"] = tj["dram_bytes_per_" + (unit_name or "entry")] * units
+            blk["traffic_source"] = f"{tj['dram_bytes_per_' + (unit_name or 'entry')]:.2f} B per {unit_name or 'entry'} measured by ncu ({tj.get('report')})"
+    return blk
+
+
 def also_configs(ctx, sp, torch, stream, args, hbm):
-    """BASELINE configs 2 and 3 on one GPU (device-resident inputs, CUDA events on the library stream)."""
+    """BASELINE configs 2, 3 and 4 on one GPU (device-resident inputs, CUDA events on the library stream)."""
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # ---- config 2: consolidate 200M entries, ~30% duplicates, 2^24 x 2^24 ----------------------------
@@ -679,6 +696,9 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
         "pass_gbs": 32.0 * st.n_kept / (float(np.mean([s.ms_pass for s in sts])) * 1e-3) / 1e9,
         "first_entry": [int(idx[0][0]), int(idx[1][0])] if idx is not None else None,
         "sum_values": float(val.sum()) if val is not None else None,
+        "roofline": kernel_roofline(f"k_radix_pass{'9' if st.digit_bits == 9 else ''}<false, BULK> ({st.passes - 1} of its {st.passes} scatter passes; pass 0 reads the caller's arrays)",
+                                    "k_radix_pass9" if st.digit_bits == 9 else "k_radix_pass", 32.0 * st.n_kept,
+                                    float(np.mean([s.ms_pass for s in sts])), hbm, st.n_kept),
     }
     A.free()
     # ---- config 3: regridding SpGEMM  C = A diag(s) A^T, A = 1e7 x 1e6 ---------------------------------
@@ -703,6 +723,9 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
         "products_per_sec": st.products / (ms_k * 1e-3), "nnz_c_per_sec": st.nnz_c / (ms_k * 1e-3),
         "model_bytes": model, "model_frac": model / (ms_k * 1e-3) / 1e9 / hbm,
         "compulsory_frac": (12.0 * st.nnz_a + 12.0 * st.nnz_b + 8.0 * gy * gx + 16.0 * st.nnz_c) / (ms_k * 1e-3) / 1e9 / hbm,
+        "roofline": kernel_roofline("k_merge_numeric<4, 16> (register k-way merge, numeric pass: 12 B per product read, 16 B per output written)",
+                                    "k_merge_numeric", 12.0 * st.products + 16.0 * st.nnz_c,
+                                    float(np.mean([x.ms_merge_numeric for x in sts])), hbm, st.nnz_c, "output"),
     }
     for x in (A, s, Ar, Bt):
         x.free()
@@ -733,6 +756,12 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
         "ms_numeric": float(np.mean([x.ms_numeric for x in sts])), "ms_prepare_incl_consolidate": float(np.mean([x.ms_prepare for x in sts])),
         "ms_kernels": kernel_ms(sts),
         "products_per_sec": st.products / (ms_k * 1e-3), "model_bytes": model, "model_frac": model / (ms_k * 1e-3) / 1e9 / hbm,
+        "roofline": kernel_roofline("k_hash_numeric<256, 2560, 4096> (shared-memory hash accumulators: 12 B per product read, 20 B per output written)",
+                                    "k_hash_numeric", 12.0 * st.products_hash + 20.0 * st.nnz_c,
+                                    float(np.mean([x.ms_hash_numeric for x in sts])), hbm, st.products_hash, "product"),
+        "roofline_symbolic": kernel_roofline("k_hash_symbolic (one bitmap pass: 4 B per product read, 4 B per output written)",
+                                             "k_hash_symbolic", 4.0 * st.products_hash + 4.0 * st.nnz_c,
+                                             float(np.mean([x.ms_hash_count for x in sts])), hbm, st.products_hash, "product"),
     }
     A.free()
     # (b) config 4 AS NAMED: 2^24 rows.  Its product (5.6e10 outputs) fits no single array -- VectorCooArray offsets are int
