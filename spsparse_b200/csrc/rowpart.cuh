@@ -59,11 +59,13 @@ __device__ __forceinline__ bool rp_wait_ge(const u64 *p, u64 want, u32 *error) {
     return true;
 }
 
-// ---- publish: wait until every peer has finished reading the previous publication, copy, raise the ready counters --------
+// ---- publish: wait until every peer has finished reading this buffer's previous publication (two steps ago), copy, raise the
+//      ready counters ------------------------------------------------------------------------------------------------------------
 __global__ void k_rp_wait_done(RpArgs a) {
     const int q = threadIdx.x;
-    if (q < a.n_ranks && q != a.rank && a.step > 1)
-        rp_wait_ge(a.reg[a.rank].flags + RP_MAX_RANKS + q, a.step - 1, a.error);
+    // (two shard buffers alternate: this step's buffer was last read in step - 2)
+    if (q < a.n_ranks && q != a.rank && a.step > 2)
+        rp_wait_ge(a.reg[a.rank].flags + RP_MAX_RANKS + q, a.step - 2, a.error);
 }
 
 // local_ptr: rows_local + 1 offsets into (cols, vals) of the consolidated shard (spb_coo_dense_ptr_range); published re-based to 0

@@ -2155,7 +2155,7 @@ struct spb_rowpart {
     u64 cap_entries, cap_rows;   // per-rank capacity of the published shard (the same on every rank)
     u64 slack;                   // entries of room before and after the shard (halo rows of the neighbours)
     int mode;                    // 0: halos fetched in place around the own shard; 1: everything copied (sticky once needed)
-    size_t off_ptr, off_cols, off_vals, region_bytes;
+    size_t off_ptr, off_cols, off_vals, buf_bytes, region_bytes;   // two buffers (ptr, cols, vals) behind the flags: steps alternate
     void *region;                // this rank's exported allocation
     void *peer_base[RP_MAX_RANKS];
     bool attached;
@@ -2178,19 +2178,23 @@ static void rp_layout(spb_rowpart *rp) {
     rp->off_ptr = rp_align(RP_FLAG_WORDS * sizeof(u64));
     rp->off_cols = rp->off_ptr + rp_align((rp->cap_rows + 2) * sizeof(u32));
     rp->off_vals = rp->off_cols + rp_align((rp->cap_entries + 2 * rp->slack) * sizeof(i32));
-    rp->region_bytes = rp->off_vals + rp_align((rp->cap_entries + 2 * rp->slack) * sizeof(double));
+    rp->buf_bytes = rp->off_vals + rp_align((rp->cap_entries + 2 * rp->slack) * sizeof(double)) - rp->off_ptr;
+    rp->region_bytes = rp->off_ptr + 2 * rp->buf_bytes;
 }
 
 static void rp_args(const spb_rowpart *rp, RpArgs *a) {
     memset(a, 0, sizeof *a);
     a->rank = rp->rank; a->n_ranks = rp->n_ranks; a->step = rp->step; a->error = rp->error;
     for (int g = 0; g <= rp->n_ranks; ++g) a->row_lo[g] = rp->row_lo[g];
+    // Two shard buffers, used by alternate steps: step s is written while the peers may still be reading step s - 1, so a
+    // rank only ever waits for the readers of step s - 2 (in practice never) before it consolidates its next shard.
+    const size_t par = (size_t)(rp->step & 1) * rp->buf_bytes;
     for (int g = 0; g < rp->n_ranks; ++g) {
         char *b = (char *)rp->peer_base[g];
         a->reg[g].flags = (u64 *)b;
-        a->reg[g].ptr = (u32 *)(b + rp->off_ptr);
-        a->reg[g].cols = (i32 *)(b + rp->off_cols) + rp->slack;     // the shard itself; the slack lies on either side
-        a->reg[g].vals = (double *)(b + rp->off_vals) + rp->slack;
+        a->reg[g].ptr = (u32 *)(b + par + rp->off_ptr);
+        a->reg[g].cols = (i32 *)(b + par + rp->off_cols) + rp->slack;     // the shard itself; the slack lies on either side
+        a->reg[g].vals = (double *)(b + par + rp->off_vals) + rp->slack;
     }
     a->slack = (u32)rp->slack;
 }
@@ -2240,7 +2244,7 @@ int spb_rowpart_create(spb_ctx *ctx, int rank, int n_ranks, const uint64_t *row_
     auto body = [&]() -> int {
         if (n_ranks > 1) {
             CK(cudaMalloc(&rp->region, rp->region_bytes));
-            CK(cudaMemset(rp->region, 0, rp->off_cols));   // step counters and pointers start at 0
+            CK(cudaMemset(rp->region, 0, rp->region_bytes));   // step counters and pointers start at 0
             rp->g_cap = rp->cap_entries * (u64)n_ranks;   // the copy buffers themselves are allocated when first needed
             CK(cudaMalloc((void **)&rp->g_ptr, (rp->m + 2) * sizeof(u32)));
             CK(cudaMalloc((void **)&rp->hull, 8 * sizeof(u64)));
