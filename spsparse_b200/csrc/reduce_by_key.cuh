@@ -13,7 +13,10 @@
 #pragma once
 #include "scan.cuh"
 
-constexpr int RK_THREADS = 256;
+#ifndef RK_THREADS_N
+#define RK_THREADS_N 256   // threads per block of the reduce pass (same-box A/B builds: -DRK_THREADS_N=128 -DRK_MIN_BLOCKS=10)
+#endif
+constexpr int RK_THREADS = RK_THREADS_N;
 constexpr int RK_IPT = 8;
 constexpr int RK_TILE = RK_THREADS * RK_IPT;
 constexpr int RK_WARPS = RK_THREADS / 32;

@@ -1142,6 +1142,11 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     // 6-list one at a third more warps), while the numeric kernel still prefers the lean one (10.9 -> 8.8 ms).
     const int nl_count = getenv("SPB_MERGE_NL_COUNT") ? atoi(getenv("SPB_MERGE_NL_COUNT")) : (avg_b_len > 16.0 ? nl_fit : 8);
     int nl_num = getenv("SPB_MERGE_NL_NUMERIC") ? atoi(getenv("SPB_MERGE_NL_NUMERIC")) : nl_fit;
+    // (measured slower than the global merge on the banded config -- count 7.3 -> 11.0 ms, numeric 8.9 -> 16.3 ms: the staging
+    // puts three barriers and four serialised round trips in front of every block -- so off unless SPB_MERGE_LOCAL=1;
+    // profiles/r02_notes.md)
+    const bool local_count = avg_b_len <= 16.0 && getenv("SPB_MERGE_LOCAL") && atoi(getenv("SPB_MERGE_LOCAL")) != 0;
+    const int local_carve = getenv("SPB_MERGE_LOCAL_CARVE") ? atoi(getenv("SPB_MERGE_LOCAL_CARVE")) : -1;
     const int blk_count = getenv("SPB_MERGE_BLOCKS_COUNT") ? atoi(getenv("SPB_MERGE_BLOCKS_COUNT")) : 0;
     const int blk_num = getenv("SPB_MERGE_BLOCKS_NUMERIC") ? atoi(getenv("SPB_MERGE_BLOCKS_NUMERIC")) : 0;
     {
@@ -1152,7 +1157,12 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         // thread and want the larger L1; short ones keep the driver's default
         const double avg_b_row = n_inner ? (double)B->n / (double)n_inner : 0.0;
         const int carve_c = getenv("SPB_MERGE_CARVEOUT_COUNT") ? atoi(getenv("SPB_MERGE_CARVEOUT_COUNT")) : (avg_b_row > 16.0 ? 25 : -1);
-#define SPB_LAUNCH_COUNT(NL) do { if (bal) CKR(allow_ballast(k_merge_count<NL>)); \
+        // SPB_MERGE_LOCAL=1, short B rows: the LOCAL kernels (a block stages the stretch of B its rows reference in shared
+        // memory; blocks whose rows reach too far fall back to the global merge by themselves)
+#define SPB_LAUNCH_COUNT(NL) do { if (local_count) { \
+            if (local_carve >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, local_carve)); \
+            k_merge_count<NL, true><<<g, 128, 0, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); break; } \
+        if (bal) CKR(allow_ballast(k_merge_count<NL>)); \
         if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
         k_merge_count<NL><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); } while (0)
         if (nl_count <= 2 && nl_fit <= 2) SPB_LAUNCH_COUNT(2);
@@ -1177,7 +1187,9 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(cudaMemcpyAsync(&nnz_c_spec, c_ptr + nrows, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     memset(h_stats, 0, sizeof h_stats);
+    ull staged_blocks = 0;   // LOCAL count kernel: blocks that ran from shared memory
     for (int sx = 0; sx < MC_STRIPES; ++sx) {
+        staged_blocks += h_mstats[sx * 8 + 3];
         for (int q = 0; q < 3; ++q) h_stats[q] += h_mstats[sx * 8 + q];
         if (h_mstats[sx * 8 + 6] > h_stats[6]) h_stats[6] = h_mstats[sx * 8 + 6];
     }
@@ -1371,7 +1383,12 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         // walks through B) ran best with 4 blocks and half of the array as L1, short rows with 7 blocks.
         const double avg_row_products = h_stats[1] ? (double)h_stats[0] / (double)h_stats[1] : 0.0;
         const int carve_n = getenv("SPB_MERGE_CARVEOUT_NUMERIC") ? atoi(getenv("SPB_MERGE_CARVEOUT_NUMERIC")) : (avg_row_products > 64.0 ? 50 : 75);
-#define SPB_LAUNCH_NUM(NL, ST) do { if (bal) CKR(allow_ballast(k_merge_numeric<NL, ST>)); \
+        // most blocks of the count kernel found their stretch of B small enough to stage: the numeric kernel stages too
+        const bool local_num = local_count && stage == 16 && staged_blocks * 2 >= (ull)div_up(nrows, 128);
+#define SPB_LAUNCH_NUM(NL, ST) do { if (local_num && ST == 16) { \
+            if (local_carve >= 0) CK(cudaFuncSetAttribute(k_merge_numeric<NL, 16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, local_carve)); \
+            k_merge_numeric<NL, 16, true><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val); break; } \
+        if (bal) CKR(allow_ballast(k_merge_numeric<NL, ST>)); \
         if (carve_n >= 0) CK(cudaFuncSetAttribute(k_merge_numeric<NL, ST>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_n)); \
         k_merge_numeric<NL, ST><<<g, MR_THREADS, bal, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val); } while (0)
         if (stage == 4) SPB_LAUNCH_NUM(8, 4);

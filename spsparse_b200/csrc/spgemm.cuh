@@ -105,13 +105,28 @@ __global__ void k_esc_row_products(MMOperands m, const u64 *__restrict__ ent_off
 // ---- short rows: k-way merge in registers, one thread per row -----------------------------------
 // The heads of up to NL column-sorted B rows live in registers; each step takes the smallest head
 // column, sums every list that holds it in list (= ascending j) order and advances those lists.
-template <int NL>
+// Where a merge reads B from: the global arrays (k0 = j0 = 0, read-only cache loads), or -- LOCAL -- the copies a block made in
+// shared memory of the stretch of B its rows reference (k0 / j0 = first entry / first row of that stretch).
+struct BView {
+    const i32 *k;
+    const double *v;
+    const u32 *p;
+    u32 k0, j0;
+};
+template <bool LOCAL> __device__ __forceinline__ i32 bv_k(const BView &b, u32 e) { return LOCAL ? b.k[e - b.k0] : __ldg(b.k + e); }
+template <bool LOCAL> __device__ __forceinline__ double bv_v(const BView &b, u32 e) { return LOCAL ? b.v[e - b.k0] : __ldg(b.v + e); }
+template <bool LOCAL> __device__ __forceinline__ u32 bv_p(const BView &b, u32 j) { return LOCAL ? b.p[j - b.j0] : __ldg(b.p + j); }
+
+template <int NL, bool LOCAL = false>
 struct RowMerge {
     u32 cur[NL], end[NL];
     i32 hk[NL];
     double hv[NL], as[NL];
+    BView b;
 
-    __device__ __forceinline__ void init(const MMOperands &m, u32 s, u32 len) {
+    __device__ __forceinline__ void init(const MMOperands &m, u32 s, u32 len, const BView *view = nullptr) {
+        if (view) b = *view;
+        else { b.k = m.b_k; b.v = m.b_val; b.p = m.bptr; b.k0 = 0; b.j0 = 0; }
 #pragma unroll
         for (int l = 0; l < NL; ++l) {
             cur[l] = end[l] = 0;
@@ -123,12 +138,12 @@ struct RowMerge {
                 double a = __ldg(m.a_val + s + l);
                 bool ok = !m.sj_mask || m.sj_mask[j];
                 if (ok) {
-                    cur[l] = __ldg(m.bptr + j);
-                    end[l] = __ldg(m.bptr + j + 1);
+                    cur[l] = bv_p<LOCAL>(b, (u32)j);
+                    end[l] = bv_p<LOCAL>(b, (u32)j + 1);
                     as[l] = m.sj ? __dmul_rn(a, __ldg(m.sj + j)) : a;  // (a*s) first, multiply_sparse.hpp:228
                     if (cur[l] < end[l]) {
-                        hk[l] = __ldg(m.b_k + cur[l]);
-                        hv[l] = __ldg(m.b_val + cur[l]);
+                        hk[l] = bv_k<LOCAL>(b, cur[l]);
+                        hv[l] = bv_v<LOCAL>(b, cur[l]);
                     }
                 }
             }
@@ -160,8 +175,8 @@ struct RowMerge {
                 acc = __dadd_rn(acc, __dmul_rn(as[l], hv[l]));
                 ++cur[l];
                 if (cur[l] < end[l]) {
-                    hk[l] = __ldg(m.b_k + cur[l]);
-                    hv[l] = __ldg(m.b_val + cur[l]);
+                    hk[l] = bv_k<LOCAL>(b, cur[l]);
+                    hv[l] = bv_v<LOCAL>(b, cur[l]);
                 } else {
                     hk[l] = INT32_MAX;
                 }
@@ -184,11 +199,57 @@ __device__ __forceinline__ bool keep_output(const MMOperands &m, i32 k, double s
     return keep;
 }
 
+// ---- LOCAL variants of the merge kernels: the block's stretch of B in shared memory ---------------------------------------
+// Matrices with row locality (banded, stencil-like: consecutive rows of A reference neighbouring rows of B) make a block's
+// 128 rows read one short CONTIGUOUS stretch of B -- rows jlo..jhi of a row-sorted B are adjacent in memory.  The block copies
+// that stretch (row pointers, columns, values) into shared memory once, with coalesced loads, and its merges then chase their
+// list heads at shared-memory latency instead of one L2 round trip per step.  Blocks whose rows reach too far (the stretch
+// does not fit) run the ordinary global-memory merge: nothing is assumed about the matrix.
+constexpr int ML_JCAP = 1024;      // rows of B a block may stage
+constexpr int ML_CAP_COUNT = 1536; // entries of B, count kernel (22 KB per block)
+constexpr int ML_CAP_NUM = 1024;   // entries of B, numeric kernel (next to its 26 KB of output staging)
+template <int CAP, int JCAP = ML_JCAP>
+struct BStage {
+    i32 k[CAP];
+    double v[CAP];
+    u32 p[JCAP + 2];
+    u32 red[2][4];
+};
+// jlo..jhi: the inner indices of this thread's row (jlo > jhi: none).  Block-uniform result; three barriers.
+template <int CAP, int JCAP>
+__device__ __forceinline__ bool stage_b(const MMOperands &m, BStage<CAP, JCAP> &sm, u32 jlo, u32 jhi, BView &view) {
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    jlo = __reduce_min_sync(SPB_FULL_MASK, jlo);
+    jhi = __reduce_max_sync(SPB_FULL_MASK, jhi);
+    if (lane == 0) { sm.red[0][warp] = jlo; sm.red[1][warp] = jhi; }
+    __syncthreads();
+    u32 JLO = sm.red[0][0], JHI = sm.red[1][0];
+    for (u32 w = 1; w < (blockDim.x >> 5); ++w) { JLO = min(JLO, sm.red[0][w]); JHI = max(JHI, sm.red[1][w]); }
+    bool ok = JLO <= JHI && JHI - JLO < (u32)JCAP;
+    if (ok)
+        for (u32 t = tid; t < JHI - JLO + 2; t += blockDim.x) sm.p[t] = __ldg(m.bptr + JLO + t);
+    __syncthreads();
+    u32 seg0 = 0, seg1 = 0;
+    if (ok) {
+        seg0 = sm.p[0];
+        seg1 = sm.p[JHI - JLO + 1];
+        ok = seg1 - seg0 <= (u32)CAP;
+    }
+    if (ok)
+        for (u32 t = tid; t < seg1 - seg0; t += blockDim.x) {
+            sm.k[t] = ld_stream_i32(m.b_k + seg0 + t);
+            sm.v[t] = ld_stream_f64(m.b_val + seg0 + t);
+        }
+    __syncthreads();
+    view.k = sm.k; view.v = sm.v; view.p = sm.p; view.k0 = seg0; view.j0 = JLO;
+    return ok;
+}
+
 // symbolic: bin the row and, for a short row, count its outputs exactly
-template <int NL>
-__device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u32 max_products, u32 &count, u64 &f) {
-    RowMerge<NL> st;
-    st.init(m, s, len);
+template <int NL, bool LOCAL = false>
+__device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u32 max_products, u32 &count, u64 &f, const BView *view = nullptr) {
+    RowMerge<NL, LOCAL> st;
+    st.init(m, s, len, view);
     f = 0;
 #pragma unroll
     for (int l = 0; l < NL; ++l) f += st.end[l] - st.cur[l];
@@ -215,18 +276,43 @@ template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 
 // stripes.  (One set of counters for the whole grid, one atomic per warp, made this kernel wait for the L2 atomic unit of a
 // single address: 6 M atomics on one cache line in a 6.5 ms kernel.)
 constexpr int MC_STRIPES = 64;
-template <int NLMAX>
+template <int NLMAX, bool LOCAL = false>
 __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
+    __shared__ BStage<LOCAL ? ML_CAP_COUNT : 1, LOCAL ? ML_JCAP : 1> s_b;
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     int cls = ROW_SKIP;
     u32 c = 0;
     u64 f = 0;
+    u32 s = 0, len = 0;
+    bool on = false;
     if (r < m.nrows) {
-        const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
-        const bool on = !m.si || m.si[m.arow_id[r]] != 0.0;  // row excluded by scalei (multiply_sparse.hpp:195)
+        s = m.arow_start[r];
+        len = m.arow_start[r + 1] - s;
+        on = !m.si || m.si[m.arow_id[r]] != 0.0;  // row excluded by scalei (multiply_sparse.hpp:195)
+    }
+    BView view;
+    bool staged = false;
+    if (LOCAL) {
+        u32 jlo = 0xffffffffu, jhi = 0;
+        if (on && len <= (u32)MERGE_MAX_LISTS)
+            for (u32 l = 0; l < len; ++l) {
+                const u32 j = (u32)__ldg(m.a_j + s + l);
+                jlo = min(jlo, j);
+                jhi = max(jhi, j);
+            }
+        staged = stage_b(m, s_b, jlo, jhi, view);
+        if (staged && threadIdx.x == 0) atomicAdd(&stats[(size_t)(blockIdx.x % MC_STRIPES) * 8 + 3], 1ull);   // blocks that ran from shared memory
+    }
+    if (r < m.nrows) {
         if (on) {
             if (len > (u32)MERGE_MAX_LISTS) cls = ROW_ESC;   // products counted later, from the per-entry prefix sums
+            else if (LOCAL && staged) {
+                if (len <= 2) cls = count_row<2, true>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), true>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), true>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), true>(m, s, len, max_products, c, f, &view);
+            }
             else if (len <= 2) cls = count_row<2>(m, s, len, max_products, c, f);
             else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2)>(m, s, len, max_products, c, f);
             else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2)>(m, s, len, max_products, c, f);
@@ -260,14 +346,14 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
 // sectors instead of one 4/8-byte store per thread per step.
 constexpr int MR_THREADS = 128;
 
-template <int NL, int STAGE>
+template <int NL, int STAGE, bool LOCAL = false>
 __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, u32 s, u32 len, i32 irow,
-                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v) {
+                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v, const BView *view = nullptr) {
     constexpr int PITCH = STAGE + 1;
     constexpr int RUNS = 32 / STAGE;  // lanes' runs written per flush iteration
     const u32 lane = lane_id();
-    RowMerge<NL> st;
-    st.init(m, s, mine ? len : 0);
+    RowMerge<NL, LOCAL> st;
+    st.init(m, s, mine ? len : 0, view);
     double a_scale = 1.0;
     if (mine && m.si) a_scale = m.si[irow];
     u32 cnt = 0;
@@ -314,12 +400,13 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
     }
 }
 
-template <int NLMAX, int STAGE>
-__global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? MergeBlocks<NLMAX>::value : 1)) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
+template <int NLMAX, int STAGE, bool LOCAL = false>
+__global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBlocks<NLMAX>::value > 5 ? 5 : MergeBlocks<NLMAX>::value) : 1)) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
                                                               const u64 *__restrict__ c_ptr, i32 *c_i, i32 *c_k,
                                                               double *c_v) {
     __shared__ i32 s_k[MR_THREADS * (STAGE + 1)];
     __shared__ double s_v[MR_THREADS * (STAGE + 1)];
+    __shared__ BStage<LOCAL ? ML_CAP_NUM : 1, LOCAL ? ML_JCAP : 1> s_b;
     const u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 warp = threadIdx.x >> 5;
     const bool mine = (r < m.nrows) && (row_cls[r] == ROW_MERGE);
@@ -332,10 +419,28 @@ __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? MergeBlocks<NLMAX>:
         irow = m.arow_id[r];
         dst = c_ptr[r];
     }
+    BView view;
+    bool staged = false;
+    if (LOCAL) {   // before any warp leaves: the staging has barriers
+        u32 jlo = 0xffffffffu, jhi = 0;
+        for (u32 l = 0; l < len; ++l) {
+            const u32 j = (u32)__ldg(m.a_j + s + l);
+            jlo = min(jlo, j);
+            jhi = max(jhi, j);
+        }
+        staged = stage_b(m, s_b, jlo, jhi, view);
+    }
     const u32 maxlen = __reduce_max_sync(SPB_FULL_MASK, len);
     i32 *sk = s_k + warp * 32 * (STAGE + 1);
     double *sv = s_v + warp * 32 * (STAGE + 1);
     if (maxlen == 0) return;
+    if (LOCAL && staged) {
+        if (maxlen <= 2) merge_rows_warp<2, STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
+        else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
+        else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
+        else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
+        return;
+    }
     if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
     else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
     else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);

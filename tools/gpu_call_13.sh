@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, call 13 (1 GPU): LOCAL merge kernels (block stages its stretch of B in shared memory) -- parity, same-process A/B
+set -u
+out=gpurun_out/r02_c13
+mkdir -p "$out"
+run() { local name=$1 t=$2; shift 2
+    ( timeout "$t" "$@" > "$out/$name.out" 2> "$out/$name.err"; echo "rc=$?" >> "$out/$name.err" )
+    tail -n 2 "$out/$name.err" | tr '\n' ' '; echo "<- $name"; }
+run t_mult 600 python -m pytest tests/test_gpu_multiply.py tests/test_gpu_dropin.py -x -q -p no:cacheprovider
+run t_full5 600 python -m pytest tests/test_gpu_full_size.py -x -q -p no:cacheprovider -k "config5 or config3"
+run local_banded 200 python tools/profile_target.py banded 1 4
+SPB_MERGE_LOCAL=0 run global_banded 200 python tools/profile_target.py banded 1 4
+run local_regrid 200 python tools/profile_target.py regrid 1 4
+run rmat20 200 python tools/profile_target.py rmat 20 3
+run bench 600 python bench.py --no-e2e --no-cpu --no-also --steps 5 --warmup 3
