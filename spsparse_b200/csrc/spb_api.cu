@@ -1121,6 +1121,80 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CKR(ws.zeroed(&stats, 8));
     CKR(ws.zeroed(&mstats, (u64)MC_STRIPES * 8));
     const u32 cap = (u32)ctx->sm_count * 32;
+    // ---- one pass for matrices of short rows (k_merge_onepass): no symbolic phase at all ------------------------------------------
+    // Tried when rows of A and of B are short on average (their product bounds the outputs per row) and the longest row of A,
+    // if known, is a merge row; C is allocated for 16 outputs per row.  Anything the kernel cannot take makes it fail fast and
+    // the two-pass path below runs as if nothing had happened.  Measured on the banded config: 17.8 ms against 7.3 + 8.8 ms for
+    // count + numeric -- with ~3000 warps in flight a finishing warp walks ~90 look-back rounds back to the nearest inclusive
+    // prefix, longer than its merges took -- so OFF unless SPB_MERGE_ONEPASS=1 (profiles/r02_notes.md).
+    {
+        const double avg_a_len = nrows ? (double)m.nnz_a / (double)nrows : 0.0;
+        const double avg_b = n_inner ? (double)B->n / (double)n_inner : 0.0;
+        const u64 cap_out = (u64)nrows * 16;
+        const bool want = !symbolic_only && nrows && avg_a_len * avg_b <= 40.0 && (A->max_row_len == 0 || A->max_row_len <= (u32)MERGE_MAX_LISTS) &&
+                          cap_out < (1ull << 31) && cap_out * 16 <= (48ull << 30) &&
+                          getenv("SPB_MERGE_ONEPASS") && atoi(getenv("SPB_MERGE_ONEPASS")) != 0;
+        if (want) {
+            spb_coo *Am1 = const_cast<spb_coo *>(A);
+            if (!Am1->max_row_len) {   // picks the kernel build (registers per thread follow the longest row)
+                u32 *mx;
+                CKR(ws.zeroed(&mx, 1));
+                ++ctx->launches, k_row_maxlen<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m.arow_start, nrows, mx);
+                CK(cudaMemcpyAsync(&Am1->max_row_len, mx, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            const u32 ml = A->max_row_len;
+            if (ml <= (u32)MERGE_MAX_LISTS) {
+                const u32 g = (u32)div_up(nrows, MR_THREADS);
+                u64 *state;
+                u32 *tk;
+                ull *o1;
+                i32 *ci = nullptr, *ck = nullptr;
+                double *cv = nullptr;
+                CKR(ws.zeroed(&state, (u64)g * (MR_THREADS / 32)));
+                CKR(ws.zeroed(&tk, 2));
+                CKR(ws.zeroed(&o1, 8 + (u64)MC_STRIPES * 8));
+                if (ctx->pool.alloc((void **)&ci, cap_out * sizeof(i32)) != cudaSuccess || ctx->pool.alloc((void **)&ck, cap_out * sizeof(i32)) != cudaSuccess ||
+                    ctx->pool.alloc((void **)&cv, cap_out * sizeof(double)) != cudaSuccess) {
+                    cudaGetLastError();
+                    ctx->pool.release(ci); ctx->pool.release(ck); ctx->pool.release(cv);
+                } else {
+                    ++ctx->launches;
+                    if (ml <= 2) k_merge_onepass<2><<<g, MR_THREADS, 0, ctx->stream>>>(m, ctx->merge_max_products, state, tk, tk + 1, o1, ci, ck, cv);
+                    else if (ml <= 4) k_merge_onepass<4><<<g, MR_THREADS, 0, ctx->stream>>>(m, ctx->merge_max_products, state, tk, tk + 1, o1, ci, ck, cv);
+                    else if (ml <= 6) k_merge_onepass<6><<<g, MR_THREADS, 0, ctx->stream>>>(m, ctx->merge_max_products, state, tk, tk + 1, o1, ci, ck, cv);
+                    else k_merge_onepass<8><<<g, MR_THREADS, 0, ctx->stream>>>(m, ctx->merge_max_products, state, tk, tk + 1, o1, ci, ck, cv);
+                    CK(cudaGetLastError());
+                    const int t_one = tm.mark();
+                    ull h_o[8 + MC_STRIPES * 8];
+                    u32 h_tk[2], h_badv = 0;
+                    CK(cudaMemcpyAsync(h_o, o1, sizeof h_o, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaMemcpyAsync(h_tk, tk, sizeof h_tk, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaMemcpyAsync(&h_badv, bad_vec, sizeof h_badv, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    if (h_badv) { ctx->pool.release(ci); ctx->pool.release(ck); ctx->pool.release(cv); return bad_scale_vector(); }
+                    if (!h_tk[1]) {   // it went through
+                        ull F1 = 0, rows1 = 0;
+                        for (int sx = 0; sx < MC_STRIPES; ++sx) { F1 += h_o[8 + sx * 8]; rows1 += h_o[8 + sx * 8 + 1]; }
+                        out->idx[0] = ci; out->idx[1] = ck; out->val = cv;
+                        out->owned = true;
+                        out->n = h_o[0];
+                        if (st) {
+                            st->products = F1; st->rows_merge = rows1; st->nnz_a = A->n; st->nnz_b = B->n; st->rows_a = nrows; st->nnz_c = h_o[0];
+                            st->ms_prepare = tm.ms(t_begin, t_prep);
+                            st->ms_symbolic = 0.f;
+                            st->ms_numeric = tm.ms(t_prep, t_one);
+                            st->ms_merge_numeric = st->ms_numeric;
+                            st->ms_total = tm.ms(t_begin, t_one);
+                        }
+                        return SPB_OK;
+                    }
+                    ctx->pool.release(ci); ctx->pool.release(ck); ctx->pool.release(cv);
+                }
+            }
+        }
+    }
+
     // longest row of op(A): picks the leanest register-merge kernels that still cover every mergeable row.  Only the count
     // kernel's choice for long B rows needs it up front; otherwise the count kernel itself reports it (stats[6]) and it is
     // read back with the other counters -- one host round trip less per multiply of a freshly consolidated A.

@@ -447,6 +447,128 @@ __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBloc
     else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
 }
 
+// ---- short rows, ONE pass: merge, then place ---------------------------------------------------------------------------------
+// When every row of op(A) is a register-merge row with at most STAGE outputs (banded / stencil matrices: 9 outputs per row), the
+// symbolic pass is pure overhead: it runs the same merges as the numeric pass only to learn where the rows go.  Here a warp
+// merges its 32 rows ONCE, keeping their outputs in its staging area, learns its place in C from a decoupled look-back over the
+// warps (in row order: tiles are handed out by a ticket, so every predecessor is running or done), and writes.  C is allocated
+// for STAGE outputs per row; the exact count comes back with the kernel.  A row this kernel cannot take (more than 8 inner
+// indices, more than max_products products, more than STAGE outputs) raises *fail: the remaining warps skip their merges (they
+// still publish, nobody may wait forever), the host throws the result away and runs the two-pass path.
+// out[0] = outputs, out[1] = products, out[2] = rows merged, out[3] = longest row
+template <int NL, int STAGE>
+__device__ __forceinline__ bool merge_rows_stage(const MMOperands &m, bool mine, u32 s, u32 len, i32 irow, u32 max_products,
+                                                 i32 *sk, double *sv, u32 &cnt, u64 &f) {
+    constexpr int PITCH = STAGE + 1;
+    const u32 lane = lane_id();
+    RowMerge<NL> st;
+    st.init(m, s, mine ? len : 0);
+    f = 0;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) f += st.end[l] - st.cur[l];
+    double a_scale = 1.0;
+    if (mine && m.si) a_scale = m.si[irow];
+    cnt = 0;
+    bool ok = f <= (u64)max_products;
+    bool active = mine && ok && f != 0;
+    if (st.touch() + a_scale == -1.2345678e300) active = false;  // never true; see RowMerge::touch
+    while (__any_sync(SPB_FULL_MASK, active)) {
+        if (active) {
+            i32 k;
+            double sum, b_scale;
+            if (!st.next(m, k, sum)) active = false;
+            else if (keep_output(m, k, sum, b_scale)) {
+                if (cnt == (u32)STAGE) { ok = false; active = false; }
+                else {
+                    sk[lane * PITCH + cnt] = k;
+                    sv[lane * PITCH + cnt] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
+                    ++cnt;
+                }
+            }
+        }
+    }
+    return ok;
+}
+
+template <int NLMAX>
+__global__ void __launch_bounds__(MR_THREADS, MergeBlocks<NLMAX>::value) k_merge_onepass(MMOperands m, u32 max_products, u64 *state, u32 *ticket,
+                                                                                         u32 *fail, ull *out, i32 *c_i, i32 *c_k, double *c_v) {
+    constexpr int STAGE = 16, PITCH = STAGE + 1, RUNS = 32 / STAGE;
+    __shared__ i32 s_k[MR_THREADS * PITCH];
+    __shared__ double s_v[MR_THREADS * PITCH];
+    __shared__ u32 s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 r = (u64)tile * MR_THREADS + threadIdx.x;
+    const bool skip = *(volatile u32 *)fail != 0;   // the result is lost already: publish an empty aggregate and leave
+    u32 s = 0, len = 0, cnt = 0;
+    i32 irow = 0;
+    u64 f = 0;
+    bool bad = false, mine = false;
+    if (r < m.nrows && !skip) {
+        s = m.arow_start[r];
+        len = m.arow_start[r + 1] - s;
+        irow = m.arow_id[r];
+        const bool on = !m.si || m.si[irow] != 0.0;  // row excluded by scalei (multiply_sparse.hpp:195)
+        bad = on && len > (u32)MERGE_MAX_LISTS;
+        mine = on && !bad;
+    }
+    const u32 rowlen = len;
+    if (!mine) len = 0;
+    const u32 maxlen = __reduce_max_sync(SPB_FULL_MASK, len);
+    i32 *sk = s_k + warp * 32 * PITCH;
+    double *sv = s_v + warp * 32 * PITCH;
+    bool ok = true;
+    if (maxlen == 0) ok = true;
+    else if (maxlen <= 2) ok = merge_rows_stage<2, STAGE>(m, mine, s, len, irow, max_products, sk, sv, cnt, f);
+    else if (NLMAX >= 4 && maxlen <= 4) ok = merge_rows_stage<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, max_products, sk, sv, cnt, f);
+    else if (NLMAX >= 6 && maxlen <= 6) ok = merge_rows_stage<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, max_products, sk, sv, cnt, f);
+    else if (NLMAX >= 8) ok = merge_rows_stage<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, max_products, sk, sv, cnt, f);
+    else ok = false;   // a row longer than this build covers (the host picks NLMAX from the longest row: cannot happen)
+    if (__any_sync(SPB_FULL_MASK, bad || !ok)) {
+        if (lane == 0) *fail = 1u;
+        cnt = 0;
+    }
+    // place the warp: exclusive prefix of the warps' output counts, in row order
+    const u32 incl = warp_incl_scan(cnt);
+    const u32 wtotal = __shfl_sync(SPB_FULL_MASK, incl, 31);
+    const u32 wid = tile * (MR_THREADS / 32) + warp;
+    const u64 base = lookback_exclusive(state, wid, (u64)wtotal);
+    const u64 dst = base + incl - cnt;
+    __syncwarp();
+#pragma unroll 4
+    for (int it = 0; it < 32 / RUNS; ++it) {
+        const int l = RUNS * it + (int)(lane / STAGE);
+        const u32 t = lane % STAGE;
+        const u32 n_l = __shfl_sync(SPB_FULL_MASK, cnt, l);
+        const u64 d_l = __shfl_sync(SPB_FULL_MASK, dst, l);
+        const i32 i_l = __shfl_sync(SPB_FULL_MASK, irow, l);
+        if (t < n_l) {
+            __stcs(c_k + d_l + t, sk[l * PITCH + t]);
+            __stcs(c_v + d_l + t, sv[l * PITCH + t]);
+            __stcs(c_i + d_l + t, i_l);
+        }
+    }
+    // totals: one stripe per warp in turn (see k_merge_count)
+    u64 fsum = mine ? f : 0;
+    u32 nm = mine && f != 0 && f <= (u64)max_products;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fsum += __shfl_xor_sync(SPB_FULL_MASK, fsum, o);
+        nm += __shfl_xor_sync(SPB_FULL_MASK, nm, o);
+    }
+    const u32 longest = __reduce_max_sync(SPB_FULL_MASK, rowlen);
+    if (lane == 0) {
+        ull *mine_s = out + 8 + (size_t)(wid % MC_STRIPES) * 8;
+        if (fsum) atomicAdd(&mine_s[0], (ull)fsum);
+        if (nm) atomicAdd(&mine_s[1], (ull)nm);
+        if (longest > (u32)mine_s[6]) atomicMax(&mine_s[6], (ull)longest);
+        if ((u64)tile * MR_THREADS + (u64)(warp + 1) * 32 >= (u64)m.nrows && (u64)tile * MR_THREADS + (u64)warp * 32 < (u64)m.nrows)
+            out[0] = base + wtotal;   // the warp that holds the last row: everything before it is placed
+    }
+}
+
 // ---- longer rows: shared-memory bitmap (symbolic) + shared-memory hash accumulators (numeric) ----------
 // Symbolic, one block per row: every product sets the bit of its column in a shared-memory bitmap (order-free,
 // so all warps work at once); scanning the bitmap yields the row's DISTINCT OUTPUT COLUMNS ALREADY IN ASCENDING
