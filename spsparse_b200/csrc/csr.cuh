@@ -79,6 +79,23 @@ __global__ void k_scatter_row_len(const u32 *__restrict__ row_start, const i32 *
         len[row_id[r]] = row_start[r + 1] - row_start[r];
 }
 
+// Dense pointer straight from the compressed rows: ptr[v] = offset of the first entry whose leading index is >= v, for v in
+// [0, extent].  Compressed row t fills the values (id[t-1], id[t]] -- the empty rows in front of it and itself -- and the last
+// one also everything behind it.  One read of the compressed rows, one write of the pointer; no zero-fill, no scan.
+__global__ void k_dense_ptr_from_rows(const u32 *__restrict__ row_start, const i32 *__restrict__ row_id, u32 nrows, u32 n, u64 extent, u32 *ptr) {
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < nrows; t += (u64)gridDim.x * blockDim.x) {
+        const u64 hi = (u64)(u32)row_id[t];
+        const u64 lo = t ? (u64)(u32)row_id[t - 1] + 1 : 0;
+        const u32 at = row_start[t];
+        for (u64 v = lo; v <= hi; ++v) ptr[v] = at;
+        if (t + 1 == nrows)
+            for (u64 v = hi + 1; v <= extent; ++v) ptr[v] = n;
+    }
+}
+__global__ void k_fill_u32(u32 *p, u64 count, u32 value) {
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (u64)gridDim.x * blockDim.x) p[t] = value;
+}
+
 // Same for the leading-index values lo..hi-1 only: len[1 + id - lo] = entries of that row, len[0] = entries of the
 // rows below lo (so that the exclusive scan of len[] yields absolute offsets from its second element on).
 __global__ void k_scatter_row_len_range(const u32 *__restrict__ row_start, const i32 *__restrict__ row_id,

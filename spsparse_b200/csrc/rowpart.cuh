@@ -196,19 +196,43 @@ __global__ void __launch_bounds__(RP_PULL_THREADS) k_rp_pull(RpArgs a, const u64
             const double *sv = a.reg[g].vals + s_elo[g];
             i32 *dc = out_c + s_base[g];
             double *dv = out_v + s_base[g];
-            for (u64 c0 = (u64)blockIdx.x * CHUNK; c0 < cnt; c0 += (u64)gridDim.x * CHUNK) {
-                i32 k[RP_PULL_UNROLL];
-                double v[RP_PULL_UNROLL];
+            // 16-byte loads from the peer (NVLink moves 512 B per warp request instead of 128 / 256): the source is aligned to
+            // 16 bytes from entry `head` on (the shard starts on a 256-byte boundary), the destination is written entry by entry
+            const u32 head_c = min(cnt, (4u - (s_elo[g] & 3u)) & 3u), quads = (cnt - head_c) / 4, tail_c = head_c + quads * 4;
+            const u32 head_v = min(cnt, s_elo[g] & 1u), pairs = (cnt - head_v) / 2, tail_v = head_v + pairs * 2;
+            const int4 *sc4 = reinterpret_cast<const int4 *>(sc + head_c);
+            const double2 *sv2 = reinterpret_cast<const double2 *>(sv + head_v);
+            for (u64 q0 = (u64)blockIdx.x * CHUNK; q0 < quads; q0 += (u64)gridDim.x * CHUNK) {
+                int4 k[RP_PULL_UNROLL];
 #pragma unroll
                 for (int u = 0; u < RP_PULL_UNROLL; ++u) {
-                    const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
-                    if (t < cnt) { k[u] = __ldcg(sc + t); v[u] = __ldcg(sv + t); }   // L2 only: the owner rewrites these every step
+                    const u64 q = q0 + (u64)u * RP_PULL_THREADS + tid;
+                    if (q < quads) k[u] = __ldcg(sc4 + q);   // L2 only: the owner rewrites these every other step
                 }
 #pragma unroll
                 for (int u = 0; u < RP_PULL_UNROLL; ++u) {
-                    const u64 t = c0 + (u64)u * RP_PULL_THREADS + tid;
-                    if (t < cnt) { dc[t] = k[u]; dv[t] = v[u]; }
+                    const u64 q = q0 + (u64)u * RP_PULL_THREADS + tid;
+                    if (q < quads) { i32 *d = dc + head_c + 4 * q; d[0] = k[u].x; d[1] = k[u].y; d[2] = k[u].z; d[3] = k[u].w; }
                 }
+            }
+            for (u64 q0 = (u64)blockIdx.x * CHUNK; q0 < pairs; q0 += (u64)gridDim.x * CHUNK) {
+                double2 v[RP_PULL_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RP_PULL_UNROLL; ++u) {
+                    const u64 q = q0 + (u64)u * RP_PULL_THREADS + tid;
+                    if (q < pairs) v[u] = __ldcg(sv2 + q);
+                }
+#pragma unroll
+                for (int u = 0; u < RP_PULL_UNROLL; ++u) {
+                    const u64 q = q0 + (u64)u * RP_PULL_THREADS + tid;
+                    if (q < pairs) { double *d = dv + head_v + 2 * q; d[0] = v[u].x; d[1] = v[u].y; }
+                }
+            }
+            if (blockIdx.x == 0) {   // the few entries in front of and behind the aligned body
+                if (tid < head_c) dc[tid] = __ldcg(sc + tid);
+                if (tid < cnt - tail_c) dc[tail_c + tid] = __ldcg(sc + tail_c + tid);
+                if (tid < head_v) dv[tid] = __ldcg(sv + tid);
+                if (tid < cnt - tail_v) dv[tail_v + tid] = __ldcg(sv + tail_v + tid);
             }
         }
         // row pointers of the fetched rows, re-based to where the entries are (own rows in place: offset slack)

@@ -964,15 +964,12 @@ static int build_dense_ptr(spb_ctx *ctx, const spb_coo *a_const, u64 extent, u32
     if (!a->dense_ptr) {
         RowIndex ri;
         CKR(build_row_index(ctx, a, &ri));
-        Scratch ws(ctx);
-        u32 *len, *cnt;
-        CKR(ws.zeroed(&len, extent + 1));
-        CKR(ws.get(&cnt, 1));
         CK(ctx->pool.alloc((void **)&a->dense_ptr, (extent + 2) * sizeof(u32)));
-        CK(cudaMemcpyAsync(cnt, &ri.nrows, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-        if (ri.nrows) ++ctx->launches, k_scatter_row_len<<<grid_for(ri.nrows, 256, 1u << 20), 256, 0, ctx->stream>>>(ri.start, ri.id, cnt, len);
-        CKR((exclusive_scan<u32, u32>(ctx, ws, len, a->dense_ptr, extent)));
-        CK(cudaStreamSynchronize(ctx->stream));
+        // straight from the compressed rows (one read, one write; nothing is read back: no host synchronisation)
+        ++ctx->launches;
+        if (ri.nrows) k_dense_ptr_from_rows<<<grid_for(ri.nrows, 256, (u32)ctx->sm_count * 16), 256, 0, ctx->stream>>>(ri.start, ri.id, ri.nrows, (u32)a->n, extent, a->dense_ptr);
+        else k_fill_u32<<<grid_for(extent + 1, 256, (u32)ctx->sm_count * 16), 256, 0, ctx->stream>>>(a->dense_ptr, extent + 1, 0u);
+        CK(cudaGetLastError());
     }
     *ptr_out = a->dense_ptr;
     return 0;
