@@ -838,7 +838,7 @@ def cpu_baseline(args):
     (reference semantics, NOT the reference's algorithm) on a larger member, labelled as such."""
     from oracle import oracle as O
     impl, kind = ref_impl()
-    sizes = [2 * args.cpu_rows, 4 * args.cpu_rows] if args.cpu_full else [args.cpu_rows // 2, args.cpu_rows]
+    sizes = [args.cpu_rows, 2 * args.cpu_rows] if args.cpu_full else [args.cpu_rows // 2, args.cpu_rows]
     runs = []
     for n in sizes:
         A, B, W = banded_sample(n)
@@ -871,7 +871,7 @@ def cpu_baseline(args):
                                     ", consolidate(ret, A, {0,1}), " + ("genuine reference" if kind == "reference" else "oracle port")}
     del a
     # the row-wise CPU oracle: same results as the reference wherever the reference can run, linear in the products
-    no = 100_000_000 if args.cpu_full else args.cpu_oracle_rows
+    no = 20_000_000 if args.cpu_full else args.cpu_oracle_rows
     A, B, W = banded_sample(no)
     t0 = time.perf_counter()
     out = O.port().multiply_mm(1.0, None, A, ".", W, B, ".", None)
@@ -971,11 +971,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-only", action="store_true", help="only the CPU baselines (with --cpu-full: BASELINE.md section 5's full sizes), no GPU work")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
     if args.impl == "reference":
         return run_reference(args)
+    if args.cpu_only:
+        print(json.dumps({"cpu_baseline": cpu_baseline(args)}))
+        return None
     return run_ours(args)
 
 
