@@ -11,7 +11,14 @@
 #include "common.cuh"
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_IPT = 16;
+#ifndef RS_IPT_N
+#define RS_IPT_N 16      // entries per thread of a radix-pass tile (same-box A/B builds: -DRS_IPT_N=10 -DRS_MIN_BLOCKS=4)
+#endif
+#ifndef RS_MIN_BLOCKS
+#define RS_MIN_BLOCKS 3
+#endif
+constexpr int RS_IPT = RS_IPT_N;
+constexpr int RS_HB = RS_IPT / 2;   // pass 0 without bulk copies: two batches of loads
 constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 entries per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_RADIX_BITS = 8;
@@ -188,7 +195,7 @@ struct PassArgs {
 // (cp.async.bulk + mbarrier; one thread issues them, 64 KB in flight per block at no register cost) instead of 16 + 16 loads
 // per thread; the values arrive while the keys are being ranked.
 template <bool PASS0, bool BULK = false>
-__global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortInput in) {
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) k_radix_pass(PassArgs a, SortInput in) {
     __shared__ __align__(8) u64 s_mbar[2];
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);
@@ -247,11 +254,11 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
         // two batches of 8 so that at most 8 x (hi, lo, val) loads are in flight per thread; the value
         // is only tested here (drop rule) and re-read from L2 when it is staged below
 #pragma unroll
-        for (int h = 0; h < RS_IPT; h += 8) {
-            i32 hi[8], lo[8];
-            double v[8];
+        for (int h = 0; h < RS_IPT; h += RS_HB) {
+            i32 hi[RS_HB], lo[RS_HB];
+            double v[RS_HB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RS_HB; ++k) {
                 u64 i = wbase + (u64)(h + k) * 32;
                 u64 ic = i < n ? i : (u64)n - 1;  // clamp: loads stay unconditional
                 hi[k] = ld_stream_i32(in.hi + ic);
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass(PassArgs a, SortIn
                 v[k] = in.val[ic];
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RS_HB; ++k) {
                 u64 i = wbase + (u64)(h + k) * 32;
                 bool ok = (i < n) && ((u32)hi[k] < in.extent_hi) && ((u32)lo[k] < in.extent_lo) &&
                           input_kept(in, (u32)i, v[k]);

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(R9_RADIX / 2) k_bucket_starts9(u32 *hist) {
 
 // PassArgs as for k_radix_pass, with bucket_start[512] and lookback[tiles][512] (8-byte aligned); rank_mode unused.
 template <bool PASS0, bool BULK = false>
-__global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortInput in) {
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) k_radix_pass9(PassArgs a, SortInput in) {
     __shared__ __align__(8) u64 s_mbar[2];   // BULK: see k_radix_pass
     extern __shared__ __align__(128) unsigned char smem_raw9[];
     u64 *s_keys = reinterpret_cast<u64 *>(smem_raw9);
@@ -199,11 +199,11 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
         }
     } else if (PASS0) {
 #pragma unroll
-        for (int h = 0; h < RS_IPT; h += 8) {
-            i32 hi[8], lo[8];
-            double v[8];
+        for (int h = 0; h < RS_IPT; h += RS_HB) {
+            i32 hi[RS_HB], lo[RS_HB];
+            double v[RS_HB];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RS_HB; ++k) {
                 u64 i = wbase + (u64)(h + k) * 32;
                 u64 ic = i < n ? i : (u64)n - 1;  // clamp: loads stay unconditional
                 hi[k] = ld_stream_i32(in.hi + ic);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) k_radix_pass9(PassArgs a, SortI
                 v[k] = in.val[ic];
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < RS_HB; ++k) {
                 u64 i = wbase + (u64)(h + k) * 32;
                 bool ok = (i < n) && ((u32)hi[k] < in.extent_hi) && ((u32)lo[k] < in.extent_lo) &&
                           input_kept(in, (u32)i, v[k]);

@@ -10,7 +10,14 @@
 #define LB_FLAG(w) ((w) >> 62)
 
 // Called by ALL 32 lanes of one warp.  Publishes `aggregate` for `tile`, walks back over the
-// predecessors 32 at a time, publishes the inclusive prefix and returns the exclusive prefix.
+// predecessors 32 * LB_WIDE at a time (every lane holds LB_WIDE consecutive status words, all loads of a round in
+// flight together), publishes the inclusive prefix and returns the exclusive prefix.
+// LB_WIDE = 1 (32 predecessors per round) is the measured optimum: the nearest inclusive prefix is almost always within
+// the first 32 predecessors, and 128 / 256 per round made the reduce pass slower (5.61 -> 6.50 -> 7.63 ms on 5e8 entries,
+// profiles/r02_notes.md) -- the barrier stalls of that kernel are not this walk.
+#ifndef LB_WIDE
+#define LB_WIDE 1
+#endif
 __device__ __forceinline__ u64 lookback_exclusive(u64 *state, u32 tile, u64 aggregate) {
     const u32 lane = lane_id();
     if (tile == 0) {
@@ -21,22 +28,41 @@ __device__ __forceinline__ u64 lookback_exclusive(u64 *state, u32 tile, u64 aggr
     u64 excl = 0;
     i64 top = (i64)tile - 1;
     for (;;) {
-        i64 idx = top - (i64)lane;
-        u64 w = (idx >= 0) ? ld_relaxed_u64(&state[idx]) : LB_FLAG_INCL;
-        while (__any_sync(SPB_FULL_MASK, LB_FLAG(w) == 0)) {
-            if (LB_FLAG(w) == 0) w = ld_relaxed_u64(&state[idx]);
+        // word u of lane l is the predecessor at distance l * LB_WIDE + u from `top`: nearer predecessors in lower lanes
+        u64 w[LB_WIDE];
+#pragma unroll
+        for (int u = 0; u < LB_WIDE; ++u) {
+            const i64 idx = top - (i64)(lane * LB_WIDE + u);
+            w[u] = (idx >= 0) ? ld_relaxed_u64(&state[idx]) : LB_FLAG_INCL;
         }
-        u32 incl = __ballot_sync(SPB_FULL_MASK, LB_FLAG(w) == 2);
-        u64 v = LB_VALUE(w);
+        for (;;) {
+            bool missing = false;
+#pragma unroll
+            for (int u = 0; u < LB_WIDE; ++u) missing |= LB_FLAG(w[u]) == 0;
+            if (!__any_sync(SPB_FULL_MASK, missing)) break;
+#pragma unroll
+            for (int u = 0; u < LB_WIDE; ++u)
+                if (LB_FLAG(w[u]) == 0) w[u] = ld_relaxed_u64(&state[top - (i64)(lane * LB_WIDE + u)]);
+        }
+        // my words up to and including my first inclusive one
+        u64 v = 0;
+        bool has_incl = false;
+#pragma unroll
+        for (int u = 0; u < LB_WIDE; ++u)
+            if (!has_incl) {
+                v += LB_VALUE(w[u]);
+                has_incl = LB_FLAG(w[u]) == 2;
+            }
+        const u32 incl = __ballot_sync(SPB_FULL_MASK, has_incl);
         if (incl) {
-            u32 first = __ffs(incl) - 1;
+            const u32 first = __ffs(incl) - 1;   // the nearest inclusive prefix is in this lane: farther lanes do not count
             if (lane > first) v = 0;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(SPB_FULL_MASK, v, o);
         excl += v;
         if (incl) break;
-        top -= 32;
+        top -= 32 * LB_WIDE;
     }
     if (lane == 0) st_relaxed_u64(&state[tile], LB_FLAG_INCL | (excl + aggregate));
     return excl;
