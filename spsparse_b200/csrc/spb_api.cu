@@ -1246,6 +1246,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     const int t_mcount = tm.mark();
     ull h_stats[8];
     u32 *hash_rows = nullptr;
+    u32 hash_small = 0;   // the first hash_small rows of hash_rows[] have at most HSM_CAP products
     u32 h_bad = 0;
     // the rows are placed right away, as if there were no long rows (true for banded / regridding matrices): the output
     // count then comes back with the counters in ONE round trip; with long rows the scan is repeated further down
@@ -1281,13 +1282,24 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         CKR((exclusive_scan<u32, u64>(ctx, ws, ent_f, ent_off, m.nnz_a)));
         // second-level bin: long rows with enough products use the bitmap + hash accumulators (needs the columns to fit the bitmap)
         const bool hash_ok = ctx->hash_min_products != ~0ull;
-        if (hash_ok) CKR(ws.get(&hash_rows, h_stats[2]));
-        ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, ctx->hash_min_products, hash_rows, stats);
+        u32 *hash_rows_big = nullptr;
+        if (hash_ok) { CKR(ws.get(&hash_rows, h_stats[2])); CKR(ws.get(&hash_rows_big, h_stats[2])); }
+        // rows of at most HSM_CAP products: columns listed by a sort in shared memory (SPB_HASH_SMALL=0: everything by bitmap)
+        // -- for matrices wider than the bitmap, where a row costs one bitmap unit PER COLUMN WINDOW (2^24 columns: 11): measured
+        // 3.67 -> 2.69 s of config 4's sweep; with one window (R-MAT scale 20) the bitonic sort loses to the bitmap (29.8 -> 36.4 ms),
+        // so there it needs SPB_HASH_SMALL=1
+        const char *hs_env = getenv("SPB_HASH_SMALL");
+        const bool wide = n_cols > (getenv("SPB_HASH_WIN_COLS") ? strtoull(getenv("SPB_HASH_WIN_COLS"), nullptr, 10) : (u64)HASH_MAX_COLS);
+        const u64 small_max = (hs_env ? atoi(hs_env) != 0 : wide) ? (u64)HSM_CAP : 0;
+        ++ctx->launches, k_esc_row_products<<<grid_for(nrows, 256, cap), 256, 0, ctx->stream>>>(m, ent_off, row_cls, esc_f, ctx->hash_min_products, small_max, hash_rows, hash_rows_big, stats);
         CK(cudaGetLastError());
         ull h_long[8];
         CK(cudaMemcpyAsync(h_long, stats, sizeof h_long, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         h_stats[3] = h_long[3]; h_stats[4] = h_long[4]; h_stats[5] = h_long[5];   // [0..2], [6] came from the count kernel's stripes
+        hash_small = (u32)h_long[6];
+        if (h_long[7])   // one list: the small rows, then the others
+            CK(cudaMemcpyAsync(hash_rows + h_long[6], hash_rows_big, h_long[7] * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
         ws.release(ent_f);
     }
 
@@ -1314,7 +1326,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         ha.n_win = (u32)div_up(n_cols ? n_cols : 1, win_cols);
         ha.win_cols = (u32)win_cols;
         const u64 units = (u64)ha.nrows * ha.n_win;
-        CKR(ws.get(&ha.win_cnt, units));
+        CKR(ws.zeroed(&ha.win_cnt, units));
         CKR(ws.get(&ha.win_pre, units));
         CKR(ws.get(&ha.seg_off, units));
         // the rows' output columns, written by the one bitmap pass before the rows are placed: at most one per product
@@ -1332,7 +1344,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         CKR(ws.zeroed(&ha.split_total, 2));
         ha.tmp_cursor = ha.split_total + 1;
         CKR(ws.get(&ha.row_split, ha.nrows));
-        if (ha.n_win > 1 && (u64)m.nnz_a * (ha.n_win - 1) <= (1ull << 30) && !getenv("SPB_HASH_NO_WIN_BOUNDS")) {
+        ha.row0 = hash_small;
+        if (ha.nrows > hash_small && ha.n_win > 1 && (u64)m.nnz_a * (ha.n_win - 1) <= (1ull << 30) && !getenv("SPB_HASH_NO_WIN_BOUNDS")) {
             // wide matrix: where every window begins in every B row, found by one parallel kernel (4 GB of positions at most;
             // beyond that the bitmap kernel searches for itself)
             u32 *wb;
@@ -1340,7 +1353,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
             ++ctx->launches, k_hash_win_bounds<<<ha.nrows < 65535u * 16u ? ha.nrows : 65535u * 16u, 128, 0, ctx->stream>>>(m, ha, wb);
             ha.win_bound = wb;
         }
-        ++ctx->launches, k_hash_symbolic<<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
+        if (hash_small) ++ctx->launches, k_hash_symbolic_small<<<hash_small < (u32)ctx->sm_count * 6 ? hash_small : (u32)ctx->sm_count * 6, HSM_THREADS, 0, ctx->stream>>>(m, ha, hash_small);
+        if (ha.nrows > hash_small) ++ctx->launches, k_hash_symbolic<<<hs_grid, HS_THREADS, hs_smem, ctx->stream>>>(m, ha);
         CK(cudaGetLastError());
     }
 

@@ -74,8 +74,10 @@ __global__ void k_entry_products(MMOperands m, const i32 *__restrict__ a_row, u3
 // Long rows with at least hash_min_products products go to the bitmap + hash-accumulator kernels (ROW_HASH; only
 // offered when the output columns fit the shared-memory bitmap), the rest stay with expand-sort-compress (ROW_ESC).
 // stats: [0] F merged rows, [1] rows merged, [2] rows long (ESC+HASH), [3] F ESC rows, [4] F HASH rows, [5] rows HASH
+// ROW_HASH rows with at most hash_small_max products go to hash_rows (k_hash_symbolic_small lists their columns by sorting them in
+// shared memory, whatever the width of the matrix), the others to hash_rows_big (bitmap, column windows); stats[6] / [7] count them.
 __global__ void k_esc_row_products(MMOperands m, const u64 *__restrict__ ent_off, unsigned char *row_cls, u64 *esc_f,
-                                   u64 hash_min_products, u32 *hash_rows, ull *stats) {
+                                   u64 hash_min_products, u64 hash_small_max, u32 *hash_rows, u32 *hash_rows_big, ull *stats) {
     u64 f_esc = 0, f_hash = 0;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < m.nrows; r += (u64)gridDim.x * blockDim.x) {
         u64 f = 0;
@@ -83,7 +85,9 @@ __global__ void k_esc_row_products(MMOperands m, const u64 *__restrict__ ent_off
             f = ent_off[m.arow_start[r + 1]] - ent_off[m.arow_start[r]];
             if (hash_rows && f >= hash_min_products) {
                 row_cls[r] = ROW_HASH;
-                hash_rows[atomicAdd(&stats[5], 1ull)] = (u32)r;
+                atomicAdd(&stats[5], 1ull);
+                if (f <= hash_small_max) hash_rows[atomicAdd(&stats[6], 1ull)] = (u32)r;
+                else hash_rows_big[atomicAdd(&stats[7], 1ull)] = (u32)r;
                 f_hash += f;
                 f = 0;
             }
@@ -590,8 +594,9 @@ constexpr int HS_WARPS = HS_THREADS / 32;
 constexpr u32 HASH_MAX_COLS = 1572864;      // 192 KB of bitmap
 
 struct HashArgs {
-    const u32 *rows;     // compressed row numbers of the ROW_HASH rows
+    const u32 *rows;     // compressed row numbers of the ROW_HASH rows: the small ones (k_hash_symbolic_small) first
     u32 nrows;
+    u32 row0;            // bitmap kernel: first row of rows[] it handles (the rows before it went to k_hash_symbolic_small)
     u32 *next;           // work counter (zeroed before every launch)
     u32 wpw;             // bitmap words per warp of the symbolic kernel (multiple of 32; HS_WARPS * wpw * 32 >= columns)
     u32 cap;             // outputs per numeric work item (HASH_CAP of the numeric kernel that will run)
@@ -671,7 +676,7 @@ __device__ __forceinline__ u32 hn_lower_bound(const i32 *__restrict__ b_k, u32 l
 // dependent L2 round trips in front of every (row, window) unit, 45 % of its time at 2^24 columns (11 windows).
 __global__ void __launch_bounds__(128) k_hash_win_bounds(MMOperands m, HashArgs a, u32 *win_bound) {
     const u32 nb = a.n_win - 1;
-    for (u32 hrow = blockIdx.x; hrow < a.nrows; hrow += gridDim.x) {
+    for (u32 hrow = a.row0 + blockIdx.x; hrow < a.nrows; hrow += gridDim.x) {   // (the rows before row0 are listed without windows)
         const u32 r = a.rows[hrow];
         const u32 s = m.arow_start[r], len = m.arow_start[r + 1] - s;
         for (u32 t = threadIdx.x; t < len * nb; t += blockDim.x) {
@@ -752,8 +757,8 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
         __syncthreads();
         if (tid == 0) s_row = atomicAdd(a.next, 1u);
         __syncthreads();
-        if (s_row >= a.nrows * a.n_win) return;
-        const u32 hrow = s_row / a.n_win, win = s_row % a.n_win;  // index into rows[], column window
+        if (s_row >= (a.nrows - a.row0) * a.n_win) return;
+        const u32 hrow = a.row0 + s_row / a.n_win, win = s_row % a.n_win;  // index into rows[], column window
         const u32 col0 = win * a.win_cols;                        // first column of the window
         const u32 r = a.rows[hrow];
         const u32 s = m.arow_start[r], e = m.arow_start[r + 1];
@@ -912,6 +917,93 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
             const u32 incl = warp_incl_scan(c);
             u64 pos = base + s_gcnt[g] + incl - c;
             for (; bits; bits &= bits - 1, ++pos) a.tmp_k[pos] = (i32)(col0 + w * 32 + __ffs(bits) - 1);
+        }
+    }
+}
+
+// ---- symbolic for rows of a few thousand products: sort their columns in shared memory ---------------------------------------
+// The bitmap costs the same ~20 us per (row, column window) whether the row has 600 products or 60 000, and a matrix of 2^24
+// columns has 11 windows per row: half of config 4's long rows have fewer than 8192 products and cost half of the bitmap
+// pass for 5 % of the products.  Here a 256-thread block gathers ALL product columns of such a row into shared memory (one warp
+// per B row, coalesced), sorts them (bitonic network, padded to a power of two), drops repeats and columns masked by scalek and
+// writes the list -- one segment per row, filed under its first window, so that everything downstream (k_hash_items, the
+// numeric kernel) reads it like any other row's.  Independent of the matrix width; six blocks per SM.
+constexpr int HSM_THREADS = 256;
+constexpr u32 HSM_CAP = 8192;
+__global__ void __launch_bounds__(HSM_THREADS) k_hash_symbolic_small(MMOperands m, HashArgs a, u32 n_small) {
+    __shared__ u32 s_key[HSM_CAP];
+    __shared__ u32 s_bs[HSM_THREADS], s_pre[HSM_THREADS + 1];
+    __shared__ u32 s_wsum[2][HSM_THREADS / 32];
+    __shared__ u32 s_cnt[HSM_THREADS / 32];
+    __shared__ u64 s_base;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (u32 hrow = blockIdx.x; hrow < n_small; hrow += gridDim.x) {
+        const u32 r = a.rows[hrow];
+        const u32 s = m.arow_start[r], e = m.arow_start[r + 1];
+        // ---- all product columns of the row, entry after entry ---------------------------------------------------------
+        u32 T = 0;
+        for (u32 c0 = s; c0 < e; c0 += HSM_THREADS) {
+            const u32 ent = c0 + tid;
+            u32 bs = 0, len = 0;
+            if (ent < e) {
+                const i32 j = m.a_j[ent];
+                if (!m.sj_mask || m.sj_mask[j]) { bs = m.bptr[j]; len = m.bptr[j + 1] - bs; }
+            }
+            u32 nE, Tc;
+            __syncthreads();   // the previous chunk's staging (and the previous row's keys) are no longer read
+            stage_entries<HSM_THREADS>(bs, len, s_bs, s_pre, s_wsum, nE, Tc, [](u32) {});
+            for (u32 x = warp; x < nE; x += HSM_THREADS / 32) {
+                const u32 b0 = s_bs[x], p0 = T + s_pre[x], ln = s_pre[x + 1] - s_pre[x];
+                for (u32 t = lane; t < ln; t += 32)
+                    if (p0 + t < HSM_CAP) s_key[p0 + t] = (u32)ld_stream_i32(m.b_k + b0 + t);   // (the host only sends rows that fit)
+            }
+            T += Tc;
+        }
+        if (T > HSM_CAP) T = HSM_CAP;
+        u32 P = 64;
+        while (P < T) P <<= 1;
+        __syncthreads();
+        for (u32 t = T + tid; t < P; t += HSM_THREADS) s_key[t] = 0xffffffffu;
+        __syncthreads();
+        // ---- bitonic sort of s_key[0..P) ---------------------------------------------------------------------------------
+        for (u32 k = 2; k <= P; k <<= 1)
+            for (u32 j = k >> 1; j > 0; j >>= 1) {
+                for (u32 p = tid; p < P / 2; p += HSM_THREADS) {
+                    const u32 lo = ((p & ~(j - 1)) << 1) | (p & (j - 1)), hi = lo + j;
+                    const u32 x = s_key[lo], y = s_key[hi];
+                    if ((x > y) == ((lo & k) == 0)) { s_key[lo] = y; s_key[hi] = x; }
+                }
+                __syncthreads();
+            }
+        // ---- distinct, unmasked columns: every thread a contiguous stretch --------------------------------------------
+        const u32 per = P / HSM_THREADS > 0 ? P / HSM_THREADS : 1;   // P >= 64: threads beyond P / per have nothing
+        const u32 i0 = tid * per, i1 = min(P, i0 + per);
+        u32 mine = 0;
+        for (u32 i = i0; i < i1 && i0 < P; ++i) {
+            const u32 c = s_key[i];
+            if (c != 0xffffffffu && (i == 0 || s_key[i - 1] != c) && (!m.sk || m.sk[c] != 0.0)) ++mine;
+        }
+        const u32 incl = warp_incl_scan(mine);
+        if (lane == 31) s_cnt[warp] = incl;
+        __syncthreads();
+        u32 before = incl - mine, total = 0;
+#pragma unroll
+        for (int w = 0; w < HSM_THREADS / 32; ++w) {
+            if ((u32)w < warp) before += s_cnt[w];
+            total += s_cnt[w];
+        }
+        if (tid == 0) {
+            const u64 unit = (u64)hrow * a.n_win;
+            s_base = total ? atomicAdd(a.tmp_cursor, (ull)total) : 0ull;
+            a.seg_off[unit] = s_base;
+            a.win_cnt[unit] = total;     // the other windows of the row stay 0 (zeroed by the host)
+            a.row_cnt[r] = total;
+        }
+        __syncthreads();
+        u64 pos = s_base + before;
+        for (u32 i = i0; i < i1 && i0 < P; ++i) {
+            const u32 c = s_key[i];
+            if (c != 0xffffffffu && (i == 0 || s_key[i - 1] != c) && (!m.sk || m.sk[c] != 0.0)) a.tmp_k[pos++] = (i32)c;
         }
     }
 }

@@ -86,6 +86,11 @@ def test_mm_fixtures_through_the_hash_accumulator_bin(monkeypatch, variant, item
         monkeypatch.setenv("SPB_HASH_ITEM_CAP", str(item_cap))
     if win_cols:  # bitmap narrower than the matrix: rows are handled in several column windows
         monkeypatch.setenv("SPB_HASH_WIN_COLS", str(win_cols))
+        # ... by the bitmap kernel: rows of a few thousand products would otherwise have their columns listed by the
+        # shared-memory sort (k_hash_symbolic_small), which knows no windows -- the runs without win_cols go through that one
+        monkeypatch.setenv("SPB_HASH_SMALL", "0" if variant != 1 else "1")
+    else:
+        monkeypatch.setenv("SPB_HASH_SMALL", "1" if variant == 2 else "0")
     p = _golden.pack("multiply_mm_cases")
     with sp.Context(0) as c2:
         for s in range(variant, int(p["count"]), 3 if item_cap == 0 else 5):
