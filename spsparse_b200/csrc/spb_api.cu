@@ -1335,6 +1335,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         CKR(ws.get(&ha.tmp_k, tmp_cap));
         ha.wpw = (u32)(div_up(div_up(ha.n_win > 1 ? win_cols : n_cols, 32), HS_WARPS) + 31) & ~31u;
         ha.cap = hash_cap;
+        ha.no_sparse_walk = (getenv("SPB_HASH_SPARSE_WALK") && atoi(getenv("SPB_HASH_SPARSE_WALK")) == 0) ? 1u : 0u;
         ha.row_cnt = row_cnt;
         hs_grid = units < (u64)ctx->sm_count ? (u32)units : (u32)ctx->sm_count;
         hs_smem = (size_t)HS_WARPS * ha.wpw * sizeof(u32);

@@ -592,6 +592,8 @@ __global__ void __launch_bounds__(MR_THREADS, MergeBlocks<NLMAX>::value) k_merge
 constexpr int HS_THREADS = 1024;            // symbolic (bitmap) kernel
 constexpr int HS_WARPS = HS_THREADS / 32;
 constexpr u32 HASH_MAX_COLS = 1572864;      // 192 KB of bitmap
+constexpr u32 HS_LIST_CAP = HASH_MAX_COLS / 1024 * 3;   // sparse units: at most this many non-zero bitmap words (4608; list of u16)
+constexpr int HS_LIST_PER = (HS_LIST_CAP + HS_THREADS - 1) / HS_THREADS;   // consecutive list entries per thread (5)
 
 struct HashArgs {
     const u32 *rows;     // compressed row numbers of the ROW_HASH rows: the small ones (k_hash_symbolic_small) first
@@ -599,6 +601,7 @@ struct HashArgs {
     u32 row0;            // bitmap kernel: first row of rows[] it handles (the rows before it went to k_hash_symbolic_small)
     u32 *next;           // work counter (zeroed before every launch)
     u32 wpw;             // bitmap words per warp of the symbolic kernel (multiple of 32; HS_WARPS * wpw * 32 >= columns)
+    u32 no_sparse_walk;  // SPB_HASH_SPARSE_WALK=0: every unit walks all its 32-word groups (the round-2 path, for A/B runs)
     u32 cap;             // outputs per numeric work item (HASH_CAP of the numeric kernel that will run)
     u32 n_win;           // column windows per row: the bitmap covers win_cols columns at a time (1 when they all fit)
     u32 win_cols;        // multiple of 32
@@ -749,10 +752,16 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
     __shared__ u64 s_segbase;
     __shared__ u32 s_wsum[2][HS_WARPS];
     __shared__ u32 s_bs[HS_THREADS], s_pre[HS_THREADS + 1];
-    __shared__ u32 s_gcnt[HASH_MAX_COLS / 1024];  // set bits per group of 32 bitmap words, then their exclusive prefix
-    __shared__ unsigned short s_glist[HASH_MAX_COLS / 1024];  // the non-empty groups
+    // dense units: set bits per group of 32 bitmap words (then their exclusive prefix) and the list of the non-empty groups;
+    // sparse units: the list of the non-zero bitmap WORDS (same storage -- a unit takes one path or the other)
+    __shared__ __align__(8) unsigned char s_walk[HASH_MAX_COLS / 1024 * 6];
+    u32 *const s_gcnt = reinterpret_cast<u32 *>(s_walk);
+    unsigned short *const s_glist = reinterpret_cast<unsigned short *>(s_walk + HASH_MAX_COLS / 1024 * 4);
+    unsigned short *const s_list = reinterpret_cast<unsigned short *>(s_walk);
+    __shared__ u32 s_summ[HASH_MAX_COLS / 1024];  // one bit per bitmap word: set by the atomicOr that found the word empty
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (u32 w = tid; w < HS_WARPS * a.wpw; w += HS_THREADS) s_bitmap[w] = 0;
+    for (u32 w = tid; w < HASH_MAX_COLS / 1024; w += HS_THREADS) s_summ[w] = 0;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_row = atomicAdd(a.next, 1u);
@@ -818,7 +827,7 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
                         const u32 t = __shfl_down_sync(SPB_FULL_MASK, bits, o);
                         if (lane + o <= last) bits |= t;
                     }
-                    if (lane == first && bits) atomicOr(&s_bitmap[word], bits);
+                    if (lane == first && bits && atomicOr(&s_bitmap[word], bits) == 0) atomicOr(&s_summ[word >> 5], 1u << (word & 31));
                 }
             }
         }
@@ -828,6 +837,84 @@ __global__ void __launch_bounds__(HS_THREADS, 1) k_hash_symbolic(MMOperands m, H
         //      power-law rows pack their columns into one end of the bitmap, a contiguous stretch per warp would leave
         //      one warp with all the work. -------------------------------------------------------------------------------
         const u32 ngroups = HS_WARPS * a.wpw / 32;
+        // ---- how many bitmap words hold anything (summary bits; a thread owns summary words 2t and 2t+1, which it clears) ----
+        u32 n_nz, nz_before;
+        u32 sw0 = 0, sw1 = 0;
+        {
+            if (2 * tid < ngroups) { sw0 = s_summ[2 * tid]; s_summ[2 * tid] = 0; }
+            if (2 * tid + 1 < ngroups) { sw1 = s_summ[2 * tid + 1]; s_summ[2 * tid + 1] = 0; }
+            const u32 c = __popc(sw0) + __popc(sw1);
+            const u32 incl = warp_incl_scan(c);
+            if (lane == 31) s_wsum[0][warp] = incl;
+            __syncthreads();
+            nz_before = incl - c;
+            n_nz = 0;
+#pragma unroll
+            for (int w = 0; w < HS_WARPS; ++w) {
+                const u32 t = s_wsum[0][w];
+                if ((u32)w < warp) nz_before += t;
+                n_nz += t;
+            }
+        }
+        if (EMIT && n_nz <= HS_LIST_CAP && !a.no_sparse_walk) {
+            // ---- sparse unit (a few thousand outputs in tens of thousands of words -- most units of a wide matrix): only the
+            //      non-zero words are visited.  Their ordered list; then every thread takes HS_LIST_PER consecutive words of it,
+            //      counts, and writes its columns behind those of the threads before it.  Walking all the 32-word groups cost
+            //      the same ~45 instructions per group whether a group held one column or a thousand. ------------------------
+            {
+                u32 pos = nz_before;
+                for (u32 t = sw0; t; t &= t - 1) s_list[pos++] = (unsigned short)(2 * tid * 32 + __ffs(t) - 1);
+                for (u32 t = sw1; t; t &= t - 1) s_list[pos++] = (unsigned short)((2 * tid + 1) * 32 + __ffs(t) - 1);
+            }
+            __syncthreads();   // list complete; s_wsum read by everyone
+            const u32 per = (n_nz + HS_THREADS - 1) / HS_THREADS;   // <= HS_LIST_PER
+            const u32 l0 = tid * per;
+            u32 wbits[HS_LIST_PER];
+            u32 cnt = 0;
+#pragma unroll
+            for (int u = 0; u < HS_LIST_PER; ++u) {
+                wbits[u] = 0;
+                if ((u32)u < per && l0 + u < n_nz) {
+                    const u32 w = s_list[l0 + u];
+                    u32 bits = s_bitmap[w];
+                    s_bitmap[w] = 0;
+                    if (m.sk) {
+                        for (u32 t = bits; t; t &= t - 1) {
+                            const u32 b = __ffs(t) - 1;
+                            if (m.sk[col0 + w * 32 + b] == 0.0) bits &= ~(1u << b);
+                        }
+                    }
+                    wbits[u] = bits;
+                    cnt += __popc(bits);
+                }
+            }
+            const u32 incl = warp_incl_scan(cnt);
+            if (lane == 31) s_wsum[1][warp] = incl;
+            __syncthreads();
+            u32 before = incl - cnt, total = 0;
+#pragma unroll
+            for (int w = 0; w < HS_WARPS; ++w) {
+                const u32 t = s_wsum[1][w];
+                if ((u32)w < warp) before += t;
+                total += t;
+            }
+            if (tid == 0) {
+                const u64 unit = (u64)hrow * a.n_win + win;
+                s_segbase = total ? atomicAdd(a.tmp_cursor, (ull)total) : 0ull;
+                a.seg_off[unit] = s_segbase;
+                a.win_cnt[unit] = total;
+                if (total) atomicAdd(&a.row_cnt[r], total);
+            }
+            __syncthreads();
+            u64 pos = s_segbase + before;
+#pragma unroll
+            for (int u = 0; u < HS_LIST_PER; ++u) {
+                if (!wbits[u]) continue;
+                const u32 c0w = col0 + (u32)s_list[l0 + u] * 32;   // (the list stays put until the next unit)
+                for (u32 t = wbits[u]; t; t &= t - 1, ++pos) a.tmp_k[pos] = (i32)(c0w + __ffs(t) - 1);
+            }
+            continue;
+        }
         u32 mine = 0;
         for (u32 g = warp; g < ngroups; g += HS_WARPS) {
             const u32 w = g * 32 + lane;

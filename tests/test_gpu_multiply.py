@@ -293,8 +293,8 @@ def test_medium_scale_against_oracle(ctx, orc):
     dA.free(); R.free()
 
 
-@pytest.mark.parametrize("variant,win_cols", [(0, 0), (1, 0), (2, 0), (2, 4096)])
-def test_hash_accumulator_bin(orc, monkeypatch, variant, win_cols):
+@pytest.mark.parametrize("variant,win_cols,walk", [(0, 0, None), (1, 0, None), (2, 0, None), (2, 4096, None), (2, 0, "0"), (2, 4096, "0")])
+def test_hash_accumulator_bin(orc, monkeypatch, variant, win_cols, walk):
     """Long rows through the bitmap + hash-accumulator kernels: all three bins side by side, scale vectors, a row
     wider than one work item, and rows whose sums cancel exactly (they emit fewer entries than the symbolic
     bound -> gap compaction).  Bit-identical values throughout."""
@@ -333,6 +333,8 @@ def test_hash_accumulator_bin(orc, monkeypatch, variant, win_cols):
         monkeypatch.setenv("SPB_HASH_VARIANT", str(variant))
         if win_cols:
             monkeypatch.setenv("SPB_HASH_WIN_COLS", str(win_cols))
+        if walk is not None:   # "0": the bitmap kernel walks every 32-word group of every unit (the path before the summary bits)
+            monkeypatch.setenv("SPB_HASH_SPARSE_WALK", walk)
         with sp.Context(0) as c2:
             hs = [up(c2, x) for x in (scales[0], A, B, scales[1])]
             R, gst = sp.multiply(c2, 1.5, hs[0], hs[1], ".", None, hs[2], ".", hs[3], stats=True)
