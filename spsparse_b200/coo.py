@@ -33,6 +33,12 @@ class Context:
     def sync(self):
         check(self.lib.spb_ctx_sync(self.h))
 
+    def trim(self) -> int:
+        """Hands the context's cached device blocks back to the driver (spb_ctx_trim); returns the bytes released."""
+        freed = C.c_uint64(0)
+        check(self.lib.spb_ctx_trim(self.h, C.byref(freed)))
+        return freed.value
+
     def close(self):
         if self.h:
             self.lib.spb_ctx_destroy(self.h)

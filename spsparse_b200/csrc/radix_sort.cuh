@@ -446,9 +446,28 @@ constexpr int SG_IPT = 8;
 constexpr int SG_TILE = SG_THREADS * SG_IPT;
 constexpr int SEG_MAX = 64;
 
+// By-product for the reduce pass (reduce_warp.cuh): how many run heads (entries that are not a repeat of an earlier entry of
+// their row) and row heads (first entry of a row) end up in every 256-entry tile of the SORTED array.  The in-row sort knows
+// both for every entry it places; with the counts scanned, a reduce tile knows its place in the output without waiting for
+// its predecessors (no look-back chain).  The 32 entries a warp places in one step lie within 32 + 2 * (SEG_MAX - 1)
+// positions, i.e. in at most two consecutive tiles.  tile_cnt: head count | row-head count << 31, zeroed by the host.
+constexpr int SG_CNT_SHIFT = 8;   // log2 of the reduce pass's tile (RW_TILE)
+__device__ __forceinline__ void sg_count_heads(u64 *tile_cnt, bool valid, u64 dst, bool head, bool rhead) {
+    const u32 td = valid ? (u32)(dst >> SG_CNT_SHIFT) : 0xffffffffu;
+    const u32 t0 = __reduce_min_sync(SPB_FULL_MASK, td);
+    if (t0 == 0xffffffffu) return;
+#pragma unroll
+    for (u32 c = 0; c < 2; ++c) {
+        const u32 hb = __ballot_sync(SPB_FULL_MASK, valid && head && td == t0 + c);
+        const u32 rb = __ballot_sync(SPB_FULL_MASK, valid && rhead && td == t0 + c);
+        if (hb && lane_id() == 0) atomicAdd((ull *)&tile_cnt[t0 + c], (ull)__popc(hb) | ((ull)__popc(rb) << 31));
+    }
+}
+
 __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
                                                                 const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
-                                                                unsigned char *flags, u32 *long_count) {
+                                                                unsigned char *flags, u32 *long_count, u64 *tile_cnt = nullptr,
+                                                                int keep_all = 0) {
     // window = the tile plus SEG_MAX entries either side: a row of at most SEG_MAX entries that owns an entry of the
     // tile lies inside it completely
     constexpr int W = SG_TILE + 2 * SEG_MAX;
@@ -536,22 +555,27 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__res
         const u32 q = SEG_MAX + (u32)k * SG_THREADS + tid;
         const u64 g = base + (u64)k * SG_THREADS + tid;
         shift_by[k] = 0;
-        if (g >= n) continue;
-        const u32 grp = q >> 5, l = q & 31, hb = s_hb[grp];
-        const u32 below = hb & (0xffffffffu >> (31 - l));
-        const u32 st = below ? (grp << 5) + 31 - __clz(below) : s_last[grp];
-        const u32 above = l < 31 ? hb & (0xffffffffu << (l + 1)) : 0u;
-        const u32 nx = above ? (grp << 5) + __ffs(above) - 1 : s_first[grp];   // start of the next row
-        const bool is_long = nx - st > (u32)SEG_MAX;  // (a row cut by the window's edge shows more than SEG_MAX entries too)
-        if (!is_long) {
-            const u32 col = s_col[q];
-            u32 before = 0;
-            for (u32 j = st; j < q; ++j) before += s_col[j] <= col;      // earlier entries: stable
-            for (u32 j = q + 1; j < nx; ++j) before += s_col[j] < col;   // later entries
-            shift_by[k] = (i32)(st + before) - (i32)q;
+        bool head = true, rhead = false;
+        if (g < n) {
+            const u32 grp = q >> 5, l = q & 31, hb = s_hb[grp];
+            const u32 below = hb & (0xffffffffu >> (31 - l));
+            const u32 st = below ? (grp << 5) + 31 - __clz(below) : s_last[grp];
+            const u32 above = l < 31 ? hb & (0xffffffffu << (l + 1)) : 0u;
+            const u32 nx = above ? (grp << 5) + __ffs(above) - 1 : s_first[grp];   // start of the next row
+            const bool is_long = nx - st > (u32)SEG_MAX;  // (a row cut by the window's edge shows more than SEG_MAX entries too)
+            if (!is_long) {
+                const u32 col = s_col[q];
+                u32 before = 0, same = 0;
+                for (u32 j = st; j < q; ++j) { before += s_col[j] <= col; same += s_col[j] == col; }   // earlier entries: stable
+                for (u32 j = q + 1; j < nx; ++j) before += s_col[j] < col;   // later entries
+                shift_by[k] = (i32)(st + before) - (i32)q;
+                head = keep_all || same == 0;   // a repeat of an earlier entry of the row is folded into it by the reduce pass
+                rhead = before == 0;            // first of its row in column order
+            }
+            if (flags) flags[g] = is_long;
+            n_long += is_long;
         }
-        if (flags) flags[g] = is_long;
-        n_long += is_long;
+        if (tile_cnt) sg_count_heads(tile_cnt, g < n, (u64)((i64)g + shift_by[k]), head, rhead);
     }
     double v[SG_IPT];
 #pragma unroll
@@ -577,7 +601,8 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__res
 // kernel above; at config 2's 12 entries per row the walk costs 4.5 ms against 2.5 ms.
 __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
                                                              const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
-                                                             unsigned char *flags, u32 *long_count) {
+                                                             unsigned char *flags, u32 *long_count, u64 *tile_cnt = nullptr,
+                                                             int keep_all = 0) {
     __shared__ u64 s_key[SG_TILE + 2 * SEG_MAX];
     const u32 n = *n_ptr;
     const u64 base = (u64)blockIdx.x * SG_TILE;
@@ -600,28 +625,37 @@ __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__r
     for (int k = 0; k < SG_IPT; ++k) {
         const u32 q = SEG_MAX + (u32)k * SG_THREADS + tid;
         const u64 g = base + (u64)k * SG_THREADS + tid;
-        if (g >= n) continue;
-        const u64 key = s_key[q];
-        const u64 row = key >> bits_lo, col = key & lo_mask;
-        u32 b = 0, f = 0, before = 0;
-        // inside a row of more than 2 * SEG_MAX entries: no need to walk to find that out
-        if ((s_key[q - SEG_MAX] >> bits_lo) == row || (s_key[q + SEG_MAX] >> bits_lo) == row) b = f = (u32)SEG_MAX;
-        for (; b < (u32)SEG_MAX; ++b) {   // earlier entries of my row
-            const u64 kk = s_key[q - 1 - b];
-            if ((kk >> bits_lo) != row) break;
-            before += (kk & lo_mask) <= col;
+        u64 dst = g;
+        bool head = true, rhead = false;
+        if (g < n) {
+            const u64 key = s_key[q];
+            const u64 row = key >> bits_lo, col = key & lo_mask;
+            u32 b = 0, f = 0, before = 0, same = 0;
+            // inside a row of more than 2 * SEG_MAX entries: no need to walk to find that out
+            if ((s_key[q - SEG_MAX] >> bits_lo) == row || (s_key[q + SEG_MAX] >> bits_lo) == row) b = f = (u32)SEG_MAX;
+            for (; b < (u32)SEG_MAX; ++b) {   // earlier entries of my row
+                const u64 kk = s_key[q - 1 - b];
+                if ((kk >> bits_lo) != row) break;
+                before += (kk & lo_mask) <= col;
+                same += kk == key;
+            }
+            for (; f < (u32)SEG_MAX; ++f) {   // later entries of my row
+                const u64 kk = s_key[q + 1 + f];
+                if ((kk >> bits_lo) != row) break;
+                before += (kk & lo_mask) < col;
+            }
+            const bool is_long = b == (u32)SEG_MAX || f == (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
+            if (!is_long) {
+                dst = g - b + before;
+                head = keep_all || same == 0;   // a repeat of an earlier entry of the row is folded into it by the reduce pass
+                rhead = before == 0;            // first of its row in column order
+            }
+            keys_out[dst] = key;
+            vals_out[dst] = v[k];
+            if (flags) flags[g] = is_long;
+            n_long += is_long;
         }
-        for (; f < (u32)SEG_MAX; ++f) {   // later entries of my row
-            const u64 kk = s_key[q + 1 + f];
-            if ((kk >> bits_lo) != row) break;
-            before += (kk & lo_mask) < col;
-        }
-        const bool is_long = b == (u32)SEG_MAX || f == (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
-        const u64 dst = is_long ? g : g - b + before;
-        keys_out[dst] = key;
-        vals_out[dst] = v[k];
-        if (flags) flags[g] = is_long;
-        n_long += is_long;
+        if (tile_cnt) sg_count_heads(tile_cnt, g < n, dst, head, rhead);
     }
     n_long = __reduce_add_sync(SPB_FULL_MASK, n_long);
     if (n_long && lane_id() == 0) atomicAdd(long_count, n_long);

@@ -22,6 +22,7 @@
 #include "radix_sort9.cuh"
 #include "reduce_by_key.cuh"
 #include "reduce_segsort.cuh"
+#include "reduce_warp.cuh"
 #include "scan.cuh"
 #include "spgemm.cuh"
 #include "dense_ops.cuh"
@@ -735,18 +736,31 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     // before the counters are read.  Only when rows longer than SEG_MAX turn up (hub rows) is the reduce pass run again,
     // after those rows have been re-sorted by their full key.
     bool long_rows_fixed = false;
+    // SPB_REDUCE_WARP (default 1): the reduce pass runs a warp per 256-entry tile (k_reduce_warp).  After an in-row sort the
+    // tiles' places in the output come from the head counts that kernel produced (scanned here), not from a look-back;
+    // "0": a block per 2048-entry tile with a look-back (k_reduce_by_key), "2": a warp per tile with a look-back everywhere.
+    const int rw_mode = getenv("SPB_REDUCE_WARP") ? atoi(getenv("SPB_REDUCE_WARP")) : 1;
+    const u32 wtiles = (u32)div_up(div_up(n ? n : 1, RW_TILE), RW_WARPS) * RW_WARPS;   // warp tiles, whole blocks
     for (int attempt = 0;; ++attempt) {
         ks = ks_rows; vs = vs_rows;
         u64 *ko = (ks == kA) ? kB : kA;
         double *vo = (vs == vA) ? vB : vA;
         const u32 stiles = (u32)div_up(n, SG_TILE);
+        u64 *tile_off = nullptr;   // exclusive prefix of the reduce tiles' head counts, when the in-row sort counted them
         if (seg && !fused) {
             // rows are grouped (insertion order inside): order every row by column
             if (!long_rows_fixed) {
+                u64 *tile_cnt = nullptr;
+                if (rw_mode == 1) {
+                    CKR(ws.zeroed(&tile_cnt, (u64)wtiles + 2));
+                    CKR(ws.get(&tile_off, (u64)wtiles + 2));
+                }
+                const int keep_all = job.policy == POLICY_KEEP_ALL;
                 ++ctx->launches;
-                if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
-                else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5);
+                if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5, tile_cnt, keep_all);
+                else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5, tile_cnt, keep_all);
                 CK(cudaGetLastError());
+                if (tile_cnt) CKR((exclusive_scan<u64, u64>(ctx, ws, tile_cnt, tile_off, (u64)wtiles + 1)));
             } else {
                 // rows longer than SEG_MAX exist (h[0] kept entries, h[5] of them in such rows): their entries (left in place
                 // above) are pulled out in order, sorted by the full key with the radix passes, and put back -- the
@@ -778,12 +792,15 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         }
         t1 = tm.mark();
 
-        const u32 rtiles = (u32)div_up(n, RK_TILE);
+        // the reduce pass
+        const bool rwarp = !fused && (tile_off != nullptr || rw_mode == 2);
+        const u32 rtiles = rwarp ? wtiles / RW_WARPS : (u32)div_up(n, RK_TILE);   // blocks
         ReduceArgs ra;
         memset(&ra, 0, sizeof ra);
         ra.keys = ks; ra.vals = vs; ra.n_ptr = counters; ra.bits_lo = in.bits_lo; ra.policy = job.policy;
         ra.out_hi = out_hi; ra.out_lo = out_lo; ra.out_val = out_val; ra.out_count = counters + 2;
-        CKR(ws.zeroed(&ra.state, rtiles));
+        if (tile_off) ra.state = tile_off;
+        else CKR(ws.zeroed(&ra.state, rwarp ? (u64)wtiles : (u64)rtiles));
         CKR(ws.zeroed(&ra.ticket, 1));
         ra.long_cap = n / RK_LONG_RUN + 1;
         CKR(ws.get(&ra.long_list, 2ull * ra.long_cap));
@@ -792,7 +809,9 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
         if (fused) {
             ++ctx->launches, k_reduce_segsort<<<rtiles, RK_THREADS, sizeof(RfSmem), ctx->stream>>>(ra, counters + 5);
         } else {
-            ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
+            if (rwarp && tile_off) ++ctx->launches, k_reduce_warp<false><<<rtiles, RW_THREADS, 0, ctx->stream>>>(ra);
+            else if (rwarp) ++ctx->launches, k_reduce_warp<true><<<rtiles, RW_THREADS, 0, ctx->stream>>>(ra);
+            else ++ctx->launches, k_reduce_by_key<MODE_CONSOLIDATE><<<rtiles, RK_THREADS, 0, ctx->stream>>>(ra);
             if (job.policy == POLICY_ADD || job.policy == POLICY_REPLACE)
                 ++ctx->launches, k_long_runs<<<(u32)ctx->sm_count * 4, 256, 0, ctx->stream>>>(ra);
         }
