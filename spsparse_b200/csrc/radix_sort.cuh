@@ -603,14 +603,25 @@ __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__r
                                                              const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
                                                              unsigned char *flags, u32 *long_count, u64 *tile_cnt = nullptr,
                                                              int keep_all = 0) {
-    __shared__ u64 s_key[SG_TILE + 2 * SEG_MAX];
+    // the window's keys split into their two 32-bit halves (indices are int32): the walk compares rows and columns with
+    // 32-bit instructions -- a 64-bit shift + compare per neighbour made this kernel issue-bound
+    __shared__ u32 s_row[SG_TILE + 2 * SEG_MAX];
+    __shared__ u32 s_col[SG_TILE + 2 * SEG_MAX];
     const u32 n = *n_ptr;
     const u64 base = (u64)blockIdx.x * SG_TILE;
     if (base >= n) return;
     const u32 tid = threadIdx.x;
+    const u32 lo_mask = bits_lo >= 32 ? 0xffffffffu : (1u << bits_lo) - 1u;
     for (u32 q = tid; q < SG_TILE + 2 * SEG_MAX; q += SG_THREADS) {
         const i64 g = (i64)base + (i64)q - SEG_MAX;
-        s_key[q] = (g >= 0 && g < (i64)n) ? ld_stream_u64(keys_in + g) : ~0ull;  // ~0: belongs to no row
+        u32 row = 0xffffffffu, col = 0;   // row 0xffffffff: belongs to no row (indices are non-negative int32)
+        if (g >= 0 && g < (i64)n) {
+            const u64 key = ld_stream_u64(keys_in + g);
+            row = (u32)(key >> bits_lo);
+            col = (u32)key & lo_mask;
+        }
+        s_row[q] = row;
+        s_col[q] = col;
     }
     double v[SG_IPT];
 #pragma unroll
@@ -619,7 +630,6 @@ __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__r
         v[k] = g < n ? ld_stream_f64(vals_in + g) : 0.0;
     }
     __syncthreads();
-    const u64 lo_mask = (1ull << bits_lo) - 1;
     u32 n_long = 0;
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
@@ -628,21 +638,19 @@ __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__r
         u64 dst = g;
         bool head = true, rhead = false;
         if (g < n) {
-            const u64 key = s_key[q];
-            const u64 row = key >> bits_lo, col = key & lo_mask;
+            const u32 row = s_row[q], col = s_col[q];
             u32 b = 0, f = 0, before = 0, same = 0;
             // inside a row of more than 2 * SEG_MAX entries: no need to walk to find that out
-            if ((s_key[q - SEG_MAX] >> bits_lo) == row || (s_key[q + SEG_MAX] >> bits_lo) == row) b = f = (u32)SEG_MAX;
+            if (s_row[q - SEG_MAX] == row || s_row[q + SEG_MAX] == row) b = f = (u32)SEG_MAX;
             for (; b < (u32)SEG_MAX; ++b) {   // earlier entries of my row
-                const u64 kk = s_key[q - 1 - b];
-                if ((kk >> bits_lo) != row) break;
-                before += (kk & lo_mask) <= col;
-                same += kk == key;
+                if (s_row[q - 1 - b] != row) break;
+                const u32 c = s_col[q - 1 - b];
+                before += c <= col;
+                same += c == col;
             }
             for (; f < (u32)SEG_MAX; ++f) {   // later entries of my row
-                const u64 kk = s_key[q + 1 + f];
-                if ((kk >> bits_lo) != row) break;
-                before += (kk & lo_mask) < col;
+                if (s_row[q + 1 + f] != row) break;
+                before += s_col[q + 1 + f] < col;
             }
             const bool is_long = b == (u32)SEG_MAX || f == (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
             if (!is_long) {
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__r
                 head = keep_all || same == 0;   // a repeat of an earlier entry of the row is folded into it by the reduce pass
                 rhead = before == 0;            // first of its row in column order
             }
-            keys_out[dst] = key;
+            keys_out[dst] = ((u64)row << bits_lo) | col;
             vals_out[dst] = v[k];
             if (flags) flags[g] = is_long;
             n_long += is_long;
