@@ -4,6 +4,7 @@
 // hand-checkable small cases.
 #include <spsparse/VectorCooArray.hpp>
 #include <spsparse/multiply_sparse.hpp>
+#include <spsparse_b200/device_array.hpp>
 
 #include <cmath>
 #include <cstdio>
@@ -187,7 +188,85 @@ static void test_mult_xiters() {
     CHECK(same(cols, {0, 3, 4, 9}) && same(rows, {1, 1, 2, 6, 9}));
 }
 
+static void test_device_resident_chain() {
+    // b200::DeviceCooArray: the same operations with the array kept on the GPU between them; every step is compared with the
+    // host-container call of the same name
+    typedef b200::DeviceCooArray<2> DMat;
+    typedef b200::DeviceCooArray<1> DVec;
+    Mat a({3, 4});
+    a.add({2, 1}, 4.); a.add({0, 3}, 1.5); a.add({2, 1}, -1.); a.add({1, 0}, 0.); a.add({0, 0}, 2.); a.add({2, 3}, 7.);
+    DMat da(a);
+    CHECK(da.size() == 6 && da.shape()[0] == 3 && da.shape()[1] == 4 && da.sort_order()[0] == -1);
+    // copy / transpose (algorithm.hpp:30-57): entries keep their order
+    {
+        Mat want({4, 3}), got({4, 3});
+        transpose(want, a, {1, 0});
+        da.transpose({1, 0}).download(got);
+        CHECK(col(got, 0) == col(want, 0) && col(got, 1) == col(want, 1) && got.val_data() == want.val_data());
+        Mat cp({3, 4});
+        da.copy().download(cp);
+        CHECK(col(cp, 0) == col(a, 0) && col(cp, 1) == col(a, 1) && cp.val_data() == a.val_data());
+    }
+    // consolidate on the device == consolidate through the host container; the flag travels
+    DMat dc = da.consolidate(ROW_MAJOR);
+    {
+        Mat want(a.shape), got(a.shape);
+        consolidate(want, a, ROW_MAJOR);
+        dc.download(got);
+        CHECK(dc.sort_order()[0] == 0 && dc.sort_order()[1] == 1);
+        CHECK(col(got, 0) == col(want, 0) && col(got, 1) == col(want, 1) && got.val_data() == want.val_data());
+        CHECK(same(got.val_data(), {2., 1.5, 3., 7.}));                       // the zero dropped, the duplicate summed
+        CHECK(same(dc.dim_beginnings(), {size_t(0), size_t(2), size_t(4)}));  // rows 0 and 2, and the sentinel
+    }
+    // to_dense with the three duplicate policies of DenseAccum (accum.hpp:110-140), from_dense = to_sparse
+    {
+        std::vector<double> add = da.to_dense(), repl = da.to_dense(DuplicatePolicy::REPLACE);
+        CHECK(add.size() == 12 && add[2 * 4 + 1] == 3. && repl[2 * 4 + 1] == -1. && add[0] == 2. && add[3] == 1.5 && add[11] == 7. && add[4] == 0.);
+        DMat back = DMat::from_dense({3, 4}, add.data());
+        Mat got({3, 4});
+        back.download(got);
+        CHECK(same(col(got, 0), {0, 0, 2, 2}) && same(col(got, 1), {0, 3, 1, 3}) && same(got.val_data(), {2., 1.5, 3., 7.}));
+    }
+    // multiply, matrix x matrix and matrix x vector, against the host-container calls
+    {
+        Mat b({4, 2});
+        b.add({3, 1}, 2.); b.add({0, 0}, 3.); b.add({1, 1}, 5.); b.add({3, 0}, -1.);
+        Vec w({4}), v({4});
+        w.add({0}, 2.); w.add({1}, 1.); w.add({3}, 0.5);
+        v.add({1}, 10.); v.add({3}, 1.);
+        DMat db(b);
+        DVec dw(w), dv(v);
+        Mat want, got;
+        multiply(want, 2., (Vec *)0, a, '.', &w, b, '.', (Vec *)0);
+        got.set_shape(want.shape);
+        b200::multiply(2., nullptr, da, '.', &dw, db, '.', nullptr).download(got);
+        CHECK(got.size() == want.size() && col(got, 0) == col(want, 0) && col(got, 1) == col(want, 1) && got.val_data() == want.val_data());
+        Vec wantv, gotv;
+        multiply(wantv, 1., (Vec *)0, a, '.', (Vec *)0, v);
+        gotv.set_shape(wantv.shape);
+        b200::multiply(1., nullptr, da, '.', nullptr, dv).download(gotv);
+        CHECK(gotv.size() == wantv.size() && gotv.index_data(0) == wantv.index_data(0) && gotv.val_data() == wantv.val_data());
+        // A^T * A through a device transpose + consolidate equals the 'T' flag
+        Mat t1, t2;
+        multiply(t1, 1., (Vec *)0, a, 'T', (Vec *)0, a, '.', (Vec *)0);
+        t2.set_shape(t1.shape);
+        b200::multiply(1., nullptr, da.transpose({1, 0}).consolidate(ROW_MAJOR), '.', nullptr, dc, '.', nullptr).download(t2);
+        CHECK(t2.size() == t1.size() && col(t2, 0) == col(t1, 0) && col(t2, 1) == col(t1, 1) && t2.val_data() == t1.val_data());
+    }
+    // moves, empties, errors
+    {
+        DMat moved(std::move(dc));
+        CHECK(dc.handle() == nullptr && moved.size() == 4);
+        DMat empty;
+        CHECK(empty.size() == 0 && empty.dim_beginnings().empty());
+        bool threw = false;
+        try { (void)da.dim_beginnings(); } catch (spsparse::Exception const &) { threw = true; }   // not flagged sorted
+        CHECK(threw);
+    }
+}
+
 int main() {
+    test_device_resident_chain();
     test_mult_xiters();
     test_consolidate();
     test_permutation_and_rows();
