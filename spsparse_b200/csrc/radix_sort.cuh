@@ -450,20 +450,9 @@ constexpr int SEG_MAX = 64;
 // their row) and row heads (first entry of a row) end up in every 256-entry tile of the SORTED array.  The in-row sort knows
 // both for every entry it places; with the counts scanned, a reduce tile knows its place in the output without waiting for
 // its predecessors (no look-back chain).  The 32 entries a warp places in one step lie within 32 + 2 * (SEG_MAX - 1)
-// positions, i.e. in at most two consecutive tiles.  tile_cnt: head count | row-head count << 31, zeroed by the host.
+// positions; a warp of these kernels takes 256 consecutive entries (one tile), so its destinations lie in that tile and its
+// two neighbours and the counts are summed in registers.  tile_cnt: head count | row-head count << 31, zeroed by the host.
 constexpr int SG_CNT_SHIFT = 8;   // log2 of the reduce pass's tile (RW_TILE)
-__device__ __forceinline__ void sg_count_heads(u64 *tile_cnt, bool valid, u64 dst, bool head, bool rhead) {
-    const u32 td = valid ? (u32)(dst >> SG_CNT_SHIFT) : 0xffffffffu;
-    const u32 t0 = __reduce_min_sync(SPB_FULL_MASK, td);
-    if (t0 == 0xffffffffu) return;
-#pragma unroll
-    for (u32 c = 0; c < 2; ++c) {
-        const u32 hb = __ballot_sync(SPB_FULL_MASK, valid && head && td == t0 + c);
-        const u32 rb = __ballot_sync(SPB_FULL_MASK, valid && rhead && td == t0 + c);
-        if (hb && lane_id() == 0) atomicAdd((ull *)&tile_cnt[t0 + c], (ull)__popc(hb) | ((ull)__popc(rb) << 31));
-    }
-}
-
 __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
                                                                 const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
                                                                 unsigned char *flags, u32 *long_count, u64 *tile_cnt = nullptr,
@@ -489,7 +478,7 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__res
     // the values are only moved: pull their lines into L2 now, load them when the destinations are known
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
-        const u64 g = base + (u64)k * SG_THREADS + tid;
+        const u64 g = base + (u64)warp * 256 + (u64)k * 32 + lane;
         if (g < n && (lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vals_in + g));
     }
     __syncthreads();
@@ -548,15 +537,19 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__res
     }
     __syncthreads();
     // ---- my entries: position inside the row = entries that must precede it --------------------------------------------
+    // (a warp takes 256 CONSECUTIVE entries, 32 per step: all its destinations lie in three tiles of the reduce pass, so the
+    // head counts are kept in registers and added once per warp)
     u32 n_long = 0;
     i32 shift_by[SG_IPT];  // destination - source position (inside a row: small); INT32_MIN: entry of a long row
+    u32 cnt_at = 0, cnt_before = 0, cnt_after = 0;   // run heads | row heads << 16, by destination tile: mine, the one before, the one after
+    const u64 wbase = base + (u64)warp * 256;
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
-        const u32 q = SEG_MAX + (u32)k * SG_THREADS + tid;
-        const u64 g = base + (u64)k * SG_THREADS + tid;
+        const u32 q = SEG_MAX + warp * 256 + (u32)k * 32 + lane;
+        const u64 g = wbase + (u64)k * 32 + lane;
         shift_by[k] = 0;
-        bool head = true, rhead = false;
         if (g < n) {
+            bool head = true, rhead = false;
             const u32 grp = q >> 5, l = q & 31, hb = s_hb[grp];
             const u32 below = hb & (0xffffffffu >> (31 - l));
             const u32 st = below ? (grp << 5) + 31 - __clz(below) : s_last[grp];
@@ -574,21 +567,35 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__res
             }
             if (flags) flags[g] = is_long;
             n_long += is_long;
+            const u64 dst = (u64)((i64)g + shift_by[k]);
+            const u32 inc = (head ? 1u : 0u) | (rhead ? 0x10000u : 0u);
+            if (dst < wbase) cnt_before += inc;
+            else if (dst >= wbase + 256) cnt_after += inc;
+            else cnt_at += inc;
         }
-        if (tile_cnt) sg_count_heads(tile_cnt, g < n, (u64)((i64)g + shift_by[k]), head, rhead);
+    }
+    if (tile_cnt) {
+        const u32 a0 = __reduce_add_sync(SPB_FULL_MASK, cnt_at), a1 = __reduce_add_sync(SPB_FULL_MASK, cnt_before),
+                  a2 = __reduce_add_sync(SPB_FULL_MASK, cnt_after);
+        if (lane == 0) {
+            u64 *t = tile_cnt + (wbase >> SG_CNT_SHIFT);
+            if (a0) atomicAdd((ull *)t, (ull)(a0 & 0xffffu) | ((ull)(a0 >> 16) << 31));
+            if (a1) atomicAdd((ull *)(t - 1), (ull)(a1 & 0xffffu) | ((ull)(a1 >> 16) << 31));
+            if (a2) atomicAdd((ull *)(t + 1), (ull)(a2 & 0xffffu) | ((ull)(a2 >> 16) << 31));
+        }
     }
     double v[SG_IPT];
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
-        const u64 g = base + (u64)k * SG_THREADS + tid;
+        const u64 g = wbase + (u64)k * 32 + lane;
         v[k] = g < n ? ld_stream_f64(vals_in + g) : 0.0;
     }
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
-        const u64 g = base + (u64)k * SG_THREADS + tid;
+        const u64 g = wbase + (u64)k * 32 + lane;
         if (g < n) {
             const u64 dst = (u64)((i64)g + shift_by[k]);
-            keys_out[dst] = s_key[SEG_MAX + k * SG_THREADS + tid];
+            keys_out[dst] = s_key[SEG_MAX + warp * 256 + k * 32 + lane];
             vals_out[dst] = v[k];
         }
     }
@@ -596,33 +603,32 @@ __global__ void __launch_bounds__(SG_THREADS, 5) k_segment_sort(const u64 *__res
     if (n_long && lane == 0) atomicAdd(long_count, n_long);
 }
 
-// The same for rows of a handful of entries (banded, regridding matrices), without the row table's extra phases: one barrier.
-// While the window is loaded, every group of 32 consecutive window entries leaves one word of row-start bits (a ballot of
-// "my row differs from my predecessor's"); an entry then finds the bounds of its row with a few bit operations on the words
-// around it and compares columns with the members of its row only.  (The first version walked outwards from the entry,
-// comparing 64-bit keys: ~20 instructions per neighbour visited, two visits per row wasted on finding its ends -- the kernel
-// was issue-bound, 82 % of the issue slots.)  Keys are split into their 32-bit halves (indices are int32).
-// A warp takes 256 CONSECUTIVE entries, 32 per step, so all its destinations lie in three tiles of the reduce pass and
-// the head counts (sg_count_heads' job in the row-table kernel) are kept in registers and added once per warp.
-// Measured on the 5-entries-per-row config 5 block: 3.3 ms against 5.0 ms for the row-table kernel; at config 2's 12 entries per
-// row the walk costs 4.5 ms against 2.5 ms.
-constexpr int SGW_GROUPS = (SG_TILE + 2 * SEG_MAX) / 32;   // 68 words of row-start bits
-static_assert(SG_TILE % 256 == 0 && SEG_MAX == 64 && (1 << SG_CNT_SHIFT) == 256, "k_segment_sort_walk: a warp's 256 entries are one reduce tile");
-
-__global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
+// The same for rows of a handful of entries (banded, regridding matrices): every entry simply walks its neighbours in
+// the window -- no row table, one barrier.  Measured on the 5-entries-per-row config 5 block: 3.3 ms against 5.0 ms for the
+// kernel above; at config 2's 12 entries per row the walk costs 4.5 ms against 2.5 ms.
+// (Tried in round 2 and dropped: row bounds from per-group words of row-start bits instead of walking to the row's ends --
+// bit-identical, but 23.3 against 21.5 ms per consolidate of the config 5 block, with or without all window loads in flight.)
+// A warp takes 256 CONSECUTIVE entries, 32 per step: all its destinations lie in three tiles of the reduce pass, so the head
+// counts for that pass are kept in registers and added once per warp.
+static_assert(SG_TILE % 256 == 0 && (1 << SG_CNT_SHIFT) == 256, "a warp's 256 consecutive entries are one tile of the reduce pass");
+#ifndef SGW_UNROLL_N
+#define SGW_UNROLL_N 8
+#endif
+constexpr int SGW_UNROLL = SGW_UNROLL_N;
+__global__ void __launch_bounds__(SG_THREADS, 6) k_segment_sort_walk(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
                                                              const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
                                                              unsigned char *flags, u32 *long_count, u64 *tile_cnt = nullptr,
                                                              int keep_all = 0) {
+    // the window's keys split into their two 32-bit halves (indices are int32): the walk compares rows and columns with
+    // 32-bit instructions -- a 64-bit shift + compare per neighbour made this kernel issue-bound
     __shared__ u32 s_row[SG_TILE + 2 * SEG_MAX];
     __shared__ u32 s_col[SG_TILE + 2 * SEG_MAX];
-    __shared__ u32 s_hb[SGW_GROUPS];
     const u32 n = *n_ptr;
     const u64 base = (u64)blockIdx.x * SG_TILE;
     if (base >= n) return;
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tid = threadIdx.x;
     const u32 lo_mask = bits_lo >= 32 ? 0xffffffffu : (1u << bits_lo) - 1u;
-    // ---- the window: rows, columns, row-start bits -------------------------------------------------------------------------
-    for (u32 q = tid; q < SG_TILE + 2 * SEG_MAX; q += SG_THREADS) {   // (whole warps: the window is a multiple of 32)
+    for (u32 q = tid; q < SG_TILE + 2 * SEG_MAX; q += SG_THREADS) {
         const i64 g = (i64)base + (i64)q - SEG_MAX;
         u32 row = 0xffffffffu, col = 0;   // row 0xffffffff: belongs to no row (indices are non-negative int32)
         if (g >= 0 && g < (i64)n) {
@@ -632,60 +638,53 @@ __global__ void __launch_bounds__(SG_THREADS) k_segment_sort_walk(const u64 *__r
         }
         s_row[q] = row;
         s_col[q] = col;
-        u32 prev = __shfl_up_sync(SPB_FULL_MASK, row, 1);
-        if (lane == 0) prev = (g >= 1 && g - 1 < (i64)n) ? (u32)(keys_in[g - 1] >> bits_lo) : 0xffffffffu;
-        const u32 hb = __ballot_sync(SPB_FULL_MASK, row != prev || q == 0);
-        if (lane == 0) s_hb[q >> 5] = hb;
     }
+    // a warp takes 256 CONSECUTIVE entries, 32 per step: all its destinations lie in three tiles of the reduce pass, so the
+    // head counts are kept in registers and added once per warp
+    const u32 lane = tid & 31, warp = tid >> 5;
+    const u64 wbase = base + (u64)warp * 256;   // first entry of the warp = first entry of "my" tile
     double v[SG_IPT];
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
-        const u64 g = base + (u64)warp * 256 + (u64)k * 32 + lane;
+        const u64 g = wbase + (u64)k * 32 + lane;
         v[k] = g < n ? ld_stream_f64(vals_in + g) : 0.0;
     }
     __syncthreads();
     u32 n_long = 0;
-    // run heads | row heads << 16 of my entries, by the tile of the reduce pass they land in: mine, the one before, the one after
-    u32 cnt_at = 0, cnt_before = 0, cnt_after = 0;
-    const u64 wbase = base + (u64)warp * 256;   // first entry of the warp = first entry of "my" tile
+    u32 cnt_at = 0, cnt_before = 0, cnt_after = 0;   // run heads | row heads << 16, by destination tile: mine, the one before, the one after
 #pragma unroll
     for (int k = 0; k < SG_IPT; ++k) {
         const u32 q = SEG_MAX + warp * 256 + (u32)k * 32 + lane;
         const u64 g = wbase + (u64)k * 32 + lane;
+        u64 dst = g;
+        bool head = true, rhead = false;
         if (g < n) {
-            const u32 col = s_col[q];
-            const u32 G = q >> 5, pbit = q & 31;
-            // row start: the nearest start bit at or below me; next row: the nearest start bit above me (three words each way
-            // cover the 64 entries either side that decide whether the row is long)
-            u32 st = 0xffffffffu, nx = 0xffffffffu;
-            {
-                u32 w = s_hb[G] & (0xffffffffu >> (31 - pbit));
-                if (w) st = (G << 5) + 31 - __clz(w);
-                else if ((w = s_hb[G - 1]) != 0) st = ((G - 1) << 5) + 31 - __clz(w);
-                else if ((w = s_hb[G - 2]) != 0) st = ((G - 2) << 5) + 31 - __clz(w);
-                w = pbit < 31 ? s_hb[G] & (0xffffffffu << (pbit + 1)) : 0u;
-                if (w) nx = (G << 5) + __ffs(w) - 1;
-                else if ((w = s_hb[G + 1]) != 0) nx = ((G + 1) << 5) + __ffs(w) - 1;
-                else if ((w = s_hb[G + 2]) != 0) nx = ((G + 2) << 5) + __ffs(w) - 1;
-            }
-            const u32 b = st == 0xffffffffu ? (u32)SEG_MAX : q - st;          // earlier entries of my row
-            const u32 f = nx == 0xffffffffu ? (u32)SEG_MAX : nx - 1 - q;      // later entries
-            const bool is_long = b >= (u32)SEG_MAX || f >= (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
-            u64 dst = g;
-            bool head = true, rhead = false;
-            if (!is_long) {
-                u32 before = 0, same = 0;
-                for (u32 j = st; j < q; ++j) {       // earlier entries: they precede me unless their column is larger (stable)
-                    const u32 c = s_col[j];
+            const u32 row = s_row[q], col = s_col[q];
+            u32 b = 0, f = 0, before = 0, same = 0;
+            // inside a row of more than 2 * SEG_MAX entries: no need to walk to find that out
+            if (s_row[q - SEG_MAX] == row || s_row[q + SEG_MAX] == row) b = f = (u32)SEG_MAX;
+            else {
+                // (unrolled: the neighbours' addresses become immediates, no loop counter in the way -- rows are a handful long)
+#pragma unroll SGW_UNROLL
+                for (b = 0; b < (u32)SEG_MAX; ++b) {   // earlier entries of my row
+                    if (s_row[q - 1 - b] != row) break;
+                    const u32 c = s_col[q - 1 - b];
                     before += c <= col;
                     same += c == col;
                 }
-                for (u32 j = q + 1; j < nx; ++j) before += s_col[j] < col;   // later entries
+#pragma unroll SGW_UNROLL
+                for (f = 0; f < (u32)SEG_MAX; ++f) {   // later entries of my row
+                    if (s_row[q + 1 + f] != row) break;
+                    before += s_col[q + 1 + f] < col;
+                }
+            }
+            const bool is_long = b == (u32)SEG_MAX || f == (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
+            if (!is_long) {
                 dst = g - b + before;
                 head = keep_all || same == 0;   // a repeat of an earlier entry of the row is folded into it by the reduce pass
                 rhead = before == 0;            // first of its row in column order
             }
-            keys_out[dst] = ((u64)s_row[q] << bits_lo) | col;
+            keys_out[dst] = ((u64)row << bits_lo) | col;
             vals_out[dst] = v[k];
             if (flags) flags[g] = is_long;
             n_long += is_long;

@@ -14,5 +14,8 @@ run new 300 python tools/env_ab_probe.py SPB_REDUCE_WARP 1 --no-config2
 SPB_LIB=$L/libspb_prev.so run prev2 300 python tools/env_ab_probe.py SPB_REDUCE_WARP 1 --no-config2
 run new2 300 python tools/env_ab_probe.py SPB_REDUCE_WARP 1 --no-config2
 cat "$out/prev.out" "$out/new.out" "$out/prev2.out" "$out/new2.out"
-run t_full 900 python -m pytest tests/test_gpu_full_size.py -x -q -p no:cacheprovider -k "config2 or config5 or config3"
+run t_full 900 python -m pytest tests/test_gpu_full_size.py -x -q -p no:cacheprovider -k "config2 or config5"
 tail -n 3 "$out/t_full.out"
+SPB_LIB=$L/libspb_prev.so run prev_c2 300 python tools/profile_target.py consolidate 1 4
+run new_c2 300 python tools/profile_target.py consolidate 1 4
+cat "$out/prev_c2.out" "$out/new_c2.out"
