@@ -566,7 +566,12 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "note": ("9-bit digits: three passes over the 27-bit row part instead of four 8-bit ones (a 9-bit pass costs 10 % more "
                                   "than an 8-bit one, three of them less than four); tiles loaded by cp.async.bulk + mbarrier "
-                                  "(profiles/r02_notes.md)") if sa.digit_bits == 9 else None},
+                                  "(profiles/r02_notes.md)") if sa.digit_bits == 9 else None,
+                         # the other kernels of a consolidate with a time of their own in spb_consolidate_stats
+                         "reduce_pass": kernel_roofline("k_reduce_warp<false> (duplicate-reduce, a warp per 256-entry tile, tile offsets from the in-row sort's head counts: "
+                                                        "16 B per entry read, 16 B per output written)" if os.environ.get("SPB_REDUCE_WARP", "1") == "1" else
+                                                        "k_reduce_by_key / k_reduce_warp<true> (SPB_REDUCE_WARP set: look-back variants)",
+                                                        "k_reduce_warp", 16.0 * sa.n_kept + 16.0 * sa.n_out, sa.ms_reduce, hbm, sa.n_kept)},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(l1 - l0),
@@ -699,6 +704,8 @@ def also_configs(ctx, sp, torch, stream, args, hbm):
         "roofline": kernel_roofline(f"k_radix_pass{'9' if st.digit_bits == 9 else ''}<false, BULK> ({st.passes - 1} of its {st.passes} scatter passes; pass 0 reads the caller's arrays)",
                                     "k_radix_pass9" if st.digit_bits == 9 else "k_radix_pass", 32.0 * st.n_kept,
                                     float(np.mean([s.ms_pass for s in sts])), hbm, st.n_kept),
+        "roofline_reduce": kernel_roofline("k_reduce_warp<false> (16 B per entry read, 16 B per output written)", "k_reduce_warp",
+                                           16.0 * st.n_kept + 16.0 * st.n_out, float(np.mean([s.ms_reduce for s in sts])), hbm, st.n_kept),
     }
     A.free()
     # ---- config 3: regridding SpGEMM  C = A diag(s) A^T, A = 1e7 x 1e6 ---------------------------------

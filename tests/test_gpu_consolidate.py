@@ -265,8 +265,9 @@ def test_medium_scale_against_oracle(ctx, orc):
     A.free()
 
 
-@pytest.mark.parametrize("mode,walk,fused", [("1", "1", "0"), ("1", "0", "0"), ("0", "0", "0"), ("1", "1", "1")])
-def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused):
+@pytest.mark.parametrize("mode,walk,fused,rwarp", [("1", "1", "0", None), ("1", "0", "0", None), ("0", "0", "0", None), ("1", "1", "1", None),
+                                                   ("1", "1", "0", "0"), ("1", "0", "0", "2"), ("0", "0", "0", "2")])
+def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused, rwarp):
     """The sort's second organisation -- radix passes over the row part of the key only, then every row ordered by
     column (k_segment_sort), rows longer than 64 entries re-sorted by their full key -- forced on (and off) for shapes
     with a wide column part: short rows, rows around the 64-entry limit, hub rows of thousands of entries next to
@@ -278,6 +279,10 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused)
     # fused = "1": the in-row sort runs inside the reduce pass (k_reduce_segsort); the cases with hub rows make it
     # give up and fall back to the separate kernels
     monkeypatch.setenv("SPB_FUSED_REDUCE", fused)
+    # reduce pass: default = a warp per tile, tile offsets from the head counts of the in-row sort (no look-back) where one ran;
+    # "0" = block per tile with look-back, "2" = warp per tile with look-back (also after full-key sorts)
+    if rwarp is not None:
+        monkeypatch.setenv("SPB_REDUCE_WARP", rwarp)
     rng = np.random.default_rng(11)
     cases = []
     for s, (shape, n, hubs) in enumerate([((300, 1 << 20), 5000, 0), ((3, 1 << 20), 4000, 0), ((2000, 1 << 18), 60000, 3),

@@ -18,8 +18,24 @@ def main():
                 R = sp.consolidate(ctx, A, so)
                 R.free()
             A.free()
+    # no long rows: the reduce pass keeps the result it formed from the in-row sort's head counts (no look-back); "2": the
+    # warp-per-tile kernel with its look-back, also after a full-key sort
+    for rw, seg in (("1", "1"), ("2", "1"), ("2", "0"), ("0", "1")):
+        os.environ["SPB_REDUCE_WARP"], os.environ["SPB_SEGMENT_SORT"] = rw, seg
+        with sp.Context(0) as ctx:
+            n = 30011
+            i, k = rng.integers(0, 9000, n), rng.integers(0, 40, n)      # short rows, many duplicates
+            A = sp.CooArray.from_host(ctx, (9000, 1 << 20), [i, k], rng.standard_normal(n))
+            for so, pol in (((0, 1), 1), ((1, 0), 2), ((0, 1), 0)):
+                R = sp.consolidate(ctx, A, so, pol)
+                R.free()
+            A.free()
+    os.environ.pop("SPB_REDUCE_WARP")
     os.environ.pop("SPB_SEGMENT_SORT"); os.environ.pop("SPB_SEGMENT_WALK")
     for env in ({}, {"SPB_MERGE_MAX_PRODUCTS": "0", "SPB_HASH_MIN_PRODUCTS": "0", "SPB_HASH_WIN_COLS": "64", "SPB_HASH_ITEM_CAP": "5"},
+                {"SPB_MERGE_MAX_PRODUCTS": "0", "SPB_HASH_MIN_PRODUCTS": "0"},                                  # one window: sparse bitmap walk
+                {"SPB_MERGE_MAX_PRODUCTS": "0", "SPB_HASH_MIN_PRODUCTS": "0", "SPB_HASH_SPARSE_WALK": "0"},      # ... and the group walk
+                {"SPB_MERGE_MAX_PRODUCTS": "0", "SPB_HASH_MIN_PRODUCTS": "0", "SPB_HASH_WIN_COLS": "64", "SPB_HASH_SMALL": "1"},
                 {"SPB_HASH_MIN_PRODUCTS": "off", "SPB_MERGE_MAX_PRODUCTS": "0", "SPB_ESC_CHUNK": "500"}):
         os.environ.update(env)
         with sp.Context(0) as ctx:
