@@ -708,6 +708,130 @@ __global__ void __launch_bounds__(SG_THREADS, 6) k_segment_sort_walk(const u64 *
     if (n_long && lane == 0) atomicAdd(long_count, n_long);
 }
 
+// The walk for rows of AT MOST SGS_ROW entries (stencil / banded / regridding matrices: 4-5 per row), in registers: a warp step
+// looks at 32 consecutive window entries, one per lane; an entry's row mates are at most SGS_ROW - 1 lanes away, so every
+// comparison is a shuffle -- no loop, no branch, no shared-memory traffic beyond the entry itself: 2 * (SGS_ROW - 1) row and
+// column shuffles per step instead of ~10 divergent loop trips of ~12 instructions.  The first and last SGS_ROW - 1 lanes of a
+// step only lend their entries (their own row mates may lie outside the 32), so a step places 32 - 2 * (SGS_ROW - 1) entries;
+// a warp takes 256 consecutive entries in 11 such steps.  Whether a step qualifies is decided from one ballot of row-start
+// flags: no SGS_ROW consecutive non-starts among the 32 lanes and the entry after them; otherwise (longer rows nearby) that step
+// walks through shared memory exactly as k_segment_sort_walk does.  Same outputs, same by-products (long-row count, flags,
+// head counts per tile of the reduce pass).
+// MEASURED (round 2): bit-identical, but 22.4 ms per consolidate of the config 5 block against 21.1 ms for k_segment_sort_walk --
+// an SM has ONE shuffle unit (a warp-wide SHFL per cycle, a quarter of the ALU rate), and 16 shuffles per 24 placed entries
+// cost more than the loop trips they replace.  Kept behind SPB_SEGMENT_WALK=2 with its parity cases.
+constexpr int SGS_ROW = 5;
+constexpr int SGS_H = SGS_ROW - 1;            // lanes either side that only lend their entries
+constexpr int SGS_STEP = 32 - 2 * SGS_H;      // entries placed per step
+constexpr int SGS_STEPS = (256 + SGS_STEP - 1) / SGS_STEP;
+__global__ void __launch_bounds__(SG_THREADS, 6) k_segment_sort_shfl(const u64 *__restrict__ keys_in, const double *__restrict__ vals_in,
+                                                                    const u32 *n_ptr, int bits_lo, u64 *keys_out, double *vals_out,
+                                                                    unsigned char *flags, u32 *long_count, u64 *tile_cnt = nullptr,
+                                                                    int keep_all = 0) {
+    __shared__ u32 s_row[SG_TILE + 2 * SEG_MAX];
+    __shared__ u32 s_col[SG_TILE + 2 * SEG_MAX];
+    __shared__ double s_val[SG_TILE];
+    const u32 n = *n_ptr;
+    const u64 base = (u64)blockIdx.x * SG_TILE;
+    if (base >= n) return;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lo_mask = bits_lo >= 32 ? 0xffffffffu : (1u << bits_lo) - 1u;
+    for (u32 q = tid; q < SG_TILE + 2 * SEG_MAX; q += SG_THREADS) {
+        const i64 g = (i64)base + (i64)q - SEG_MAX;
+        u32 row = 0xffffffffu, col = 0;   // row 0xffffffff: belongs to no row (indices are non-negative int32)
+        if (g >= 0 && g < (i64)n) {
+            const u64 key = ld_stream_u64(keys_in + g);
+            row = (u32)(key >> bits_lo);
+            col = (u32)key & lo_mask;
+        }
+        s_row[q] = row;
+        s_col[q] = col;
+    }
+#pragma unroll
+    for (int k = 0; k < SG_IPT; ++k) {
+        const u32 e = (u32)k * SG_THREADS + tid;
+        const u64 g = base + e;
+        s_val[e] = g < n ? ld_stream_f64(vals_in + g) : 0.0;
+    }
+    __syncthreads();
+    const u64 wbase = base + (u64)warp * 256;   // first entry of the warp = first entry of "my" tile of the reduce pass
+    u32 n_long = 0;
+    u32 cnt_at = 0, cnt_before = 0, cnt_after = 0;   // run heads | row heads << 16, by destination tile: mine, the one before, the one after
+    for (int t = 0; t < SGS_STEPS; ++t) {
+        const i32 e = t * SGS_STEP + (i32)lane - SGS_H;          // my entry, relative to the warp's first (halo lanes: outside [0, 256))
+        const u32 q = (u32)(SEG_MAX + (i32)warp * 256 + e);      // its window position (>= SEG_MAX - SGS_H)
+        const u64 g = wbase + (u64)(i64)e;
+        const bool mine = lane >= (u32)SGS_H && lane < (u32)(32 - SGS_H) && e < 256 && g < n;
+        const u32 row = s_row[q], col = s_col[q];
+        // row starts among my 32 entries and the one after them
+        const u32 hb = __ballot_sync(SPB_FULL_MASK, s_row[q - 1] != row);
+        const u32 tail = __shfl_sync(SPB_FULL_MASK, (u32)(s_row[q + 1] != row), 31);
+        const u64 z = ~((u64)hb | ((u64)tail << 32)) & 0x1ffffffffull;   // non-starts
+        u64 run = z;
+#pragma unroll
+        for (int d = 1; d < SGS_ROW; ++d) run &= z >> d;
+        u32 b = 0, f = 0, before = 0, same = 0;
+        if (run == 0) {
+            // every row that touches a placing lane lies inside the 32: shuffles
+#pragma unroll
+            for (int d = 1; d < SGS_ROW; ++d) {
+                const u32 ru = __shfl_up_sync(SPB_FULL_MASK, row, d), cu = __shfl_up_sync(SPB_FULL_MASK, col, d);
+                const u32 rd = __shfl_down_sync(SPB_FULL_MASK, row, d), cd = __shfl_down_sync(SPB_FULL_MASK, col, d);
+                const bool up = lane >= (u32)d && ru == row, dn = lane + d < 32u && rd == row;
+                b += up;
+                before += (up && cu <= col) + (dn && cd < col);
+                same += up && cu == col;
+                f += dn;
+            }
+        } else if (mine) {
+            // a longer row nearby: walk through shared memory (k_segment_sort_walk)
+            if (s_row[q - SEG_MAX] == row || s_row[q + SEG_MAX] == row) b = f = (u32)SEG_MAX;
+            else {
+                for (b = 0; b < (u32)SEG_MAX; ++b) {
+                    if (s_row[q - 1 - b] != row) break;
+                    const u32 c = s_col[q - 1 - b];
+                    before += c <= col;
+                    same += c == col;
+                }
+                for (f = 0; f < (u32)SEG_MAX; ++f) {
+                    if (s_row[q + 1 + f] != row) break;
+                    before += s_col[q + 1 + f] < col;
+                }
+            }
+        }
+        if (mine) {
+            const bool is_long = b == (u32)SEG_MAX || f == (u32)SEG_MAX || b + f + 1 > (u32)SEG_MAX;
+            u64 dst = g;
+            bool head = true, rhead = false;
+            if (!is_long) {
+                dst = g - b + before;
+                head = keep_all || same == 0;   // a repeat of an earlier entry of the row is folded into it by the reduce pass
+                rhead = before == 0;            // first of its row in column order
+            }
+            keys_out[dst] = ((u64)row << bits_lo) | col;
+            vals_out[dst] = s_val[warp * 256 + (u32)e];
+            if (flags) flags[g] = is_long;
+            n_long += is_long;
+            const u32 inc = (head ? 1u : 0u) | (rhead ? 0x10000u : 0u);
+            if (dst < wbase) cnt_before += inc;
+            else if (dst >= wbase + 256) cnt_after += inc;
+            else cnt_at += inc;
+        }
+    }
+    if (tile_cnt) {
+        const u32 a0 = __reduce_add_sync(SPB_FULL_MASK, cnt_at), a1 = __reduce_add_sync(SPB_FULL_MASK, cnt_before),
+                  a2 = __reduce_add_sync(SPB_FULL_MASK, cnt_after);
+        if (lane == 0) {
+            u64 *t = tile_cnt + (wbase >> SG_CNT_SHIFT);
+            if (a0) atomicAdd((ull *)t, (ull)(a0 & 0xffffu) | ((ull)(a0 >> 16) << 31));
+            if (a1) atomicAdd((ull *)(t - 1), (ull)(a1 & 0xffffu) | ((ull)(a1 >> 16) << 31));
+            if (a2) atomicAdd((ull *)(t + 1), (ull)(a2 & 0xffffu) | ((ull)(a2 >> 16) << 31));
+        }
+    }
+    n_long = __reduce_add_sync(SPB_FULL_MASK, n_long);
+    if (n_long && lane == 0) atomicAdd(long_count, n_long);
+}
+
 // entries of the long rows: out of the array (in order) and back
 __global__ void k_gather_flagged(const u64 *__restrict__ keys, const double *__restrict__ vals, const unsigned char *__restrict__ flags,
                                  const u64 *__restrict__ slot, u32 n, u64 *k_out, double *v_out) {

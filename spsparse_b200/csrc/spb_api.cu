@@ -666,6 +666,10 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
     const bool seg_short = (double)n <= 16.0 * (double)in.extent_hi && n >= (1u << 23);
     const char *walk_env = getenv("SPB_SEGMENT_WALK");
     const bool seg_walk = walk_env ? atoi(walk_env) != 0 : (double)n <= 6.0 * (double)in.extent_hi;  // very short rows: neighbour walk
+    // SPB_SEGMENT_WALK=2: the walk on shuffles for rows of at most 5 entries (k_segment_sort_shfl) -- bit-identical, measured
+    // slower than the shared-memory walk (22.4 against 21.1 ms on the config 5 block: 16 shuffles per 24 entries keep the SM's
+    // one shuffle unit busy), so not the default
+    const bool seg_shfl = walk_env && atoi(walk_env) == 2;
     const bool seg = in.bits_lo > 0 && passes_full - passes_row >= 2 &&
                      (seg_env ? atoi(seg_env) != 0 : seg_short);
     // 9-bit digits (k_radix_pass9) when they cover the same bits in fewer passes -- a 27-bit row part takes three
@@ -757,7 +761,8 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
                 }
                 const int keep_all = job.policy == POLICY_KEEP_ALL;
                 ++ctx->launches;
-                if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5, tile_cnt, keep_all);
+                if (seg_shfl) k_segment_sort_shfl<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5, tile_cnt, keep_all);
+                else if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5, tile_cnt, keep_all);
                 else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, nullptr, counters + 5, tile_cnt, keep_all);
                 CK(cudaGetLastError());
                 if (tile_cnt) CKR((exclusive_scan<u64, u64>(ctx, ws, tile_cnt, tile_off, (u64)wtiles + 1)));
@@ -774,7 +779,8 @@ static int sort_reduce(spb_ctx *ctx, const SortJob &job, i32 *out_hi, i32 *out_l
                 CKR(ws.get(&slot, (u64)n_kept + 1));
                 CK(cudaMemsetAsync(counters + 5, 0, sizeof(u32), ctx->stream));
                 ++ctx->launches;
-                if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+                if (seg_shfl) k_segment_sort_shfl<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
+                else if (seg_walk) k_segment_sort_walk<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
                 else k_segment_sort<<<stiles, SG_THREADS, 0, ctx->stream>>>(ks, vs, counters, in.bits_lo, ko, vo, flags, counters + 5);
                 CKR((exclusive_scan<unsigned char, u64>(ctx, ws, flags, slot, n_kept)));
                 CKR(ws.get(&lk, h_long)); CKR(ws.get(&lv, h_long)); CKR(ws.get(&lk2, h_long)); CKR(ws.get(&lv2, h_long));

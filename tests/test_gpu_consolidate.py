@@ -266,7 +266,8 @@ def test_medium_scale_against_oracle(ctx, orc):
 
 
 @pytest.mark.parametrize("mode,walk,fused,rwarp", [("1", "1", "0", None), ("1", "0", "0", None), ("0", "0", "0", None), ("1", "1", "1", None),
-                                                   ("1", "1", "0", "0"), ("1", "0", "0", "2"), ("0", "0", "0", "2")])
+                                                   ("1", "1", "0", "0"), ("1", "0", "0", "2"), ("0", "0", "0", "2"),
+                                                   ("1", "2", "0", None), ("1", "2", "0", "2")])
 def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused, rwarp):
     """The sort's second organisation -- radix passes over the row part of the key only, then every row ordered by
     column (k_segment_sort), rows longer than 64 entries re-sorted by their full key -- forced on (and off) for shapes
@@ -275,7 +276,7 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused,
     import spsparse_b200 as sp
     from _gpu import up, down
     monkeypatch.setenv("SPB_SEGMENT_SORT", mode)
-    monkeypatch.setenv("SPB_SEGMENT_WALK", walk)   # which of the two in-row kernels (neighbour walk / row table)
+    monkeypatch.setenv("SPB_SEGMENT_WALK", walk)   # which in-row kernel: "1" neighbour walk, "0" row table, "2" shuffles (rows <= 5) + walk
     # fused = "1": the in-row sort runs inside the reduce pass (k_reduce_segsort); the cases with hub rows make it
     # give up and fall back to the separate kernels
     monkeypatch.setenv("SPB_FUSED_REDUCE", fused)
