@@ -1243,6 +1243,9 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     // profiles/r02_notes.md)
     const bool local_count = avg_b_len <= 16.0 && getenv("SPB_MERGE_LOCAL") && atoi(getenv("SPB_MERGE_LOCAL")) != 0;
     const int local_carve = getenv("SPB_MERGE_LOCAL_CARVE") ? atoi(getenv("SPB_MERGE_LOCAL_CARVE")) : -1;
+    // SPB_MERGE_EXACT_COUNT=1: the count pass of the register-merge bin forms the sums too (round-1 behaviour: exact counts, no
+    // tombstones from this bin); default: it merges the column lists only (no values read, a third of the registers per list)
+    const bool exact_count = getenv("SPB_MERGE_EXACT_COUNT") && atoi(getenv("SPB_MERGE_EXACT_COUNT")) != 0;
     const int blk_count = getenv("SPB_MERGE_BLOCKS_COUNT") ? atoi(getenv("SPB_MERGE_BLOCKS_COUNT")) : 0;
     const int blk_num = getenv("SPB_MERGE_BLOCKS_NUMERIC") ? atoi(getenv("SPB_MERGE_BLOCKS_NUMERIC")) : 0;
     {
@@ -1258,6 +1261,10 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
 #define SPB_LAUNCH_COUNT(NL) do { if (local_count) { \
             if (local_carve >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, local_carve)); \
             k_merge_count<NL, true><<<g, 128, 0, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); break; } \
+        if (exact_count) { \
+            if (bal) CKR(allow_ballast(k_merge_count<NL, false, true>)); \
+            if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
+            k_merge_count<NL, false, true><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); break; } \
         if (bal) CKR(allow_ballast(k_merge_count<NL>)); \
         if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
         k_merge_count<NL><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); } while (0)
@@ -1484,8 +1491,11 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(ctx->pool.alloc((void **)&out->val, cnt * sizeof(double)));
     out->owned = true;
     out->n = nnz_c;
+    u32 *mshrunk = nullptr;   // register-merge rows: outputs counted by the (value-free) symbolic pass whose sums turned out exactly 0
+    u32 h_mshrunk = 0;
     if (h_stats[1] && nnz_c)
         {
+        CKR(ws.zeroed(&mshrunk, 1));
         ++ctx->launches;
         const u32 g = (u32)div_up(nrows, MR_THREADS);
         const int stage = getenv("SPB_MERGE_STAGE") ? atoi(getenv("SPB_MERGE_STAGE")) : 16;
@@ -1498,10 +1508,10 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         const bool local_num = local_count && stage == 16 && staged_blocks * 2 >= (ull)div_up(nrows, 128);
 #define SPB_LAUNCH_NUM(NL, ST) do { if (local_num && ST == 16) { \
             if (local_carve >= 0) CK(cudaFuncSetAttribute(k_merge_numeric<NL, 16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, local_carve)); \
-            k_merge_numeric<NL, 16, true><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val); break; } \
+            k_merge_numeric<NL, 16, true><<<g, MR_THREADS, 0, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val, mshrunk); break; } \
         if (bal) CKR(allow_ballast(k_merge_numeric<NL, ST>)); \
         if (carve_n >= 0) CK(cudaFuncSetAttribute(k_merge_numeric<NL, ST>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_n)); \
-        k_merge_numeric<NL, ST><<<g, MR_THREADS, bal, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val); } while (0)
+        k_merge_numeric<NL, ST><<<g, MR_THREADS, bal, ctx->stream>>>(m, row_cls, c_ptr, out->idx[0], out->idx[1], out->val, mshrunk); } while (0)
         if (stage == 4) SPB_LAUNCH_NUM(8, 4);
         else if (stage == 8) SPB_LAUNCH_NUM(8, 8);
         else if (nl_num <= 2 && nl_fit <= 2) SPB_LAUNCH_NUM(2, 16);
@@ -1566,9 +1576,11 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         }
     }
     CK(cudaGetLastError());
-    if (h_stats[5]) CK(cudaStreamSynchronize(ctx->stream));   // h_shrunk is in flight
+    if (mshrunk) CK(cudaMemcpyAsync(&h_mshrunk, mshrunk, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    if (h_stats[5] || mshrunk) CK(cudaStreamSynchronize(ctx->stream));   // h_shrunk / h_mshrunk are in flight
+    h_shrunk += h_mshrunk;
     if (h_shrunk) {
-        // some hash-accumulator outputs summed to exact zero and were dropped: close the gaps (rare)
+        // some outputs of the hash-accumulator or register-merge rows summed to exact zero and were dropped: close the gaps (rare)
         unsigned char *keep;
         u64 *slot;
         CKR(ws.get(&keep, nnz_c));

@@ -192,6 +192,50 @@ struct RowMerge {
     }
 };
 
+// The same merge over the COLUMNS only: what the symbolic pass needs.  Three registers per list instead of seven, no loads of
+// B's or A's values, no arithmetic.  It counts the distinct unmasked columns of the row; an output whose terms cancel to exactly
+// 0 (dropped by the reference, multiply_sparse.hpp:238) is therefore still counted -- the numeric pass finds it and leaves a
+// tombstone that the compaction pass (k_live_flags / k_compact_entries, shared with the hash bin) closes.  Rare: exact
+// cancellation only; measured: config 5 count pass 7.3 -> see profiles/r02_notes.md.
+template <int NL, bool LOCAL = false>
+struct RowMergeK {
+    u32 cur[NL], end[NL];
+    i32 hk[NL];
+    BView b;
+    __device__ __forceinline__ void init(const MMOperands &m, u32 s, u32 len, const BView *view = nullptr) {
+        if (view) b = *view;
+        else { b.k = m.b_k; b.v = m.b_val; b.p = m.bptr; b.k0 = 0; b.j0 = 0; }
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            cur[l] = end[l] = 0;
+            hk[l] = INT32_MAX;
+            if ((u32)l < len) {
+                const i32 j = __ldg(m.a_j + s + l);
+                if (!m.sj_mask || m.sj_mask[j]) {
+                    cur[l] = bv_p<LOCAL>(b, (u32)j);
+                    end[l] = bv_p<LOCAL>(b, (u32)j + 1);
+                    if (cur[l] < end[l]) hk[l] = bv_k<LOCAL>(b, cur[l]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ bool next(i32 &k) {
+        i32 kmin = hk[0];
+#pragma unroll
+        for (int l = 1; l < NL; ++l) kmin = min(kmin, hk[l]);
+        if (kmin == INT32_MAX) return false;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) {
+            if (hk[l] == kmin) {
+                ++cur[l];
+                hk[l] = cur[l] < end[l] ? bv_k<LOCAL>(b, cur[l]) : INT32_MAX;
+            }
+        }
+        k = kmin;
+        return true;
+    }
+};
+
 // keep iff sum != 0 (NaN kept, multiply_sparse.hpp:238) and the column's scale is present and non-zero
 __device__ __forceinline__ bool keep_output(const MMOperands &m, i32 k, double sum, double &b_scale) {
     b_scale = 1.0;
@@ -250,9 +294,25 @@ __device__ __forceinline__ bool stage_b(const MMOperands &m, BStage<CAP, JCAP> &
 }
 
 // symbolic: bin the row and, for a short row, count its outputs exactly
-template <int NL, bool LOCAL = false>
+template <int NL, bool LOCAL = false, bool EXACT = false>
 __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u32 max_products, u32 &count, u64 &f, const BView *view = nullptr) {
-    RowMerge<NL, LOCAL> st;
+    if (EXACT) {   // SPB_MERGE_EXACT_COUNT=1: the count pass forms the sums too (round 1: no tombstones from this bin)
+        RowMerge<NL, LOCAL> st;
+        st.init(m, s, len, view);
+        f = 0;
+#pragma unroll
+        for (int l = 0; l < NL; ++l) f += st.end[l] - st.cur[l];
+        count = 0;
+        if (f == 0) return ROW_SKIP;
+        if (f > max_products) return ROW_ESC;
+        i32 k;
+        double sum, bs;
+        if (st.touch() == -1.2345678e300) return ROW_SKIP;  // never true; see RowMerge::touch
+        while (st.next(m, k, sum))
+            if (keep_output(m, k, sum, bs)) ++count;
+        return ROW_MERGE;
+    }
+    RowMergeK<NL, LOCAL> st;
     st.init(m, s, len, view);
     f = 0;
 #pragma unroll
@@ -261,10 +321,8 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
     if (f == 0) return ROW_SKIP;
     if (f > max_products) return ROW_ESC;
     i32 k;
-    double sum, bs;
-    if (st.touch() == -1.2345678e300) return ROW_SKIP;  // never true; see RowMerge::touch
-    while (st.next(m, k, sum))
-        if (keep_output(m, k, sum, bs)) ++count;
+    while (st.next(k))
+        if (!m.sk || __ldg(m.sk + k) != 0.0) ++count;   // columns excluded by scalek are never outputs (:208-213)
     return ROW_MERGE;
 }
 
@@ -280,7 +338,7 @@ template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 
 // stripes.  (One set of counters for the whole grid, one atomic per warp, made this kernel wait for the L2 atomic unit of a
 // single address: 6 M atomics on one cache line in a 6.5 ms kernel.)
 constexpr int MC_STRIPES = 64;
-template <int NLMAX, bool LOCAL = false>
+template <int NLMAX, bool LOCAL = false, bool EXACT = false>
 __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
     __shared__ BStage<LOCAL ? ML_CAP_COUNT : 1, LOCAL ? ML_JCAP : 1> s_b;
@@ -312,15 +370,15 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
         if (on) {
             if (len > (u32)MERGE_MAX_LISTS) cls = ROW_ESC;   // products counted later, from the per-entry prefix sums
             else if (LOCAL && staged) {
-                if (len <= 2) cls = count_row<2, true>(m, s, len, max_products, c, f, &view);
-                else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), true>(m, s, len, max_products, c, f, &view);
-                else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), true>(m, s, len, max_products, c, f, &view);
-                else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), true>(m, s, len, max_products, c, f, &view);
+                if (len <= 2) cls = count_row<2, true, EXACT>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), true, EXACT>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), true, EXACT>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), true, EXACT>(m, s, len, max_products, c, f, &view);
             }
-            else if (len <= 2) cls = count_row<2>(m, s, len, max_products, c, f);
-            else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2)>(m, s, len, max_products, c, f);
-            else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2)>(m, s, len, max_products, c, f);
-            else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2)>(m, s, len, max_products, c, f);
+            else if (len <= 2) cls = count_row<2, false, EXACT>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), false, EXACT>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), false, EXACT>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), false, EXACT>(m, s, len, max_products, c, f);
         }
         row_cls[r] = (unsigned char)cls;
         if (cls != ROW_ESC) row_cnt[r] = c;  // ESC rows are filled by the expand-sort-compress stage
@@ -352,7 +410,8 @@ constexpr int MR_THREADS = 128;
 
 template <int NL, int STAGE, bool LOCAL = false>
 __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, u32 s, u32 len, i32 irow,
-                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v, const BView *view = nullptr) {
+                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v, const BView *view = nullptr,
+                                                u64 row_end = 0, u32 *shrunk = nullptr) {
     constexpr int PITCH = STAGE + 1;
     constexpr int RUNS = 32 / STAGE;  // lanes' runs written per flush iteration
     const u32 lane = lane_id();
@@ -402,12 +461,18 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
         }
         if (!any_active) break;
     }
+    // The symbolic pass counted distinct columns; outputs whose terms cancelled to exactly 0 were not produced (:238).  The
+    // slots they were given stay at the end of the row's range: tombstones (row index -1) for the compaction pass.
+    if (mine && shrunk && dst < row_end) {
+        for (u64 p = dst; p < row_end; ++p) c_i[p] = -1;
+        atomicAdd(shrunk, (u32)(row_end - dst));
+    }
 }
 
 template <int NLMAX, int STAGE, bool LOCAL = false>
 __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBlocks<NLMAX>::value > 5 ? 5 : MergeBlocks<NLMAX>::value) : 1)) k_merge_numeric(MMOperands m, const unsigned char *__restrict__ row_cls,
                                                               const u64 *__restrict__ c_ptr, i32 *c_i, i32 *c_k,
-                                                              double *c_v) {
+                                                              double *c_v, u32 *shrunk) {
     __shared__ i32 s_k[MR_THREADS * (STAGE + 1)];
     __shared__ double s_v[MR_THREADS * (STAGE + 1)];
     __shared__ BStage<LOCAL ? ML_CAP_NUM : 1, LOCAL ? ML_JCAP : 1> s_b;
@@ -416,12 +481,13 @@ __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBloc
     const bool mine = (r < m.nrows) && (row_cls[r] == ROW_MERGE);
     u32 s = 0, len = 0;
     i32 irow = 0;
-    u64 dst = 0;
+    u64 dst = 0, row_end = 0;
     if (mine) {
         s = m.arow_start[r];
         len = m.arow_start[r + 1] - s;
         irow = m.arow_id[r];
         dst = c_ptr[r];
+        row_end = c_ptr[r + 1];
     }
     BView view;
     bool staged = false;
@@ -439,16 +505,16 @@ __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBloc
     double *sv = s_v + warp * 32 * (STAGE + 1);
     if (maxlen == 0) return;
     if (LOCAL && staged) {
-        if (maxlen <= 2) merge_rows_warp<2, STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
-        else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
-        else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
-        else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view);
+        if (maxlen <= 2) merge_rows_warp<2, STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
+        else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
+        else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
+        else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
         return;
     }
-    if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
-    else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v);
+    if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
+    else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
+    else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
+    else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
 }
 
 // ---- short rows, ONE pass: merge, then place ---------------------------------------------------------------------------------
