@@ -178,8 +178,9 @@ int spb_multiply_mm_prepared(spb_ctx *ctx, double C, const spb_coo *scalei, cons
  * spb_mm_plan_info     which rows of C panel p holds (first/last row index), its product count, and the
  *                      shape of C (multiply_sparse.hpp:169).  panel >= n_panels: only `shape` is written.
  * spb_mm_plan_symbolic symbolic phase of one panel only: exact product count and bins, and the panel's
- *                      output count (exact, except that outputs of the hash-accumulator bin whose terms cancel
- *                      to exactly 0 are still counted) -- no result array is allocated.
+ *                      output count (exact, except that outputs of the register-merge and hash-accumulator bins whose
+ *                      terms cancel to exactly 0 are still counted: the symbolic phase reads no values) -- no result
+ *                      array is allocated.
  * spb_mm_plan_panel    the panel's rows of C, as spb_multiply_mm would have produced them. */
 typedef struct spb_mm_plan spb_mm_plan;
 int spb_mm_plan_create(spb_ctx *ctx, double C, const spb_coo *scalei, const spb_coo *A, char transpose_A,

@@ -1243,9 +1243,6 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     // profiles/r02_notes.md)
     const bool local_count = avg_b_len <= 16.0 && getenv("SPB_MERGE_LOCAL") && atoi(getenv("SPB_MERGE_LOCAL")) != 0;
     const int local_carve = getenv("SPB_MERGE_LOCAL_CARVE") ? atoi(getenv("SPB_MERGE_LOCAL_CARVE")) : -1;
-    // SPB_MERGE_EXACT_COUNT=1: the count pass of the register-merge bin forms the sums too (round-1 behaviour: exact counts, no
-    // tombstones from this bin); default: it merges the column lists only (no values read, a third of the registers per list)
-    const bool exact_count = getenv("SPB_MERGE_EXACT_COUNT") && atoi(getenv("SPB_MERGE_EXACT_COUNT")) != 0;
     const int blk_count = getenv("SPB_MERGE_BLOCKS_COUNT") ? atoi(getenv("SPB_MERGE_BLOCKS_COUNT")) : 0;
     const int blk_num = getenv("SPB_MERGE_BLOCKS_NUMERIC") ? atoi(getenv("SPB_MERGE_BLOCKS_NUMERIC")) : 0;
     {
@@ -1261,10 +1258,6 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
 #define SPB_LAUNCH_COUNT(NL) do { if (local_count) { \
             if (local_carve >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL, true>, cudaFuncAttributePreferredSharedMemoryCarveout, local_carve)); \
             k_merge_count<NL, true><<<g, 128, 0, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); break; } \
-        if (exact_count) { \
-            if (bal) CKR(allow_ballast(k_merge_count<NL, false, true>)); \
-            if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
-            k_merge_count<NL, false, true><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); break; } \
         if (bal) CKR(allow_ballast(k_merge_count<NL>)); \
         if (carve_c >= 0) CK(cudaFuncSetAttribute(k_merge_count<NL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_c)); \
         k_merge_count<NL><<<g, 128, bal, ctx->stream>>>(m, ctx->merge_max_products, row_cls, row_cnt, mstats); } while (0)
@@ -1465,7 +1458,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     const int t_sym = tm.mark();
     if (tracing()) fprintf(stderr, "[spb] mm: symbolic host %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (symbolic_only) {
-        // counts only (spb_mm_plan_symbolic): F and the bins are exact; nnz_c is exact except that hash-bin outputs whose
+        // counts only (spb_mm_plan_symbolic): F and the bins are exact; nnz_c is exact except that outputs of the merge / hash bins whose
         // terms cancel to exactly 0 are still counted (the numeric pass is what finds them)
         if (st) {
             st->products = h_stats[0] + h_stats[3] + h_stats[4]; st->rows_merge = h_stats[1]; st->rows_esc = h_stats[2] - h_stats[5];
@@ -1491,7 +1484,9 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
     CK(ctx->pool.alloc((void **)&out->val, cnt * sizeof(double)));
     out->owned = true;
     out->n = nnz_c;
-    u32 *mshrunk = nullptr;   // register-merge rows: outputs counted by the (value-free) symbolic pass whose sums turned out exactly 0
+    // register-merge rows: the (value-free) symbolic pass counted distinct columns; outputs whose sums turn out exactly 0 are
+    // written as tombstones by the numeric pass and counted here; the compaction below closes the gaps (rare)
+    u32 *mshrunk = nullptr;
     u32 h_mshrunk = 0;
     if (h_stats[1] && nnz_c)
         {
@@ -1576,6 +1571,7 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         }
     }
     CK(cudaGetLastError());
+    int t_num = tm.mark();   // (before the host looks at the tombstone counts: the wait is not kernel time)
     if (mshrunk) CK(cudaMemcpyAsync(&h_mshrunk, mshrunk, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     if (h_stats[5] || mshrunk) CK(cudaStreamSynchronize(ctx->stream));   // h_shrunk / h_mshrunk are in flight
     h_shrunk += h_mshrunk;
@@ -1599,8 +1595,8 @@ static int multiply_core(spb_ctx *ctx, double C, const spb_coo *si, const spb_co
         ctx->pool.release(out->idx[0]); ctx->pool.release(out->idx[1]); ctx->pool.release(out->val);
         out->idx[0] = i2; out->idx[1] = k2; out->val = v2;
         out->n = nnz_c = nnz2;
+        t_num = tm.mark();
     }
-    const int t_num = tm.mark();
     CK(cudaStreamSynchronize(ctx->stream));
     if (tracing()) fprintf(stderr, "[spb] mm: total host since prepare %.2f ms, alloc total %.2f ms\n", now_ms() - h0, g_alloc_ms);
     if (st) {

@@ -196,7 +196,7 @@ struct RowMerge {
 // B's or A's values, no arithmetic.  It counts the distinct unmasked columns of the row; an output whose terms cancel to exactly
 // 0 (dropped by the reference, multiply_sparse.hpp:238) is therefore still counted -- the numeric pass finds it and leaves a
 // tombstone that the compaction pass (k_live_flags / k_compact_entries, shared with the hash bin) closes.  Rare: exact
-// cancellation only; measured: config 5 count pass 7.3 -> see profiles/r02_notes.md.
+// cancellation only.  Config 5 count pass 7.3 -> 4.3 ms, config 3 2.4 -> 1.6 ms.
 template <int NL, bool LOCAL = false>
 struct RowMergeK {
     u32 cur[NL], end[NL];
@@ -294,24 +294,8 @@ __device__ __forceinline__ bool stage_b(const MMOperands &m, BStage<CAP, JCAP> &
 }
 
 // symbolic: bin the row and, for a short row, count its outputs exactly
-template <int NL, bool LOCAL = false, bool EXACT = false>
+template <int NL, bool LOCAL = false>
 __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u32 max_products, u32 &count, u64 &f, const BView *view = nullptr) {
-    if (EXACT) {   // SPB_MERGE_EXACT_COUNT=1: the count pass forms the sums too (round 1: no tombstones from this bin)
-        RowMerge<NL, LOCAL> st;
-        st.init(m, s, len, view);
-        f = 0;
-#pragma unroll
-        for (int l = 0; l < NL; ++l) f += st.end[l] - st.cur[l];
-        count = 0;
-        if (f == 0) return ROW_SKIP;
-        if (f > max_products) return ROW_ESC;
-        i32 k;
-        double sum, bs;
-        if (st.touch() == -1.2345678e300) return ROW_SKIP;  // never true; see RowMerge::touch
-        while (st.next(m, k, sum))
-            if (keep_output(m, k, sum, bs)) ++count;
-        return ROW_MERGE;
-    }
     RowMergeK<NL, LOCAL> st;
     st.init(m, s, len, view);
     f = 0;
@@ -331,14 +315,14 @@ __device__ __forceinline__ int count_row(const MMOperands &m, u32 s, u32 len, u3
 // them -- every step waits an L2 round trip for the heads it advanced.  NLMAX = the longest row of op(A) that can
 // take the merge, rounded up to 2/4/6/8 (the host knows it): configs 3 and 5 (4 and 5 entries per row) get kernels
 // with half the registers and twice the warps.
-template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 4 ? 8 : NLMAX <= 6 ? 6 : 5; };
+template <int NLMAX> struct MergeBlocks { static constexpr int value = NLMAX <= 4 ? 8 : NLMAX <= 6 ? 7 : 5; };  // (NL = 6: 72 registers = 7 blocks; at 74 the kernel loses a block and 11 % of its speed)
 
 // stats: MC_STRIPES stripes of 8 counters, one cache line apart in pairs -- [0] F of merged rows, [1] rows merged, [2] rows
 // ESC, [6] longest row of op(A) (entries); a warp adds its totals to one stripe (warps take the stripes in turn) and the host sums the
 // stripes.  (One set of counters for the whole grid, one atomic per warp, made this kernel wait for the L2 atomic unit of a
 // single address: 6 M atomics on one cache line in a 6.5 ms kernel.)
 constexpr int MC_STRIPES = 64;
-template <int NLMAX, bool LOCAL = false, bool EXACT = false>
+template <int NLMAX, bool LOCAL = false>
 __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(MMOperands m, u32 max_products, unsigned char *row_cls,
                                                      u32 *row_cnt, ull *stats) {
     __shared__ BStage<LOCAL ? ML_CAP_COUNT : 1, LOCAL ? ML_JCAP : 1> s_b;
@@ -370,15 +354,15 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
         if (on) {
             if (len > (u32)MERGE_MAX_LISTS) cls = ROW_ESC;   // products counted later, from the per-entry prefix sums
             else if (LOCAL && staged) {
-                if (len <= 2) cls = count_row<2, true, EXACT>(m, s, len, max_products, c, f, &view);
-                else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), true, EXACT>(m, s, len, max_products, c, f, &view);
-                else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), true, EXACT>(m, s, len, max_products, c, f, &view);
-                else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), true, EXACT>(m, s, len, max_products, c, f, &view);
+                if (len <= 2) cls = count_row<2, true>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), true>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), true>(m, s, len, max_products, c, f, &view);
+                else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), true>(m, s, len, max_products, c, f, &view);
             }
-            else if (len <= 2) cls = count_row<2, false, EXACT>(m, s, len, max_products, c, f);
-            else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2), false, EXACT>(m, s, len, max_products, c, f);
-            else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2), false, EXACT>(m, s, len, max_products, c, f);
-            else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2), false, EXACT>(m, s, len, max_products, c, f);
+            else if (len <= 2) cls = count_row<2>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 4 && len <= 4) cls = count_row<(NLMAX >= 4 ? 4 : 2)>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 6 && len <= 6) cls = count_row<(NLMAX >= 6 ? 6 : 2)>(m, s, len, max_products, c, f);
+            else if (NLMAX >= 8) cls = count_row<(NLMAX >= 8 ? 8 : 2)>(m, s, len, max_products, c, f);
         }
         row_cls[r] = (unsigned char)cls;
         if (cls != ROW_ESC) row_cnt[r] = c;  // ESC rows are filled by the expand-sort-compress stage
@@ -408,10 +392,14 @@ __global__ void __launch_bounds__(128, MergeBlocks<NLMAX>::value) k_merge_count(
 // sectors instead of one 4/8-byte store per thread per step.
 constexpr int MR_THREADS = 128;
 
+// The symbolic pass counted the distinct unmasked columns of the row without reading a value; an output whose terms cancel to
+// exactly 0 is dropped by the reference (:238).  It keeps its slot here as a TOMBSTONE (column and row index -1) -- every counted
+// slot is written, in order -- and the lanes that wrote any add to *shrunk; the host then runs the compaction pass it already has
+// for the hash bin.  Nothing is added to the common path but a select per stored entry (checking the rows' ranges, or counting what
+// was produced, in this kernel cost 0.4-1.0 ms of its 8.9 on config 5: profiles/r02_notes.md).
 template <int NL, int STAGE, bool LOCAL = false>
 __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, u32 s, u32 len, i32 irow,
-                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v, const BView *view = nullptr,
-                                                u64 row_end = 0, u32 *shrunk = nullptr) {
+                                                u64 dst, i32 *sk, double *sv, i32 *c_i, i32 *c_k, double *c_v, u32 *shrunk, const BView *view = nullptr) {
     constexpr int PITCH = STAGE + 1;
     constexpr int RUNS = 32 / STAGE;  // lanes' runs written per flush iteration
     const u32 lane = lane_id();
@@ -421,16 +409,23 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
     if (mine && m.si) a_scale = m.si[irow];
     u32 cnt = 0;
     bool active = mine;
+    u32 ndead = 0;
     if (st.touch() + a_scale + (double)dst == -1.2345678e300) active = false;  // never true; see RowMerge::touch
     for (;;) {
         if (active) {
             i32 k;
-            double sum, b_scale;
+            double sum, b_scale = 1.0;
             if (!st.next(m, k, sum)) active = false;
-            else if (keep_output(m, k, sum, b_scale)) {
-                sk[lane * PITCH + cnt] = k;
-                sv[lane * PITCH + cnt] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
-                ++cnt;
+            else {
+                bool masked = false;   // columns excluded by scalek are never outputs (:208-213) and were not counted
+                if (m.sk) { b_scale = __ldg(m.sk + k); masked = b_scale == 0.0; }
+                if (!masked) {
+                    const bool dead = !(sum != 0.0);   // :238 (NaN != 0 is kept)
+                    sk[lane * PITCH + cnt] = dead ? -1 : k;
+                    sv[lane * PITCH + cnt] = __dmul_rn(__dmul_rn(__dmul_rn(sum, m.C), a_scale), b_scale);  // :242
+                    ++cnt;
+                    ndead += dead;
+                }
             }
         }
         const bool any_active = __any_sync(SPB_FULL_MASK, active);
@@ -444,14 +439,15 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
                 const u64 d_l = __shfl_sync(SPB_FULL_MASK, dst, l);
                 const i32 i_l = __shfl_sync(SPB_FULL_MASK, irow, l);
                 if (t < n_l && m.debug != 1) {
+                    const i32 kk = sk[l * PITCH + t];
                     if (m.debug == 2) {
-                        c_k[d_l + t] = sk[l * PITCH + t];
+                        c_k[d_l + t] = kk;
                         c_v[d_l + t] = sv[l * PITCH + t];
-                        c_i[d_l + t] = i_l;
+                        c_i[d_l + t] = kk < 0 ? -1 : i_l;
                     } else {  // streaming stores: C is written once and never re-read here; keep L1/L2 for B
-                        __stcs(c_k + d_l + t, sk[l * PITCH + t]);
+                        __stcs(c_k + d_l + t, kk);
                         __stcs(c_v + d_l + t, sv[l * PITCH + t]);
-                        __stcs(c_i + d_l + t, i_l);
+                        __stcs(c_i + d_l + t, kk < 0 ? -1 : i_l);
                     }
                 }
             }
@@ -461,12 +457,7 @@ __device__ __forceinline__ void merge_rows_warp(const MMOperands &m, bool mine, 
         }
         if (!any_active) break;
     }
-    // The symbolic pass counted distinct columns; outputs whose terms cancelled to exactly 0 were not produced (:238).  The
-    // slots they were given stay at the end of the row's range: tombstones (row index -1) for the compaction pass.
-    if (mine && shrunk && dst < row_end) {
-        for (u64 p = dst; p < row_end; ++p) c_i[p] = -1;
-        atomicAdd(shrunk, (u32)(row_end - dst));
-    }
+    if (ndead) atomicAdd(shrunk, ndead);   // rare
 }
 
 template <int NLMAX, int STAGE, bool LOCAL = false>
@@ -481,13 +472,12 @@ __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBloc
     const bool mine = (r < m.nrows) && (row_cls[r] == ROW_MERGE);
     u32 s = 0, len = 0;
     i32 irow = 0;
-    u64 dst = 0, row_end = 0;
+    u64 dst = 0;
     if (mine) {
         s = m.arow_start[r];
         len = m.arow_start[r + 1] - s;
         irow = m.arow_id[r];
         dst = c_ptr[r];
-        row_end = c_ptr[r + 1];
     }
     BView view;
     bool staged = false;
@@ -505,16 +495,16 @@ __global__ void __launch_bounds__(MR_THREADS, (STAGE == 16 ? (LOCAL && MergeBloc
     double *sv = s_v + warp * 32 * (STAGE + 1);
     if (maxlen == 0) return;
     if (LOCAL && staged) {
-        if (maxlen <= 2) merge_rows_warp<2, STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
-        else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
-        else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
-        else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, &view, row_end, shrunk);
+        if (maxlen <= 2) merge_rows_warp<2, STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk, &view);
+        else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk, &view);
+        else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk, &view);
+        else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE, true>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk, &view);
         return;
     }
-    if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
-    else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
-    else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
-    else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, nullptr, row_end, shrunk);
+    if (maxlen <= 2) merge_rows_warp<2, STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk);
+    else if (NLMAX >= 4 && maxlen <= 4) merge_rows_warp<(NLMAX >= 4 ? 4 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk);
+    else if (NLMAX >= 6 && maxlen <= 6) merge_rows_warp<(NLMAX >= 6 ? 6 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk);
+    else if (NLMAX >= 8) merge_rows_warp<(NLMAX >= 8 ? 8 : 2), STAGE>(m, mine, s, len, irow, dst, sk, sv, c_i, c_k, c_v, shrunk);
 }
 
 // ---- short rows, ONE pass: merge, then place ---------------------------------------------------------------------------------

@@ -116,6 +116,53 @@ def test_mm_against_oracle_fresh_seeds(ctx, orc):
         assert _cases.same_coo(gpu_mm(ctx, *args), orc.multiply_mm(*args)), s
 
 
+def test_cancellation_in_the_register_merge_bin(orc):
+    """Short rows whose terms cancel to exactly 0: the reference drops such outputs (multiply_sparse.hpp:238).  The symbolic
+    pass of the register-merge bin counts distinct columns without reading a value, so the numeric pass leaves tombstones
+    that the compaction closes -- whole rows vanishing, partial cancellation, NaN sums (kept), next to ordinary rows, also
+    in row panels."""
+    import spsparse_b200 as sp
+    from _gpu import up, down
+    rng = np.random.default_rng(404)
+    m, nj, nk = 3000, 400, 5000
+    # B: rows 2j and 2j+1 identical for j < 100 (so +a / -a on that pair cancels every shared output), the rest random
+    bj, bk, bv = [], [], []
+    for j in range(100):
+        cols = np.sort(rng.choice(nk, 6, replace=False))
+        vals = rng.integers(1, 5, 6).astype(np.float64)
+        for jj in (2 * j, 2 * j + 1):
+            bj += [jj] * 6; bk += cols.tolist(); bv += vals.tolist()
+    nb = 3000
+    bj += rng.integers(200, nj, nb).tolist(); bk += rng.integers(0, nk, nb).tolist(); bv += rng.integers(1, 5, nb).astype(float).tolist()
+    B = O.Coo((nj, nk), [np.array(bj), np.array(bk)], np.array(bv))
+    ai, aj, av = [], [], []
+    for i in range(m):
+        kind = i % 4
+        if kind == 0:      # everything cancels: the row of C is empty
+            p = int(rng.integers(0, 100)); ai += [i, i]; aj += [2 * p, 2 * p + 1]; av += [3.0, -3.0]
+        elif kind == 1:    # a cancelling pair plus other terms: some outputs vanish, some survive
+            p = int(rng.integers(0, 100)); q = int(rng.integers(200, nj))
+            ai += [i, i, i]; aj += [2 * p, 2 * p + 1, q]; av += [2.0, -2.0, 1.5]
+        elif kind == 2:    # no cancellation
+            for q in rng.choice(np.arange(200, nj), 4, replace=False):
+                ai.append(i); aj.append(int(q)); av.append(float(rng.integers(1, 4)))
+        else:              # +inf - inf = NaN: kept (NaN != 0)
+            p = int(rng.integers(0, 100)); ai += [i, i]; aj += [2 * p, 2 * p + 1]; av += [np.inf, -np.inf]
+    A = O.Coo((m, nj), [np.array(ai), np.array(aj)], np.array(av))
+    want, st = orc.multiply_mm(1.0, None, A, ".", None, B, ".", None, want_stats=True)
+    with sp.Context(0) as c2:
+        hs = [up(c2, x) for x in (A, B)]
+        R, gst = sp.multiply(c2, 1.0, None, hs[0], ".", None, hs[1], ".", None, stats=True)
+        got = down(R)
+        assert gst.products == st["F"] and gst.rows_hash == 0 and gst.rows_esc == 0 and gst.rows_merge > 0
+        assert gst.nnz_c == want.n and _cases.same_coo(got, want)
+        assert np.isnan(got.val).sum() == np.isnan(want.val).sum() > 0
+        for h in hs + [R]:
+            h.free()
+        got_p, n_panels = gpu_mm_panels(c2, 1.0, None, A, ".", None, B, ".", None, max_products=2000)
+        assert n_panels > 3 and _cases.same_coo(got_p, want)
+
+
 def test_errors_and_empties(ctx):
     import spsparse_b200 as sp
     A = O.Coo((2, 3), [[0], [0]], [1.])
