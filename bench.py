@@ -377,6 +377,17 @@ def run_ours(args):
             mode["fetch_all"] = False
             Cx, _ = hot_path(A_raw, B_raw, w); Cx.free()   # pulled[0] back to what the headline run fetches
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        # every rank's own step time and phase times (the headline takes the maximum; the spread shows where a rank waits)
+        per_rank = None
+        if world > 1:
+            mine = torch.tensor([ms] + [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)],
+                                dtype=torch.float64, device="cuda")
+            allr = torch.zeros(world * mine.numel(), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allr, mine)
+            allr = allr.view(world, -1).cpu().numpy()
+            per_rank = {"ms_per_step": [float(x) for x in allr[:, 0]],
+                        "phases_ms": {k: [float(x) for x in allr[:, 1 + i]] for i, k in enumerate(
+                            ["consolidate_b", "publish_and_gaps", "consolidate_a", "replicate_b_wait", "spgemm_incl_prepare"])}}
         sa, sb, st = acc[-1]
         cnt = torch.tensor([st.products, st.nnz_c, sa.n_out + sb.n_out, nA + nB], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -559,6 +570,7 @@ def run_ours(args):
                              "timeline_ms": dict(zip(["consolidate_b", "publish_and_gaps" if rowpart[0] is not None else "replicate_b_launch", "consolidate_a", "replicate_b_wait",
                                                       "spgemm_incl_prepare"],
                                                      [float(x) for x in np.mean(np.array(timeline[args.warmup:args.warmup + args.steps]), axis=0)]))},
+            "per_rank": per_rank,
             "roofline": {"bound": "hbm", "kernel": ("k_radix_pass9<false, BULK> (one 9-bit LSD scatter pass, key+value)" if sa.digit_bits == 9 else
                                                     "k_radix_pass<false, BULK> (one 8-bit LSD scatter pass, key+value)"),
                          "achieved": pass_gbs, "peak": hbm, "unit": "GB/s", "frac": pass_gbs / hbm,
