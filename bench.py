@@ -60,7 +60,8 @@ class ClockSampler:
         import threading
         self.p = self.f = self.thread = None
         self.sm, self.reasons, self.smax = [], set(), None
-        self.halt = threading.Event()
+        self.live = threading.Event()   # set by begin(): samples before it are not kept (the sampler is started ahead of the
+        self.halt = threading.Event()   # barrier in front of the timed region, so that starting it costs no rank any timed time)
         try:
             self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -82,14 +83,15 @@ class ClockSampler:
 
             def poll():
                 while not self.halt.is_set():
-                    try:
-                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                        for b, nm in bits.items():
-                            if r & b:
-                                self.reasons.add(nm)
-                    except Exception:  # noqa: BLE001 -- a failed query is a missing sample
-                        pass
+                    if self.live.is_set():
+                        try:
+                            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                            for b, nm in bits.items():
+                                if r & b:
+                                    self.reasons.add(nm)
+                        except Exception:  # noqa: BLE001 -- a failed query is a missing sample
+                            pass
                     self.halt.wait(0.002)
 
             self.thread = threading.Thread(target=poll, daemon=True)
@@ -122,6 +124,11 @@ class ClockSampler:
             self.f.close()
             os.unlink(self.f.name)
         return sm, (max(smax) if smax else None), reasons
+
+    def begin(self):
+        """The timed region starts now."""
+        self.live.set()
+        return self
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
@@ -322,9 +329,14 @@ def run_ours(args):
         for _ in range(args.warmup):
             Cm, _ = hot_path(A_raw, B_raw, w)
             Cm.free()
+        # the clock sampler (rank 0: an nvidia-smi child process and an NVML thread) is STARTED before the barrier: starting it
+        # after the barrier delayed rank 0's first timed step by the fork + NVML initialisation (5 ... 130 ms measured), and at
+        # N > 1 the other ranks -- whose clocks were already running -- spent that time waiting for rank 0's shard
+        sampler = ClockSampler(local, gpu_uuid(torch, local)) if rank == 0 else None
         barrier()
         l0 = launches()
-        sampler = ClockSampler(local, gpu_uuid(torch, local)) if rank == 0 else None
+        if sampler:
+            sampler.begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = []
         e0.record(stream)

@@ -123,6 +123,21 @@ constexpr int RP_PULL_UNROLL = 8;
 // info[0] = entries fetched, info[1] = rows fetched, info[2] = blocks finished (zeroed by the host), info[3] = outcome:
 // 1 = done in place, 2 = done by copying, 3 = the halos do not fit the slack (nothing done, the peers NOT released: the host
 // launches the copying variant)
+// Waits, with ONE warp, for the ready counters the fetch below will need (the peers whose rows lie inside the hull, and the own
+// shard).  The fetch kernel waits for them too -- every block works its plan out for itself -- but its blocks are 512 threads with
+// eight 16-byte loads in flight each: 32 of them parked on a late neighbour took half the registers of 32 SMs away from the
+// consolidate(A) that runs meanwhile (measured at N = 8: +0.3 ms on the ranks that waited).  Launched in front of it on the side
+// stream, this kernel does the waiting; the fetch then finds the counters raised.
+__global__ void __launch_bounds__(32) k_rp_wait_ready(RpArgs a, const u64 *__restrict__ hull) {
+    const int g = (int)threadIdx.x;
+    const u64 lo = hull[0], hi = hull[1];
+    if (g < a.n_ranks) {
+        bool need = g == a.rank;
+        if (lo <= hi) need = need || max(lo, a.row_lo[g]) < min(hi + 1, a.row_lo[g + 1]);
+        if (need) rp_wait_ge(a.reg[a.rank].flags + g, a.step, a.error);
+    }
+}
+
 template <bool IN_PLACE>
 __global__ void __launch_bounds__(RP_PULL_THREADS) k_rp_pull(RpArgs a, const u64 *__restrict__ hull, u32 *g_ptr, i32 *g_cols,
                                                              double *g_vals, u64 cap_entries, u64 *info) {

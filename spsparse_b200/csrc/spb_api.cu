@@ -2527,6 +2527,7 @@ int spb_rowpart_multiply(spb_rowpart *rp, double C, const spb_coo *si, const spb
         }
         CK(cudaStreamWaitEvent(rp->side, rp->ev_pub, 0));
         CK(cudaEventRecord(rp->ev_t[1], rp->side));
+        ++ctx->launches, k_rp_wait_ready<<<1, 32, 0, rp->side>>>(ra, rp->hull);   // one warp waits for the peers; the fetch's blocks do not
         ++ctx->launches;
         if (copy_mode) k_rp_pull<false><<<96u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, rp->g_cols, rp->g_vals, rp->g_cap, rp->info);
         else k_rp_pull<true><<<32u, RP_PULL_THREADS, 0, rp->side>>>(ra, rp->hull, rp->g_ptr, nullptr, nullptr, 0, rp->info);

@@ -64,6 +64,9 @@ def test_clock_sampler_prefers_nvml_and_survives_failed_queries(monkeypatch):
     nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap = 32, 4
     monkeypatch.setitem(sys.modules, "pynvml", nv)
     s = bench.ClockSampler(0, "GPU-1234")
+    time.sleep(0.02)
+    assert s.sm == []            # nothing is kept before the timed region begins
+    s.begin()
     time.sleep(0.05)
     out = s.stop()
     assert out["samples"] >= 5 and out["source"].startswith("nvml") and 1900 <= out["sm_mhz"] <= 1901

@@ -18,3 +18,10 @@ for line in open("gpurun_out/r02_c30/bench2.out"):
         print("N=2 ms_per_step", d["ms_per_step"], "value", d["value"], "timeline", d.get("phases_rank0", {}).get("timeline_ms"))
         print("fingerprint", d["config"]["result_fingerprint"], "e2e", d["e2e"]["ms_per_step"], "full_replicate", d.get("also", {}).get("full_replicate", {}).get("ms_per_step"))
 P
+python - <<'P'
+import json
+for line in open("gpurun_out/r02_c30/bench2.out"):
+    if line.startswith("{"):
+        d = json.loads(line)
+        print("per_rank", json.dumps(d.get("per_rank")))
+P
