@@ -320,6 +320,12 @@ def test_row_passes_plus_in_row_column_sort(orc, monkeypatch, mode, walk, fused,
                     want = orc.consolidate(a, so, pol, zn)
                     assert _cases.same_coo(got, want), (s, so, pol)
                     assert np.array_equal(db, orc.dim_beginnings(want)), (s, so, pol)
+                if s in (0, 3, 8, 10):
+                    # the stable argsort keeps every entry (KEEP_ALL through the same kernels: every entry is a run head)
+                    A = up(c2, a)
+                    perm = A.sorted_permutation(so)
+                    A.free()
+                    assert np.array_equal(perm, orc.sorted_permutation(a, so)), (s, so)
 
 
 @pytest.mark.parametrize("seg", ["1", "0"])
