@@ -2389,7 +2389,9 @@ int spb_rowpart_create(spb_ctx *ctx, int rank, int n_ranks, const uint64_t *row_
             rp->error = (u32 *)(rp->hull + 6);
             int lo_pri = 0, hi_pri = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-            CK(cudaStreamCreateWithPriority(&rp->side, cudaStreamNonBlocking, hi_pri));   // small kernels: ahead of the sort's blocks
+            // small kernels: ahead of the sort's blocks (SPB_ROWPART_SIDE_PRIO=0: the default priority, for A/B runs)
+            const bool side_hi = !(getenv("SPB_ROWPART_SIDE_PRIO") && atoi(getenv("SPB_ROWPART_SIDE_PRIO")) == 0);
+            CK(cudaStreamCreateWithPriority(&rp->side, cudaStreamNonBlocking, side_hi ? hi_pri : lo_pri));
             CK(cudaEventCreateWithFlags(&rp->ev_main, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&rp->ev_pub, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&rp->ev_pull, cudaEventDisableTiming));
