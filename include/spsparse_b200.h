@@ -57,6 +57,11 @@ int spb_ctx_device(const spb_ctx *ctx, int *device, void **cuda_stream);
  * spb_ctx_trim waits for the stream and hands every cached block back to the driver -- for processes that share the GPU
  * with another allocator; released_bytes (may be NULL) reports how much. */
 int spb_ctx_trim(spb_ctx *ctx, uint64_t *released_bytes);
+/* Host-side helper for callers that download multi-GB results into freshly reserved (never touched) memory, e.g. the tail of
+ * a std::vector after reserve(): writes a zero into every page of [p, p + bytes) from several threads, so that the page
+ * faults of the first touch -- 1 GB/s from one thread, the dominant cost of spsparse::multiply into an empty VectorCooArray --
+ * are taken in parallel.  Needs no GPU and no context. */
+int spb_host_prefault(void *p, uint64_t bytes);
 /* kernels launched through this context so far (measurement aid) */
 int spb_ctx_launch_count(const spb_ctx *ctx, uint64_t *launches);
 

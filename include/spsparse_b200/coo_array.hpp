@@ -232,6 +232,16 @@ public:
     void grow_raw(size_t n, IndexT **idx_out, ValT **val_out) {
         if (!edit_mode) (*spsparse_error)(-1, "Must be in edit mode to use VectorCooArray::add()");
         const size_t old = val_vec.size();
+        if (n >= (size_t(1) << 22)) {
+            // large results: the first touch of fresh pages from ONE thread (what resize() does) runs at ~1 GB/s and was most of
+            // the time of a multiply into an empty array (6 s for 14 GB); take the page faults in parallel first
+            for (int k = 0; k < RANK; ++k) {
+                index_vecs[k].reserve(old + n);
+                spb_host_prefault(index_vecs[k].data() + old, (uint64_t)n * sizeof(IndexT));
+            }
+            val_vec.reserve(old + n);
+            spb_host_prefault(val_vec.data() + old, (uint64_t)n * sizeof(ValT));
+        }
         for (int k = 0; k < RANK; ++k) { index_vecs[k].resize(old + n); idx_out[k] = index_vecs[k].data() + old; }
         val_vec.resize(old + n);
         *val_out = val_vec.data() + old;

@@ -53,6 +53,7 @@ SIGNATURES = {
     "spb_ctx_sync": (C.c_int, [vp]),
     "spb_ctx_device": (C.c_int, [vp, intp, C.POINTER(vp)]),
     "spb_ctx_trim": (C.c_int, [vp, u64p]),
+    "spb_host_prefault": (C.c_int, [vp, C.c_uint64]),
     "spb_ctx_launch_count": (C.c_int, [vp, u64p]),
     "spb_coo_upload": (C.c_int, [vp, C.c_int, u64p, C.POINTER(i32p), f64p, C.c_uint64, intp, C.POINTER(vp)]),
     "spb_coo_wrap_device": (C.c_int, [vp, C.c_int, u64p, C.POINTER(vp), vp, C.c_uint64, intp, C.POINTER(vp)]),

@@ -401,6 +401,28 @@ int spb_ctx_trim(spb_ctx *ctx, uint64_t *released_bytes) {
     return SPB_OK;
 }
 
+int spb_host_prefault(void *p, uint64_t bytes) {
+    if (!p || !bytes) return SPB_OK;
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 16) nt = 16;
+    if (bytes < (64ull << 20) || nt < 2) nt = 1;
+    constexpr uint64_t PAGE = 4096;
+    auto work = [=](unsigned t) {
+        volatile char *c = static_cast<volatile char *>(p);
+        const uint64_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
+        if (a < b) c[a] = 0;
+        // page-aligned addresses inside [a, b): one write per page
+        const uint64_t base = reinterpret_cast<uintptr_t>(p);
+        for (uint64_t o = ((base + a + PAGE - 1) & ~(PAGE - 1)) - base; o < b; o += PAGE) c[o] = 0;
+    };
+    if (nt == 1) { work(0); return SPB_OK; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    return SPB_OK;
+}
+
 int spb_ctx_launch_count(const spb_ctx *ctx, uint64_t *launches) {
     if (!ctx || !launches) return spb_fail(SPB_ERR_ARG, "null argument");
     *launches = ctx->launches;

@@ -341,7 +341,30 @@ static void test_error_convention() {
     CHECK(sorted_permutation(z, {0, 1}).empty());
 }
 
+static void test_grow_raw_large() {
+    // room for a multi-million-entry device result at the end of an array that already holds entries: the new pages are
+    // pre-faulted in parallel (spb_host_prefault), the old entries stay, the new slots are value-initialised and writable
+    Mat a({4, 6});
+    a.add({1, 3}, 5.); a.add({0, 1}, -2.);
+    const size_t n = (size_t(1) << 22) + 5;
+    int *ip[2] = {nullptr, nullptr};
+    double *vp = nullptr;
+    a.grow_raw(n, ip, &vp);
+    CHECK(a.size() == n + 2 && ip[0] == a.index_data(0).data() + 2 && ip[1] == a.index_data(1).data() + 2 && vp == a.val_data().data() + 2);
+    CHECK(a.index(0, 0) == 1 && a.index(1, 1) == 1 && a.val(0) == 5. && a.val(1) == -2.);
+    bool zero = true;
+    for (size_t t = 0; t < n; t += 4099) zero = zero && ip[0][t] == 0 && ip[1][t] == 0 && vp[t] == 0.;
+    CHECK(zero && ip[0][n - 1] == 0 && vp[n - 1] == 0.);
+    vp[n - 1] = 3.5; ip[1][n - 1] = 5;
+    CHECK(a.val(n + 1) == 3.5 && a.index(1, n + 1) == 5);
+    // the helper itself: any range, any alignment, nothing but zeros written to the first byte of every page
+    std::vector<char> buf(3 * 4096 + 17, 7);
+    CHECK(spb_host_prefault(buf.data() + 5, buf.size() - 9) == 0 && spb_host_prefault(nullptr, 10) == 0 && spb_host_prefault(buf.data(), 0) == 0);
+    CHECK(buf[5] == 0 && buf[4] == 7 && buf[6] == 7 && buf[buf.size() - 1] == 7);
+}
+
 int main() {
+    test_grow_raw_large();
     test_container();
     test_bounds();
     test_iterators();
