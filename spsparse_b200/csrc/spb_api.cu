@@ -126,7 +126,8 @@ struct spb_ctx {
     u64 launches;            // kernels launched so far (bench.py reports it as gpu_launches)
     bool bulk_load;          // radix passes after the first bring their tile in with cp.async.bulk (SPB_BULK_LOAD, default on)
     // pageable host memory <-> device: worker threads copy through pinned staging buffers (see staged_copy)
-    static constexpr int XFER_WORKERS = 4;
+    static constexpr int XFER_WORKERS = 8;   // at most; xfer_workers of them are used (SPB_XFER_WORKERS, default: half the host's threads)
+    int xfer_workers;
     static constexpr size_t XFER_CHUNK = 16u << 20;
     void *xfer_buf[XFER_WORKERS][2];
     cudaStream_t xfer_stream[XFER_WORKERS];
@@ -217,7 +218,7 @@ static inline u32 grid_for(u64 n, u32 threads, u32 cap) {
 
 // ---- host <-> device transfers of caller memory -----------------------------------------------------------------------
 // A reference user's arrays are std::vectors: pageable memory, which the driver can only move through its own single
-// staging pipeline (6-10 GB/s measured).  Here XFER_WORKERS threads each copy every XFER_WORKERS-th chunk between the
+// staging pipeline (6-10 GB/s measured).  Here xfer_workers threads (up to XFER_WORKERS) each copy every xfer_workers-th chunk between the
 // caller's memory and a pinned double buffer of their own and move it with an asynchronous copy on their own stream, so
 // the CPU-side copies of several chunks and the DMA transfers overlap.  Pinned (or registered) caller memory is moved
 // directly.  Synchronous for the caller, as the C ABI promises.
@@ -229,7 +230,11 @@ static bool host_ptr_is_pinned(const void *p) {
 
 static int xfer_setup(spb_ctx *c) {
     if (c->xfer_ready) return 0;
-    for (int w = 0; w < spb_ctx::XFER_WORKERS; ++w) {
+    {
+        int want = getenv("SPB_XFER_WORKERS") ? atoi(getenv("SPB_XFER_WORKERS")) : (int)(std::thread::hardware_concurrency() / 2);
+        c->xfer_workers = want < 1 ? 1 : (want > spb_ctx::XFER_WORKERS ? spb_ctx::XFER_WORKERS : want);
+    }
+    for (int w = 0; w < c->xfer_workers; ++w) {
         CK(cudaStreamCreateWithFlags(&c->xfer_stream[w], cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
             CK(cudaHostAlloc(&c->xfer_buf[w][b], spb_ctx::XFER_CHUNK, cudaHostAllocDefault));
@@ -264,12 +269,13 @@ static int staged_copy(spb_ctx *c, const XferJob *jobs, int njobs, bool to_devic
     for (int j = 0; j < njobs; ++j)
         for (size_t o = 0; o < jobs[j].bytes; o += spb_ctx::XFER_CHUNK)
             chunks.push_back({(char *)jobs[j].dev + o, (char *)jobs[j].host + o, std::min(spb_ctx::XFER_CHUNK, jobs[j].bytes - o)});
+    const int NW = c->xfer_workers;
     cudaError_t err[spb_ctx::XFER_WORKERS];
     auto work = [&](int w) {
         cudaError_t e = cudaSetDevice(c->device);
         int b = 0;
         size_t pending_chunk[2] = {(size_t)-1, (size_t)-1};   // downloads: chunk whose DMA into buffer b is in flight
-        for (size_t k = w; k < chunks.size() && e == cudaSuccess; k += spb_ctx::XFER_WORKERS, b ^= 1) {
+        for (size_t k = w; k < chunks.size() && e == cudaSuccess; k += (size_t)NW, b ^= 1) {
             const Chunk &ch = chunks[k];
             if (to_device) {
                 e = cudaEventSynchronize(c->xfer_ev[w][b]);                       // the buffer's previous DMA has finished
@@ -303,10 +309,10 @@ static int staged_copy(spb_ctx *c, const XferJob *jobs, int njobs, bool to_devic
     // back to the pool by work that is still running there
     CK(cudaStreamSynchronize(c->stream));
     std::thread th[spb_ctx::XFER_WORKERS];
-    for (int w = 1; w < spb_ctx::XFER_WORKERS; ++w) th[w] = std::thread(work, w);
+    for (int w = 1; w < NW; ++w) th[w] = std::thread(work, w);
     work(0);
-    for (int w = 1; w < spb_ctx::XFER_WORKERS; ++w) th[w].join();
-    for (int w = 0; w < spb_ctx::XFER_WORKERS; ++w)
+    for (int w = 1; w < NW; ++w) th[w].join();
+    for (int w = 0; w < NW; ++w)
         if (err[w] != cudaSuccess) return spb_fail(SPB_ERR_CUDA, "host transfer failed: %s", cudaGetErrorString(err[w]));
     return 0;
 }
@@ -376,7 +382,7 @@ int spb_ctx_destroy(spb_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->xfer_ready)
-        for (int w = 0; w < spb_ctx::XFER_WORKERS; ++w) {
+        for (int w = 0; w < ctx->xfer_workers; ++w) {
             cudaStreamDestroy(ctx->xfer_stream[w]);
             for (int b = 0; b < 2; ++b) { cudaFreeHost(ctx->xfer_buf[w][b]); cudaEventDestroy(ctx->xfer_ev[w][b]); }
         }
