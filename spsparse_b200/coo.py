@@ -79,6 +79,23 @@ class CooArray:
         return cls(ctx, h)
 
     @classmethod
+    def from_netcdf(cls, ctx, path, vname):
+        """The array stored under `vname` by ncio_spsparse (reference slib/spsparse/netcdf.hpp:86-138; classic-format files,
+        spsparse_b200/ncio.py), uploaded as unsorted COO."""
+        from . import ncio
+        shape, idx, val = ncio.read_spsparse(path, vname)
+        if any(s > 2 ** 31 for s in shape):
+            raise ValueError(f"{vname}: shape {shape} does not fit 32-bit indices")
+        return cls.from_host(ctx, shape, idx, val)
+
+    def to_netcdf(self, path, vname):
+        """Writes the array the way ncio_spsparse does (one array per file here; ncio.write_spsparse takes several)."""
+        from . import ncio
+        _, shape, _, _ = self._info()
+        idx, val = self.to_host()
+        ncio.write_spsparse(path, {vname: (tuple(shape), idx, val)})
+
+    @classmethod
     def wrap_device(cls, ctx, shape, idx_ptrs, val_ptr, n, sort_order=None):
         shape = [int(s) for s in shape]
         rank = len(shape)

@@ -87,3 +87,24 @@ def test_dense_ops_larger_and_errors(ctx, orc):
     with pytest.raises(sp.SpbError):
         sp.transpose(ctx, bad, (0, 0))
     bad.free()
+
+
+def test_netcdf_round_trip_through_the_python_mirror(ctx, tmp_path):
+    """CooArray.to_netcdf / from_netcdf (spsparse_b200/ncio.py: the layout of ncio_spsparse, netcdf.hpp:86-138): the array that
+    comes back consolidates to the same result, entry for entry."""
+    import spsparse_b200 as sp
+    rng = np.random.default_rng(12)
+    n = 5000
+    idx = [rng.integers(0, 700, n), rng.integers(0, 100000, n)]
+    val = rng.standard_normal(n)
+    A = sp.CooArray.from_host(ctx, (700, 100000), idx, val)
+    p = str(tmp_path / "a.nc")
+    A.to_netcdf(p, "A")
+    B = sp.CooArray.from_netcdf(ctx, p, "A")
+    (bi, bv) = B.to_host()
+    assert np.array_equal(bi[0], idx[0]) and np.array_equal(bi[1], idx[1]) and np.array_equal(bv, val)
+    Ra, Rb = sp.consolidate(ctx, A, sp.ROW_MAJOR), sp.consolidate(ctx, B, sp.ROW_MAJOR)
+    (ia, va), (ib, vb) = Ra.to_host(), Rb.to_host()
+    assert all(np.array_equal(x, y) for x, y in zip(ia, ib)) and np.array_equal(va, vb)
+    for x in (A, B, Ra, Rb):
+        x.free()

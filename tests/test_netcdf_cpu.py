@@ -97,6 +97,56 @@ def test_reader_takes_a_file_assembled_from_the_grammar(exe, tmp_path):
     assert "var v.indices int64 v.size v.rank\nvalues 8 0 3\n" in out and "var v.vals double v.size\nvalues 1.5 -2 1.0000000000000001e+300\n" in out, out
 
 
+# ---- the Python mirror's reader / writer (spsparse_b200/ncio.py): the same files ---------------------------------------------------
+def test_python_mirror_writes_the_same_bytes_and_reads_the_cpp_files(exe, tmp_path):
+    from spsparse_b200 import ncio
+    idx = [np.array([r for r, _ in FIXED_IDX]), np.array([c for _, c in FIXED_IDX])]
+    p_py, p_cpp = tmp_path / "py.nc", tmp_path / "cpp.nc"
+    ncio.write_spsparse(str(p_py), {"arr1": ((5, 6), idx, FIXED_VAL)})
+    run(exe, "write", str(p_cpp))
+    assert p_py.read_bytes() == p_cpp.read_bytes() == cdf5_spsparse("arr1", (5, 6), FIXED_IDX, FIXED_VAL)
+    shape, ridx, rval = ncio.read_spsparse(str(p_cpp), "arr1")
+    assert shape == (5, 6) and [x.tolist() for x in ridx] == [x.tolist() for x in idx] and rval.tolist() == FIXED_VAL
+    # two arrays of different rank in one file, through the C++ reader
+    rng = np.random.default_rng(3)
+    n = 1000
+    big = ((7000, 9000), [rng.integers(0, 7000, n), rng.integers(0, 9000, n)], rng.standard_normal(n))
+    vec = ((50,), [rng.integers(0, 50, 7)], rng.standard_normal(7))
+    p2 = tmp_path / "two.nc"
+    ncio.write_spsparse(str(p2), {"M": big, "v": vec})
+    for name, (shp, ix, vv) in (("M", big), ("v", vec)):
+        s2, i2, v2 = ncio.read_spsparse(str(p2), name)
+        assert s2 == shp and all(np.array_equal(a, b) for a, b in zip(i2, ix)) and np.array_equal(v2, vv)
+    out = run(exe, "dump", str(p2))
+    assert "var M.indices int64 M.size M.rank" in out and "var v.vals double v.size" in out
+    assert "values " + " ".join(repr(float(x)) if False else f"{x:.17g}" for x in vec[2]) in out
+    with pytest.raises(KeyError):
+        ncio.read_spsparse(str(p2), "nope")
+    bad = tmp_path / "bad.nc"
+    bad.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(ValueError, match="HDF5"):
+        ncio.read_spsparse(str(bad), "M")
+
+
+def test_python_mirror_reads_classic_files_from_scipy(tmp_path):
+    """CDF-1 / CDF-2 files with the same variable names (int32 indices: the classic types), written by scipy."""
+    from scipy.io import netcdf_file
+    from spsparse_b200 import ncio
+    for version in (1, 2):
+        p = tmp_path / f"classic{version}.nc"
+        with netcdf_file(str(p), "w", version=version) as f:
+            f.createDimension("A.size", 4)
+            f.createDimension("A.rank", 2)
+            info = f.createVariable("A.info", "i4", ())
+            info.shape_ = 0   # (scipy reserves the attribute name "shape"; written below through _attributes)
+            info._attributes.clear()
+            info._attributes["shape"] = np.array([10, 20], dtype=np.int32)
+            ind = f.createVariable("A.indices", "i4", ("A.size", "A.rank")); ind[:] = np.array([[1, 2], [3, 4], [9, 19], [0, 0]], dtype=np.int32)
+            vals = f.createVariable("A.vals", "f8", ("A.size",)); vals[:] = np.array([1.5, -2.0, 3.25, 0.0])
+        shape, idx, val = ncio.read_spsparse(str(p), "A")
+        assert shape == (10, 20) and idx[0].tolist() == [1, 3, 9, 0] and idx[1].tolist() == [2, 4, 19, 0] and val.tolist() == [1.5, -2.0, 3.25, 0.0]
+
+
 # ---- (3) against scipy's netCDF-3 implementation ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("fmt,version", [("classic", 1), ("classic64", 2)])
 def test_scipy_reads_what_the_writer_wrote(exe, tmp_path, fmt, version):
